@@ -1,0 +1,177 @@
+/* spr_b200.h -- C ABI of libspr_b200.so, the sm_100a implementation of the Superpoints_Registration
+ * hot path (KPConv preprocessing, KPConv layer, superpoint matching, pose solve).
+ *
+ * Conventions
+ *   - every pointer prefixed d_ is a DEVICE pointer; the caller (PyTorch in the shipped host code)
+ *     owns every buffer, including workspaces: the library never allocates or frees device memory
+ *     and keeps no state between calls;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - every call returns 0 on success, a negative SPR_E* code on failure; spr_last_error() gives the
+ *     message of the last failure on the calling thread.  The reference's extensions raise
+ *     RuntimeError in the same situations (cpp_neighbors/wrapper.cpp:77,95,133,203;
+ *     cpp_subsampling/wrapper.cpp:266-270) and the Python host layer does the same;
+ *   - stacked-cloud layout as in the reference: points of all clouds concatenated [N,3] fp32 row-major,
+ *     plus per-cloud lengths int32 [B] (kpconv.py:322-323);
+ *   - neighbour matrices are row-major [Nq, row_stride] with the shadow value Ns_total marking padding
+ *     (neighbors.cpp:321-327), element type int64 (the reference's collate dict dtype, kpconv.py:396-398)
+ *     or int32, selected by idx_is_64.
+ *
+ * Paths are relative to /root/reference/src/.
+ */
+#ifndef SPR_B200_H_
+#define SPR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SPR_API __attribute__((visibility("default")))
+#else
+#define SPR_API
+#endif
+
+#define SPR_OK 0
+#define SPR_EINVAL (-1)  /* bad argument (empty input, limit out of range, ...) */
+#define SPR_ECUDA (-2)   /* a CUDA runtime call or launch failed */
+#define SPR_ENOSPACE (-3) /* caller-provided workspace too small */
+#define SPR_EUNSUPPORTED (-4)
+
+#define SPR_MAX_NEIGHBOR_LIMIT 128
+
+SPR_API int spr_version(void);
+SPR_API const char* spr_last_error(void);
+/* Number of kernels this library has launched from the calling process (all threads); bench.py reports
+ * the delta over the timed region as gpu_launches. */
+SPR_API unsigned long long spr_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Grid (voxel) subsampling.
+ * Replaces grid_subsampling.subsample_batch(points, batches, sampleDl=..., max_p=0)
+ *   models/backbone_kpconv/cpp_wrappers/cpp_subsampling/wrapper.cpp:62-333
+ *   -> batch_grid_subsampling  cpp_subsampling/grid_subsampling/grid_subsampling.cpp:109-211
+ * (the features/classes variants are not on the path: kpconv.py:370 passes points only).
+ * Barycentres are bit-identical to the reference's (sequential fp32 sum in input order times
+ * (float)(1.0/count)); they are emitted per cloud in FIRST-OCCURRENCE order (voxels ordered by their
+ * lowest member index) instead of the reference's std::unordered_map iteration order.
+ *
+ *   d_points [n_points,3] f32, d_lengths [n_clouds] i32
+ *   d_out_points: room for n_points*3 f32; d_out_lengths [n_clouds] i32; d_out_total [1] i32
+ * The caller reads d_out_total / d_out_lengths back to learn M.
+ * ------------------------------------------------------------------------------------------- */
+SPR_API size_t spr_grid_subsample_workspace_bytes(int n_points, int n_clouds);
+SPR_API int spr_grid_subsample_batch(const float* d_points, const int32_t* d_lengths, int n_points, int n_clouds,
+                             float sample_dl, float* d_out_points, int32_t* d_out_lengths, int32_t* d_out_total,
+                             void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched fixed-radius neighbour search.
+ * Replaces radius_neighbors.batch_query(queries, supports, q_batches, s_batches, radius=...)
+ *   models/backbone_kpconv/cpp_wrappers/cpp_neighbors/wrapper.cpp:58-238
+ *   -> batch_nanoflann_neighbors  cpp_neighbors/neighbors/neighbors.cpp:211-332
+ * fused with the truncation the Python caller applies (kpconv.py:259-260, [:, :max_neighbors]).
+ * Row i holds the supports of query i's cloud with fp32 d2 < radius^2, nearest first (ties by lower
+ * index), at most `limit` of them, then the shadow value n_supports.  *d_out_max_count receives the
+ * un-truncated batch-wide maximum in-radius count, i.e. the width the reference matrix had before
+ * truncation (neighbors.cpp:296-297); min(max_count, limit) leading columns are the reference's output.
+ *
+ * Two-step form so that one cell grid over the supports serves several query sets (the conv and the
+ * pool searches of a level share supports and radius, kpconv.py:353,380):
+ *   spr_cell_grid_build   bins the supports of every cloud into a uniform grid with cell >= radius
+ *   spr_radius_query      answers queries against a built grid
+ * ------------------------------------------------------------------------------------------- */
+SPR_API size_t spr_cell_grid_workspace_bytes(int n_supports, int n_clouds);
+SPR_API int spr_cell_grid_build(const float* d_supports, const int32_t* d_s_lengths, int n_supports, int n_clouds, float radius,
+                        void* d_grid_workspace, size_t workspace_bytes, void* stream);
+SPR_API int spr_radius_query(const float* d_queries, const int32_t* d_q_lengths, int n_queries, int n_clouds,
+                     const void* d_grid_workspace, int n_supports, float radius, int limit, void* d_out_idx,
+                     int idx_is_64, int row_stride, int32_t* d_out_max_count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * KPConv layer forward (rigid kernel, linear influence, sum aggregation -- the only mode any shipped
+ * config uses: conf/qk_regtr_full_*.yaml KP_influence: linear, aggregation_mode: sum).
+ * Replaces KPConv.forward(q_pts, s_pts, neighb_inds, x)  models/backbone_kpconv/kpconv_blocks.py:269-414
+ *   out[n,:] = ( sum_k ( sum_h max(0, 1 - |s[idx[n,h]] - q[n] - kp[k]| / extent) * x[idx[n,h],:] ) @ W[k] )
+ *              / max(1, #{h : rowsum(x)[idx[n,h]] > 0})
+ * One fused kernel: neighbour-feature gather -> kernel-point influence -> (K*Cin)xCout contraction.
+ *   d_q [nq,3], d_s [ns,3], d_idx [nq,row_stride] (first H columns used; value ns = shadow),
+ *   d_x [ns,cin], d_w [K,cin,cout], d_kp [K,3], d_out [nq,cout]; all fp32 row-major.
+ *   mode: 0 = fp32 CUDA-core contraction (parity anchor); 1 = tcgen05 tensor-core contraction with
+ *         split-precision operands (when built in; SPR_EUNSUPPORTED otherwise).
+ * ------------------------------------------------------------------------------------------- */
+SPR_API size_t spr_kpconv_workspace_bytes(int nq, int ns, int cin, int cout, int n_kernel_points);
+SPR_API int spr_kpconv_forward(const float* d_q, const float* d_s, const void* d_idx, int idx_is_64, int row_stride, int H,
+                       const float* d_x, int cin, const float* d_w, int cout, const float* d_kp, int n_kernel_points,
+                       float extent, float* d_out, int nq, int ns, int mode, void* d_workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* Per-cloud instance normalisation + LeakyReLU (+ optional residual add before the activation).
+ * Replaces BatchNormBlock.forward with nn.InstanceNorm1d (kpconv_blocks.py:474-530: per cloud, per
+ * channel, biased variance, eps, no affine, no running stats) followed by nn.LeakyReLU
+ * (kpconv_blocks.py:556-561,645,727,741).
+ *   y = lrelu( (x - mean_b,c) / sqrt(var_b,c + eps) [+ residual] ),  slope = 1 disables the activation,
+ *   d_residual may be NULL.  d_x may alias d_out.  Deterministic: fp64 partial sums over fixed row chunks. */
+SPR_API size_t spr_instance_norm_workspace_bytes(int n_rows, int n_clouds, int c);
+SPR_API int spr_instance_norm_lrelu(const float* d_x, const int32_t* d_lengths, int n, int n_clouds, int c, float eps,
+                            float slope, const float* d_residual, float* d_out, void* d_workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* max_pool(x, inds)  kpconv_blocks.py:127-143: out[n,c] = max_h xpad[idx[n,h],c] where xpad has a zero
+ * row appended for the shadow index. */
+SPR_API int spr_max_pool(const float* d_x, const void* d_idx, int idx_is_64, int row_stride, int H, int nq, int ns, int c,
+                 float* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Superpoint matching.  Replaces the per-pair body of RegTR.softmax_correlation
+ *   models/qk_regtr_full.py:445-576 : corr = S T^T / sqrt(D); attn = softmax(corr, dim=-2) * softmax(corr, dim=-1);
+ *   N > M : val,ind = max(attn, dim=1) (one source per target), else val,ind = max(attn, dim=2).
+ * Batched over pairs with packed features: d_src [sum N_p, D], d_tgt [sum M_p, D], offsets [P+1] i32.
+ *   d_corr: caller-provided scratch/result, packed per pair, pair p at d_corr_offsets[p] (i64), N_p*M_p f32.
+ *   d_val / d_ind: packed per pair; pair p writes M_p entries if N_p > M_p, else N_p entries, starting at
+ *   d_out_offsets[p] (i32 [P+1]).  max_n / max_m: largest N_p / M_p of the batch (grid sizing).
+ *   d_attn (optional, may be NULL): same layout as d_corr, receives the dual-softmax matrix
+ *   (the reference returns it as outputs['attn'], qk_regtr_full.py:295).
+ * ------------------------------------------------------------------------------------------- */
+SPR_API size_t spr_match_workspace_bytes(int total_src, int total_tgt, int n_pairs);
+SPR_API int spr_dual_softmax_match(const float* d_src, const float* d_tgt, const int32_t* d_src_offsets,
+                           const int32_t* d_tgt_offsets, const int64_t* d_corr_offsets, const int32_t* d_out_offsets,
+                           int n_pairs, int total_src, int total_tgt, int D, int max_n, int max_m, float* d_corr,
+                           float* d_attn, float* d_val, int64_t* d_ind, void* d_workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* Sinkhorn soft assignment + weighted targets for the 3DMatch configuration.
+ * Replaces qk_regtr_full.py:532-536 (affinity from the correlation) + utils/se3_torch.py:166-202 (sinkhorn with
+ * slack) + :204-231 (perm = exp(log_alpha), weighted_t = perm @ tgt / (rowsum + 1e-6), weights = rowsum):
+ *   score = clamp(corr, 0); aff = -(score - softplus(alpha)) / (exp(beta) + 0.02)
+ * d_corr as produced by spr_dual_softmax_match.  Outputs packed per source point:
+ *   d_weighted_tgt [total_src,3], d_weights [total_src]. */
+SPR_API size_t spr_sinkhorn_workspace_bytes(int total_src, int total_tgt, int n_pairs);
+SPR_API int spr_sinkhorn_weighted_targets(const float* d_corr, const int64_t* d_corr_offsets, const int32_t* d_src_offsets,
+                                  const int32_t* d_tgt_offsets, int n_pairs, int total_src, int total_tgt, int max_n,
+                                  int max_m, const float* d_tgt_xyz, float softplus_alpha, float exp_beta, int n_iters, int slack,
+                                  float* d_weighted_tgt, float* d_weights, void* d_workspace, size_t workspace_bytes,
+                                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched weighted Procrustes (Kabsch).  Replaces compute_rigid_transform(a, b, weights)
+ *   utils/se3_torch.py:109-163 : w~ = w / max(sum w, 1e-6); weighted centroids; cov = (a-ca)^T ((b-cb) * w~);
+ *   U,S,V = svd(cov); R = V U^T, third column of V negated when det(R) <= 0; t = -R ca + cb; out = [R | t].
+ * Packed correspondences: d_a, d_b [total,3], d_w [total] (NULL = uniform weights, the `weights is None`
+ * branch :145-150), pair p owns rows offsets[p]..offsets[p+1].  d_out [n_pairs,12] row-major 3x4.
+ * Moments are accumulated in fp64 and the 3x3 SVD is a one-sided Jacobi in fp64, one warp per pair.
+ * ------------------------------------------------------------------------------------------- */
+SPR_API int spr_weighted_procrustes(const float* d_a, const float* d_b, const float* d_w, const int32_t* d_offsets, int n_pairs,
+                            float* d_out, void* stream);
+
+/* Gather rows: out[i,:] = src[base_offset(pair of i) + ind[i], :]  (the torch.gather at qk_regtr_full.py:478,589
+ * that turns argmax indices into corresponding points). */
+SPR_API int spr_gather_rows3(const float* d_src, const int64_t* d_ind, const int32_t* d_row_pair_base, int n_rows, float* d_out,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPR_B200_H_ */

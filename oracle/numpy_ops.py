@@ -1,0 +1,138 @@
+"""oracle/numpy_ops.py -- NumPy restatement of the floating-point stages of the hot path.  TEST INFRASTRUCTURE ONLY.
+
+Each function cites the reference lines it follows (paths relative to /root/reference/src).  Parity status:
+pinned by tests/test_oracle_golden.py against vectors produced by the imported reference
+(tests/golden/make_golden.py).  dtype=np.float32 reproduces the reference's working precision;
+dtype=np.float64 gives the exact-arithmetic value used to put fp32 differences into perspective.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+
+def _lse(x: np.ndarray, axis: int) -> np.ndarray:
+    m = x.max(axis=axis, keepdims=True)
+    return m + np.log(np.exp(x - m).sum(axis=axis, keepdims=True, dtype=x.dtype))
+
+
+def _softmax(x: np.ndarray, axis: int) -> np.ndarray:
+    e = np.exp(x - x.max(axis=axis, keepdims=True))
+    return e / e.sum(axis=axis, keepdims=True, dtype=x.dtype)
+
+
+def instance_norm_lrelu(x, lengths, eps=1e-5, slope=1.0, residual=None):
+    """models/backbone_kpconv/kpconv_blocks.py:510-519 (per-cloud nn.InstanceNorm1d: biased variance, eps inside
+    the sqrt, no affine) followed by the LeakyReLU of :556-561 / the residual sum + LeakyReLU of :741."""
+    x = np.asarray(x, np.float32)
+    out = np.empty_like(x)
+    o = 0
+    for n in np.asarray(lengths).tolist():
+        seg = x[o:o + n].astype(np.float64)
+        mean = seg.mean(0)
+        var = seg.var(0)
+        out[o:o + n] = ((seg - mean) / np.sqrt(var + eps)).astype(np.float32)
+        o += n
+    if residual is not None:
+        out = out + np.asarray(residual, np.float32)
+    return np.where(out >= 0, out, out * np.float32(slope)).astype(np.float32)
+
+
+def max_pool(x, inds):
+    """kpconv_blocks.py:127-143: a zero row is appended for the shadow index, then max over the neighbourhood."""
+    x = np.asarray(x, np.float32)
+    xp = np.concatenate([x, np.zeros_like(x[:1])], 0)
+    return xp[np.asarray(inds)].max(1)
+
+
+def kpconv_forward_numpy(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent, dtype=np.float64):
+    """kpconv_blocks.py:305-414 (non-deformable) written with dense arrays, for SMALL inputs (it materialises
+    [N,H,K] like the reference does).  The C version (spr_oracle.c:orc_kpconv_forward) is the fast one."""
+    q, s = np.asarray(q_pts, np.float32), np.asarray(s_pts, np.float32)
+    idx = np.asarray(neighb_inds)
+    sp = np.concatenate([s, np.full((1, 3), 1e6, np.float32)], 0)                  # :309
+    nb = sp[idx] - q[:, None, :]                                                   # :312-315
+    diff = nb[:, :, None, :] - np.asarray(kernel_points, np.float32)[None, None]   # :324-325
+    sq = (diff.astype(np.float32) ** 2).sum(-1, dtype=np.float32)                  # :328
+    w = np.clip(1 - np.sqrt(sq) / np.float32(extent), 0, None).astype(np.float32)  # :368
+    w = w.transpose(0, 2, 1).astype(dtype)                                         # [N,K,H]
+    xp = np.concatenate([np.asarray(x, np.float32), np.zeros((1, np.shape(x)[1]), np.float32)], 0)  # :388
+    nx = xp[idx]                                                                   # :391
+    wf = w @ nx.astype(dtype)                                                      # :394  [N,K,Cin]
+    out = np.einsum('nkc,kco->no', wf, np.asarray(weights).astype(dtype))          # :401-406
+    nn = (nx.sum(-1, dtype=np.float32) > 0).sum(-1)                                # :409-410
+    nn = np.maximum(nn, 1)                                                         # :411
+    return (out / nn[:, None]).astype(np.float32)
+
+
+def dual_softmax_match(src_feat, tgt_feat, dtype=np.float32):
+    """models/qk_regtr_full.py:453-468 / :565-576 for one pair.
+    -> corr (N,M), attn (N,M), val, ind  (per target if N > M else per source)."""
+    S, T = np.asarray(src_feat, dtype), np.asarray(tgt_feat, dtype)
+    N, D = S.shape
+    M = T.shape[0]
+    corr = (S @ T.T) / dtype(D ** 0.5)                          # :453
+    attn = _softmax(corr, axis=0) * _softmax(corr, axis=1)      # :457-459 (dim=-2 is axis 0, dim=-1 is axis 1)
+    if N > M:
+        ind = attn.argmax(axis=0)                               # :468 max over dim=1 of (1,N,M)
+        val = attn.max(axis=0)
+    else:
+        ind = attn.argmax(axis=1)                               # :576
+        val = attn.max(axis=1)
+    return corr, attn, val, ind.astype(np.int64)
+
+
+def sinkhorn_log(log_alpha, n_iters: int):
+    """utils/se3_torch.py:166-202 for one (J,K) matrix: zero-pad a slack row and column, then alternately
+    normalise rows (all but the slack row) and columns (all but the slack column) in log space."""
+    la = np.pad(log_alpha, ((0, 1), (0, 1)))                                        # :182-184
+    for _ in range(n_iters):
+        la = np.concatenate([la[:-1, :] - _lse(la[:-1, :], axis=1), la[-1:, :]], 0)  # :188-192
+        la = np.concatenate([la[:, :-1] - _lse(la[:, :-1], axis=0), la[:, -1:]], 1)  # :194-198
+    return la[:-1, :-1]                                                              # :201
+
+
+def sinkhorn_weighted_targets(corr, tgt_xyz, softplus_alpha, exp_beta, n_iters, dtype=np.float32):
+    """qk_regtr_full.py:641-647 (score = clamp(corr, 0); affinity) + se3_torch.py:209-231
+    (perm = exp(sinkhorn); weighted_t = perm @ tgt / (rowsum + 1e-6); weights = rowsum)."""
+    c = np.asarray(corr, dtype)
+    score = np.clip(c, 0, None)
+    aff = -(score - dtype(softplus_alpha)) / (dtype(exp_beta) + dtype(0.02))
+    perm = np.exp(sinkhorn_log(aff, n_iters))
+    rows = perm.sum(1, keepdims=True, dtype=dtype)
+    wt = perm @ np.asarray(tgt_xyz, dtype) / (rows + dtype(1e-6))
+    return wt, rows[:, 0]
+
+
+def compute_rigid_transform(a, b, weights=None, dtype=np.float32):
+    """utils/se3_torch.py:109-163 for one pair."""
+    a, b = np.asarray(a, dtype), np.asarray(b, dtype)
+    if weights is not None:
+        w = np.asarray(weights, dtype)
+        wn = (w / np.maximum(w.sum(dtype=dtype), dtype(1e-6)))[:, None]      # :137-138
+        ca = (a * wn).sum(0, dtype=dtype)                                    # :139-140
+        cb = (b * wn).sum(0, dtype=dtype)
+        cov = (a - ca).T @ ((b - cb) * wn)                                   # :141-143
+    else:
+        ca, cb = a.mean(0, dtype=dtype), b.mean(0, dtype=dtype)              # :145-150
+        cov = (a - ca).T @ (b - cb)
+    u, s, vt = np.linalg.svd(cov)                                            # :152
+    v = vt.T
+    rot = v @ u.T                                                            # :153
+    if not np.linalg.det(rot) > 0:                                           # :154-158
+        v2 = v.copy()
+        v2[:, 2] *= -1
+        rot = v2 @ u.T
+    t = -rot @ ca + cb                                                       # :161
+    return np.concatenate([rot, t[:, None]], 1).astype(np.float32)
+
+
+def pose_error(pred, gt) -> Tuple[float, float]:
+    """Chordal rotation error (deg) and translation error in fp64 -- see SURVEY.md row a13 for why this is used
+    instead of the reference's se3_compare."""
+    p, g = np.asarray(pred, np.float64), np.asarray(gt, np.float64)
+    fro = np.linalg.norm(p[..., :3, :3] - g[..., :3, :3], axis=(-2, -1))
+    rot = 2 * np.degrees(np.arcsin(np.clip(fro / (2 * np.sqrt(2)), 0, 1)))
+    tr = np.linalg.norm(p[..., :3, 3] - g[..., :3, 3], axis=-1)
+    return rot, tr

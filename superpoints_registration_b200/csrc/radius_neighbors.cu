@@ -1,0 +1,451 @@
+// radius_neighbors.cu -- batched fixed-radius neighbour search on sm_100a (uniform cell list).
+//
+// Replaces batch_nanoflann_neighbors (reference: models/backbone_kpconv/cpp_wrappers/cpp_neighbors/neighbors/
+// neighbors.cpp:211-332) plus the [:, :max_neighbors] truncation of kpconv.py:259-260.
+//
+// Build (spr_cell_grid_build): per-cloud bounding box of the supports -> per-cloud uniform grid with
+// cell edge c >= radius*(1+1/256) (doubled until the cloud's cells fit its share of the cell table) ->
+// counting sort of the supports by (cloud, z, y, x) cell: histogram, exclusive scan, scatter.  Sorted
+// supports are stored as float4 (x, y, z, original global index) so a candidate costs one 16-byte load.
+//
+// Query (spr_radius_query): ONE WARP PER QUERY.  The 27 neighbouring cells are 9 contiguous runs in the
+// sorted array (the 3 x-adjacent cells of a (z,y) row are adjacent in memory); 9 lanes fetch the run
+// bounds, the warp then streams the concatenated runs 32 candidates at a time (coalesced float4 loads),
+// tests d2 < r2 with the reference's exact fp32 rounding sequence, and stages the hits in shared memory.
+// The row is finished by ranking the staged hits by (d2, index) -- the reference sorts by distance
+// (nanoflann.hpp:1286-1287) and Python keeps the first `limit` -- and writing hit e to column rank(e).
+// If more than kStage hits accumulate, the stage is compacted to the best `limit` and a (d2, index)
+// admission threshold is kept, so arbitrarily dense neighbourhoods are handled in bounded memory.
+#include "spr_common.cuh"
+
+namespace spr {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarpsPerBlock = 8;
+constexpr int kStage = 320;  // staged hits per warp (>= 2*SPR_MAX_NEIGHBOR_LIMIT + 32)
+constexpr int kMaxDim = 1024;
+
+struct CellGrid {  // per cloud
+  float lox, loy, loz, cell;
+  int dx, dy, dz;
+  int base;  // first cell of this cloud in the global cell table
+};
+
+// Workspace header (device): lives at the start of the grid workspace.
+struct GridHeader {
+  int total_cells;
+  int pad[3];
+};
+
+__global__ void k_bbox_init(uint32_t* __restrict__ bb, int B) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * 3) {
+    bb[i] = 0xffffffffu;
+    bb[B * 3 + i] = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_bbox(const float* __restrict__ pts, const int* __restrict__ offs, int B,
+                                                   int n, uint32_t* __restrict__ bb) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  int b = valid ? find_cloud(offs, B, i) : -1;
+  float x = 0, y = 0, z = 0;
+  if (valid) {
+    x = pts[3 * (size_t)i];
+    y = pts[3 * (size_t)i + 1];
+    z = pts[3 * (size_t)i + 2];
+  }
+  const int b0 = __shfl_sync(kFull, b, 0);
+  const bool uniform = __all_sync(kFull, b == b0) && b0 >= 0;
+  if (uniform) {
+    uint32_t mnx = f2ord(x), mny = f2ord(y), mnz = f2ord(z), mxx = mnx, mxy = mny, mxz = mnz;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mnx = min(mnx, __shfl_xor_sync(kFull, mnx, o));
+      mny = min(mny, __shfl_xor_sync(kFull, mny, o));
+      mnz = min(mnz, __shfl_xor_sync(kFull, mnz, o));
+      mxx = max(mxx, __shfl_xor_sync(kFull, mxx, o));
+      mxy = max(mxy, __shfl_xor_sync(kFull, mxy, o));
+      mxz = max(mxz, __shfl_xor_sync(kFull, mxz, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(bb + 3 * b0 + 0, mnx);
+      atomicMin(bb + 3 * b0 + 1, mny);
+      atomicMin(bb + 3 * b0 + 2, mnz);
+      atomicMax(bb + 3 * (B + b0) + 0, mxx);
+      atomicMax(bb + 3 * (B + b0) + 1, mxy);
+      atomicMax(bb + 3 * (B + b0) + 2, mxz);
+    }
+  } else if (valid) {
+    atomicMin(bb + 3 * b + 0, f2ord(x));
+    atomicMin(bb + 3 * b + 1, f2ord(y));
+    atomicMin(bb + 3 * b + 2, f2ord(z));
+    atomicMax(bb + 3 * (B + b) + 0, f2ord(x));
+    atomicMax(bb + 3 * (B + b) + 1, f2ord(y));
+    atomicMax(bb + 3 * (B + b) + 2, f2ord(z));
+  }
+}
+
+// Cells a cloud of ns points may use.  Must match between workspace sizing and planning.
+__host__ __device__ inline long long cell_budget(int ns) { return 16ll * ns + 512ll; }
+
+// One thread per cloud chooses the cell edge; a serial prefix over clouds assigns table bases.
+__global__ void k_plan_grids(const uint32_t* __restrict__ bb, const int* __restrict__ offs, int B, float radius,
+                             CellGrid* __restrict__ grids, GridHeader* __restrict__ hdr) {
+  __shared__ int s_cells[1024];
+  __shared__ int s_total;
+  int carry = 0;
+  for (int base = 0; base < B; base += blockDim.x) {
+    const int b = base + threadIdx.x;
+    int cells = 0;
+    CellGrid g;
+    if (b < B) {
+      const int ns = offs[b + 1] - offs[b];
+      float lo[3], hi[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        lo[a] = ns > 0 ? ord2f(bb[3 * b + a]) : 0.f;
+        hi[a] = ns > 0 ? ord2f(bb[3 * (B + b) + a]) : 0.f;
+      }
+      // margin: a pair accepted by the fp32 test d2 < r2 can never sit two cells apart
+      float cell = radius * 1.00390625f;
+      int d[3];
+      const long long budget = cell_budget(ns);
+      for (int it = 0; it < 64; ++it) {
+        bool ok = true;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          double v = floor(((double)hi[a] - (double)lo[a]) / (double)cell) + 1.0;
+          if (!(v <= (double)kMaxDim)) ok = false;
+          d[a] = v < 1.0 ? 1 : (v > (double)kMaxDim ? kMaxDim : (int)v);
+        }
+        if (ok && (long long)d[0] * d[1] * d[2] <= budget) break;
+        cell *= 2.f;
+      }
+      g.lox = lo[0];
+      g.loy = lo[1];
+      g.loz = lo[2];
+      g.cell = cell;
+      g.dx = d[0];
+      g.dy = d[1];
+      g.dz = d[2];
+      cells = d[0] * d[1] * d[2];
+    }
+    s_cells[threadIdx.x] = cells;
+    __syncthreads();
+    if (threadIdx.x == 0) {  // B is small (2 x pairs): a serial prefix is fine
+      int run = carry;
+      for (int t = 0; t < blockDim.x && base + t < B; ++t) {
+        int c = s_cells[t];
+        s_cells[t] = run;
+        run += c;
+      }
+      s_total = run;
+    }
+    __syncthreads();
+    if (b < B) {
+      g.base = s_cells[threadIdx.x];
+      grids[b] = g;
+    }
+    carry = s_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) hdr->total_cells = carry;
+}
+
+__device__ __forceinline__ int cell_coord(float p, float lo, float cell, int dim) {
+  // fp32, same expression at build and query time
+  float u = floorf(__fdiv_rn(__fsub_rn(p, lo), cell));
+  u = fminf(fmaxf(u, -2.f), (float)dim + 1.f);
+  return (int)u;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_cell_count(const float* __restrict__ s, const int* __restrict__ offs, int B, int n,
+                 const CellGrid* __restrict__ grids, int* __restrict__ cell_cnt, int* __restrict__ point_cell) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = find_cloud(offs, B, i);
+  const CellGrid g = grids[b];
+  int cx = min(max(cell_coord(s[3 * (size_t)i + 0], g.lox, g.cell, g.dx), 0), g.dx - 1);
+  int cy = min(max(cell_coord(s[3 * (size_t)i + 1], g.loy, g.cell, g.dy), 0), g.dy - 1);
+  int cz = min(max(cell_coord(s[3 * (size_t)i + 2], g.loz, g.cell, g.dz), 0), g.dz - 1);
+  const int c = g.base + (cz * g.dy + cy) * g.dx + cx;
+  point_cell[i] = c;
+  atomicAdd(cell_cnt + c, 1);
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_cell_scatter(const float* __restrict__ s, int n, const int* __restrict__ point_cell,
+                   const int* __restrict__ cell_start, int* __restrict__ cell_fill, float4* __restrict__ sorted) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = point_cell[i];
+  const int pos = cell_start[c] + atomicAdd(cell_fill + c, 1);
+  sorted[pos] = make_float4(s[3 * (size_t)i], s[3 * (size_t)i + 1], s[3 * (size_t)i + 2], __int_as_float(i));
+}
+
+// (d2, idx) lexicographic "a before b"
+__device__ __forceinline__ bool before(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+
+// Keep the `limit` best staged hits (by (d2, idx)), packed at the front in rank order.
+__device__ __forceinline__ int compact_stage(float* __restrict__ sd, int* __restrict__ si, int cnt, int limit,
+                                             int lane) {
+  // ranks are computed against the un-modified stage, then written to a register-held list
+  float kd[(kStage + 31) / 32];
+  int ki[(kStage + 31) / 32], kr[(kStage + 31) / 32];
+#pragma unroll
+  for (int t = 0; t < (kStage + 31) / 32; ++t) {
+    const int e = t * 32 + lane;
+    kr[t] = 0x7fffffff;
+    if (e < cnt) {
+      const float d = sd[e];
+      const int id = si[e];
+      int r = 0;
+      for (int f = 0; f < cnt; ++f) r += before(sd[f], si[f], d, id) ? 1 : 0;
+      kd[t] = d;
+      ki[t] = id;
+      kr[t] = r;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < (kStage + 31) / 32; ++t) {
+    if (kr[t] < limit) {
+      sd[kr[t]] = kd[t];
+      si[kr[t]] = ki[t];
+    }
+  }
+  __syncwarp();
+  return min(cnt, limit);
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(kThreads)
+    k_radius_query(const float* __restrict__ q, const int* __restrict__ q_offs, int B, int nq,
+                   const CellGrid* __restrict__ grids, const int* __restrict__ cell_start,
+                   const float4* __restrict__ sorted, int ns_total, float r2, int limit, IdxT* __restrict__ out,
+                   int row_stride, int* __restrict__ max_count) {
+  __shared__ float s_d[kWarpsPerBlock][kStage];
+  __shared__ int s_i[kWarpsPerBlock][kStage];
+  __shared__ int s_beg[kWarpsPerBlock][9];
+  __shared__ int s_pre[kWarpsPerBlock][10];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sd = s_d[warp];
+  int* si = s_i[warp];
+  int block_max = 0;
+
+  for (int qi = blockIdx.x * kWarpsPerBlock + warp; qi < nq; qi += gridDim.x * kWarpsPerBlock) {
+    const int b = find_cloud(q_offs, B, qi);
+    const CellGrid g = grids[b];
+    const float px = __ldg(q + 3 * (size_t)qi), py = __ldg(q + 3 * (size_t)qi + 1), pz = __ldg(q + 3 * (size_t)qi + 2);
+    const int cx = cell_coord(px, g.lox, g.cell, g.dx);
+    const int cy = cell_coord(py, g.loy, g.cell, g.dy);
+    const int cz = cell_coord(pz, g.loz, g.cell, g.dz);
+
+    // 9 runs: lane r -> (dz, dy) = (r/3-1, r%3-1)
+    int beg = 0, len = 0;
+    if (lane < 9) {
+      const int z = cz + lane / 3 - 1, y = cy + lane % 3 - 1;
+      const int xlo = max(cx - 1, 0), xhi = min(cx + 1, g.dx - 1);
+      if (z >= 0 && z < g.dz && y >= 0 && y < g.dy && xlo <= xhi) {
+        const int row = g.base + (z * g.dy + y) * g.dx;
+        beg = __ldg(cell_start + row + xlo);
+        len = __ldg(cell_start + row + xhi + 1) - beg;
+      }
+    }
+    int inc = len;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      int t = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane < 9) {
+      s_beg[warp][lane] = beg;
+      s_pre[warp][lane + 1] = inc;
+    }
+    if (lane == 0) s_pre[warp][0] = 0;
+    __syncwarp();
+    const int total = s_pre[warp][9];
+
+    int cnt = 0;         // staged hits
+    int in_radius = 0;   // all hits (for max_count)
+    bool have_thr = false;
+    float thr_d = 0.f;
+    int thr_i = 0;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int t = t0 + lane;
+      bool hit = false;
+      float d2 = 0.f;
+      int id = 0;
+      if (t < total) {
+        int r = 0;
+#pragma unroll
+        for (int k = 1; k < 9; ++k) r += (t >= s_pre[warp][k]) ? 1 : 0;
+        const float4 c = __ldg(sorted + s_beg[warp][r] + (t - s_pre[warp][r]));
+        d2 = sqdist_exact(px, py, pz, c.x, c.y, c.z);
+        id = __float_as_int(c.w);
+        hit = d2 < r2;
+      }
+      const unsigned hm = __ballot_sync(kFull, hit);
+      in_radius += __popc(hm);
+      const bool admit = hit && (!have_thr || before(d2, id, thr_d, thr_i));
+      const unsigned am = __ballot_sync(kFull, admit);
+      if (am) {
+        if (cnt + __popc(am) > kStage) {  // warp-uniform
+          cnt = compact_stage(sd, si, cnt, limit, lane);
+          have_thr = cnt == limit;
+          if (have_thr) {
+            thr_d = sd[limit - 1];
+            thr_i = si[limit - 1];
+          }
+          // re-test this batch against the new threshold
+          const bool admit2 = admit && (!have_thr || before(d2, id, thr_d, thr_i));
+          const unsigned am2 = __ballot_sync(kFull, admit2);
+          if (admit2) {
+            const int pos = cnt + __popc(am2 & ((1u << lane) - 1u));
+            sd[pos] = d2;
+            si[pos] = id;
+          }
+          cnt += __popc(am2);
+        } else {
+          if (admit) {
+            const int pos = cnt + __popc(am & ((1u << lane) - 1u));
+            sd[pos] = d2;
+            si[pos] = id;
+          }
+          cnt += __popc(am);
+        }
+        __syncwarp();
+      }
+    }
+    block_max = max(block_max, in_radius);
+
+    // rank the staged hits and emit the row
+    IdxT* __restrict__ row = out + (size_t)qi * row_stride;
+    for (int e = lane; e < cnt; e += 32) {
+      const float d = sd[e];
+      const int id = si[e];
+      int r = 0;
+      for (int f = 0; f < cnt; ++f) r += before(sd[f], si[f], d, id) ? 1 : 0;
+      if (r < limit) row[r] = (IdxT)id;
+    }
+    for (int j = min(cnt, limit) + lane; j < limit; j += 32) row[j] = (IdxT)ns_total;
+    __syncwarp();
+  }
+  if (lane == 0 && block_max > 0) atomicMax(max_count, block_max);
+}
+
+}  // namespace
+}  // namespace spr
+
+using namespace spr;
+
+namespace {
+struct GridLayout {
+  GridHeader* hdr;
+  int* offs;
+  uint32_t* bb;
+  CellGrid* grids;
+  int* cell_start;  // [cap+1]
+  int* cell_fill;   // [cap]
+  int* point_cell;  // [ns]
+  float4* sorted;   // [ns]
+  int* scan_tmp;
+  int* q_offs;      // [B+1] scratch for the query-side offsets (queries on one grid must be stream-ordered)
+  size_t cap;
+  size_t bytes;
+};
+
+GridLayout carve_grid(void* ws, size_t ws_bytes, int ns, int B) {
+  GridLayout L;
+  L.cap = (size_t)(cell_budget(0) * (long long)B + 16ll * ns);
+  Carver c(ws, ws_bytes);
+  L.hdr = c.take<GridHeader>(1);
+  L.offs = c.take<int>((size_t)B + 1);
+  L.bb = c.take<uint32_t>((size_t)B * 6);
+  L.grids = c.take<CellGrid>(B);
+  L.cell_start = c.take<int>(L.cap + 1);
+  L.cell_fill = c.take<int>(L.cap);
+  L.point_cell = c.take<int>(ns);
+  L.sorted = c.take<float4>(ns);
+  L.scan_tmp = c.take<int>(scan_tmp_ints(L.cap + 1));
+  L.q_offs = c.take<int>((size_t)B + 1);
+  L.bytes = c.off;
+  return L;
+}
+}  // namespace
+
+extern "C" size_t spr_cell_grid_workspace_bytes(int n_supports, int n_clouds) {
+  if (n_supports < 0 || n_clouds < 0) return 0;
+  GridLayout L = carve_grid(nullptr, 0, n_supports, n_clouds);
+  return L.bytes + 1024;
+}
+
+extern "C" int spr_cell_grid_build(const float* d_supports, const int32_t* d_s_lengths, int n_supports, int n_clouds,
+                                   float radius, void* d_grid_workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPR_CHECK_ARG(n_supports > 0 && n_clouds > 0, "cell_grid_build: empty input (n_supports=%d, n_clouds=%d)", n_supports,
+                n_clouds);
+  SPR_CHECK_ARG(radius > 0.f, "cell_grid_build: radius must be > 0");
+  SPR_CHECK_ARG(d_supports && d_s_lengths && d_grid_workspace, "cell_grid_build: null pointer");
+  if (workspace_bytes < spr_cell_grid_workspace_bytes(n_supports, n_clouds)) {
+    set_error("cell_grid_build: workspace too small");
+    return SPR_ENOSPACE;
+  }
+  const int ns = n_supports, B = n_clouds;
+  GridLayout L = carve_grid(d_grid_workspace, workspace_bytes, ns, B);
+  const int gp = (ns + kThreads - 1) / kThreads;
+  int rc = cloud_offsets(d_s_lengths, B, L.offs, stream);
+  if (rc) return rc;
+  k_bbox_init<<<(B * 3 + 255) / 256, 256, 0, stream>>>(L.bb, B);
+  SPR_LAUNCH_CHECK("k_bbox_init");
+  k_bbox<<<gp, kThreads, 0, stream>>>(d_supports, L.offs, B, ns, L.bb);
+  SPR_LAUNCH_CHECK("k_bbox");
+  k_plan_grids<<<1, 1024, 0, stream>>>(L.bb, L.offs, B, radius, L.grids, L.hdr);
+  SPR_LAUNCH_CHECK("k_plan_grids");
+  SPR_CUDA(cudaMemsetAsync(L.cell_start, 0, (L.cap + 1) * 4, stream));
+  SPR_CUDA(cudaMemsetAsync(L.cell_fill, 0, L.cap * 4, stream));
+  k_cell_count<<<gp, kThreads, 0, stream>>>(d_supports, L.offs, B, ns, L.grids, L.cell_start, L.point_cell);
+  SPR_LAUNCH_CHECK("k_cell_count");
+  rc = exclusive_scan_i32(L.cell_start, L.cell_start, L.cap + 1, nullptr, L.scan_tmp, stream);
+  if (rc) return rc;
+  k_cell_scatter<<<gp, kThreads, 0, stream>>>(d_supports, ns, L.point_cell, L.cell_start, L.cell_fill, L.sorted);
+  SPR_LAUNCH_CHECK("k_cell_scatter");
+  return SPR_OK;
+}
+
+extern "C" int spr_radius_query(const float* d_queries, const int32_t* d_q_lengths, int n_queries, int n_clouds,
+                                const void* d_grid_workspace, int n_supports, float radius, int limit, void* d_out_idx,
+                                int idx_is_64, int row_stride, int32_t* d_out_max_count, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPR_CHECK_ARG(n_queries > 0 && n_clouds > 0 && n_supports > 0, "radius_query: empty input (nq=%d, ns=%d, B=%d)",
+                n_queries, n_supports, n_clouds);
+  SPR_CHECK_ARG(limit > 0 && limit <= SPR_MAX_NEIGHBOR_LIMIT, "radius_query: limit %d outside [1, %d]", limit,
+                SPR_MAX_NEIGHBOR_LIMIT);
+  SPR_CHECK_ARG(row_stride >= limit, "radius_query: row_stride < limit");
+  SPR_CHECK_ARG(radius > 0.f, "radius_query: radius must be > 0");
+  SPR_CHECK_ARG(d_queries && d_q_lengths && d_grid_workspace && d_out_idx && d_out_max_count, "radius_query: null pointer");
+  GridLayout L = carve_grid(const_cast<void*>(d_grid_workspace), (size_t)-1, n_supports, n_clouds);
+  int* q_offs = L.q_offs;
+  int rc = cloud_offsets(d_q_lengths, n_clouds, q_offs, stream);
+  if (rc) return rc;
+  SPR_CUDA(cudaMemsetAsync(d_out_max_count, 0, sizeof(int32_t), stream));
+  const float r2 = radius * radius;  // fp32 product, as neighbors.cpp:226
+  int blocks = (n_queries + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int max_blocks = kNumSMs * 8 * 4;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (idx_is_64)
+    k_radius_query<long long><<<blocks, kThreads, 0, stream>>>(d_queries, q_offs, n_clouds, n_queries, L.grids,
+                                                               L.cell_start, L.sorted, n_supports, r2, limit,
+                                                               static_cast<long long*>(d_out_idx), row_stride,
+                                                               d_out_max_count);
+  else
+    k_radius_query<int><<<blocks, kThreads, 0, stream>>>(d_queries, q_offs, n_clouds, n_queries, L.grids, L.cell_start,
+                                                         L.sorted, n_supports, r2, limit, static_cast<int*>(d_out_idx),
+                                                         row_stride, d_out_max_count);
+  SPR_LAUNCH_CHECK("k_radius_query");
+  return SPR_OK;
+}

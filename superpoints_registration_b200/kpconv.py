@@ -1,0 +1,200 @@
+"""KPConv preprocessing (pyramid of subsampled clouds + neighbour / pool / upsample index matrices) and the
+encoder, on B200.
+
+Mirrors the operator surface of the reference's models/backbone_kpconv/kpconv.py:
+  batch_grid_subsampling_kpconv   kpconv.py:174-214  (cpp_subsampling.subsample_batch)
+  batch_neighbors_kpconv          kpconv.py:247-262  (cpp_neighbors.batch_query + truncation)
+  Preprocessor                    kpconv.py:295-418  (the CPU pyramid builder north_star names as oracle)
+  KPFEncoder                      kpconv.py:22-92
+Same names, argument meaning, output dict keys ('points', 'neighbors', 'pools', 'upsamples',
+'stack_lengths'), dtypes (int64 indices, shadow = number of support points, int32 lengths) and errors
+(RuntimeError from the native layer).  Everything runs on the device the inputs live on; there is no CPU
+round trip (the reference does `.cpu()` in, `.to(device)` out, kpconv.py:313-314,410-416) and no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .kpconv_blocks import block_decider
+
+
+# ------------------------------------------------------------------------------------------------
+# thin operator wrappers with the reference's names
+# ------------------------------------------------------------------------------------------------
+
+def batch_grid_subsampling_kpconv(points, batches_len, features=None, labels=None, sampleDl=0.1, max_p=0, verbose=0,
+                                  random_grid_orient=True):
+    """Grid subsampling (barycentres) of stacked clouds: -> (s_points f32[M,3], s_len i32[B]).
+
+    Points come out per cloud in first-occurrence voxel order (the reference's order is its hash table's,
+    grid_subsampling.cpp:85); coordinates are bit-identical.
+    """
+    if features is not None or labels is not None:
+        raise NotImplementedError("feature/label subsampling is not on the registration path (kpconv.py:370)")
+    if max_p != 0:
+        raise NotImplementedError("max_p > 0 truncates in emission order, which differs from the reference's hash order")
+    return ops.grid_subsample_batch(points, batches_len, float(sampleDl))
+
+
+def batch_neighbors_kpconv(queries, supports, q_batches, s_batches, radius, max_neighbors):
+    """Radius neighbours of stacked clouds: -> i64[Nq, min(max_count, max_neighbors)], shadow = Ns.
+
+    max_neighbors <= 0 (keep everything, kpconv.py:261-262) is served with the library's maximum row width.
+    """
+    limit = int(max_neighbors) if max_neighbors > 0 else 128
+    idx, mc = ops.radius_neighbors_batch(queries, supports, q_batches, s_batches, float(radius), limit)
+    width = min(int(mc.item()), limit)
+    if max_neighbors <= 0 and int(mc.item()) > limit:
+        raise RuntimeError(f"neighbourhood of {int(mc.item())} points exceeds the supported row width {limit}")
+    return idx[:, :max(width, 0)] if width > 0 else idx[:, :0]
+
+
+# ------------------------------------------------------------------------------------------------
+# pyramid
+# ------------------------------------------------------------------------------------------------
+
+def _split_levels(architecture: Sequence[str]):
+    """Group the block list into pyramid levels: (has_conv_blocks, ends_with_stride) per level.
+
+    Same grouping rule as kpconv.py:335-346: a level collects blocks until a pooling/strided block (which
+    closes it with a subsampling) or the end of the encoder; 'global'/'upsample' blocks end the walk.
+    """
+    levels = []
+    pending = 0
+    blocks = []
+    for name in architecture:
+        if "global" in name or "upsample" in name:
+            break
+        blocks.append(name)
+    for i, name in enumerate(blocks):
+        if any(t in name for t in ("deformable",)):
+            raise NotImplementedError("deformable KPConv is not used by any shipped configuration")
+        strided = "pool" in name or "strided" in name
+        if strided:
+            levels.append((pending > 0, True))
+            pending = 0
+        else:
+            pending += 1
+            if i == len(blocks) - 1:
+                levels.append((True, False))
+    return levels
+
+
+class Preprocessor(nn.Module):
+    """Computes the metadata used by the KPConv encoder (drop-in for kpconv.py:295-418)."""
+
+    def __init__(self, cfg, exact_width: bool = True, index_dtype: torch.dtype = torch.int64):
+        super().__init__()
+        self.cfg = cfg
+        # exact_width: trim each index matrix to min(batch max_count, limit) columns like the reference
+        # (one extra host sync at the end).  False keeps `limit` columns; the extra columns are all-shadow.
+        self.exact_width = exact_width
+        self.index_dtype = index_dtype
+
+    @torch.no_grad()
+    def forward(self, pts: List[torch.Tensor]) -> Dict[str, List[torch.Tensor]]:
+        cfg = self.cfg
+        if len(pts) == 0:
+            raise RuntimeError("Preprocessor: empty point cloud list")
+        device = pts[0].device
+        if device.type != "cuda":
+            raise RuntimeError("Preprocessor: inputs must be CUDA tensors (no CPU fallback on the B200 path)")
+        limits = cfg.neighborhood_limits
+        levels = _split_levels(cfg.architecture)
+
+        lengths = torch.tensor([p.shape[0] for p in pts], dtype=torch.int32, device=device)
+        points = torch.cat([p.to(torch.float32) for p in pts], dim=0).contiguous()
+        r = float(cfg.first_subsampling_dl) * float(cfg.conv_radius)
+
+        out_points, out_neighbors, out_pools, out_ups, out_lens = [], [], [], [], []
+        widths = []  # (list, position, max_count tensor)
+        grid = ops.CellGrid(points, lengths, r)
+        empty_idx = lambda: torch.zeros((0, 1), dtype=torch.int64, device=device)
+        for li, (has_conv, strided) in enumerate(levels):
+            limit = int(limits[li])
+            if has_conv:
+                conv_i, mc = grid.query(points, lengths, limit, index_dtype=self.index_dtype)
+                widths.append((out_neighbors, li, mc, limit))
+            else:
+                conv_i = empty_idx()
+            if strided:
+                dl = 2.0 * r / float(cfg.conv_radius)
+                pool_p, pool_b = ops.grid_subsample_batch(points, lengths, dl)
+                pool_i, mc = grid.query(pool_p, pool_b, limit, index_dtype=self.index_dtype)
+                widths.append((out_pools, li, mc, limit))
+                next_grid = ops.CellGrid(pool_p, pool_b, 2.0 * r)
+                up_i, mc = next_grid.query(points, lengths, limit, index_dtype=self.index_dtype)
+                widths.append((out_ups, li, mc, limit))
+            else:
+                pool_i, up_i = empty_idx(), empty_idx()
+                pool_p = torch.zeros((0, 3), dtype=torch.float32, device=device)
+                pool_b = torch.zeros((0,), dtype=torch.int64, device=device)
+                next_grid = None
+            out_points.append(points)
+            out_neighbors.append(conv_i)
+            out_pools.append(pool_i)
+            out_ups.append(up_i)
+            out_lens.append(lengths)
+            points, lengths, grid = pool_p, pool_b, next_grid
+            r *= 2.0
+
+        if self.exact_width and widths:
+            counts = torch.cat([w[2] for w in widths]).tolist()  # the single sync for all widths
+            for (lst, li, _, limit), mc in zip(widths, counts):
+                w = min(int(mc), limit)
+                lst[li] = lst[li][:, :w]
+        return {"points": out_points, "neighbors": out_neighbors, "pools": out_pools, "upsamples": out_ups,
+                "stack_lengths": out_lens}
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder
+# ------------------------------------------------------------------------------------------------
+
+class KPFEncoder(nn.Module):
+    """KPConv encoder (drop-in for kpconv.py:22-92): same block plan, same state_dict keys
+    (`encoder_blocks.{i}.KPConv.weights` ...), every block running on the fused sm_100a kernels."""
+
+    def __init__(self, config, d_bottle=None, increase_channel_when_downsample: bool = True):
+        super().__init__()
+        radius = config.first_subsampling_dl * config.conv_radius
+        in_dim, out_dim = config.in_feats_dim, config.first_feats_dim
+        level = 0
+        self.encoder_blocks = nn.ModuleList()
+        self.encoder_skips: List[int] = []
+        self.encoder_skip_dims: List[int] = []
+        last_name, last_index = None, -1
+        for index, name in enumerate(config.architecture):
+            last_name, last_index = name, index
+            if "equivariant" in name and out_dim % 3 != 0:
+                raise ValueError("Equivariant block but features dimension is not a factor of 3")
+            changes_level = any(t in name for t in ("pool", "strided", "upsample", "global"))
+            if changes_level:
+                self.encoder_skips.append(index)
+                self.encoder_skip_dims.append(in_dim)
+            if "upsample" in name:
+                break
+            self.encoder_blocks.append(block_decider(name, radius, in_dim, out_dim, level, config))
+            in_dim = out_dim // 2 if "simple" in name else out_dim
+            if "pool" in name or "strided" in name:
+                level += 1
+                radius *= 2
+                if increase_channel_when_downsample:
+                    out_dim *= 2
+        if last_name is not None and "upsample" not in last_name:
+            # encoder-only network: record the final feature width (kpconv.py:74-79)
+            self.encoder_skips.append(last_index)
+            self.encoder_skip_dims.append(in_dim)
+
+    def forward(self, x, batch):
+        skips = []
+        for index, block in enumerate(self.encoder_blocks):
+            if index in self.encoder_skips:
+                skips.append(x)
+            x = block(x, batch)
+        return x, skips

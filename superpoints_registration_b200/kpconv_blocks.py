@@ -1,0 +1,211 @@
+"""KPConv operator and the encoder blocks built on it, on B200.
+
+Mirrors the operator surface of the reference's models/backbone_kpconv/kpconv_blocks.py:
+  KPConv                 :175-420   -> one fused kernel (spr_kpconv_forward)
+  BatchNormBlock         :474-530   -> per-cloud instance norm, fused with the following LeakyReLU / residual
+  UnaryBlock             :533-567
+  SimpleBlock            :590-646
+  ResnetBottleneckBlock  :649-741
+  max_pool               :127-143   -> spr_max_pool
+  block_decider          :429-471
+Module / parameter names are the reference's, so a reference state_dict loads key for key
+(`KPConv.weights`, `KPConv.kernel_points`, `unary1.mlp.weight`, `unary2.mlp.weight`,
+`unary_shortcut.mlp.weight`).  The Linear layers of the unary blocks are plain fp32 GEMMs and go to cuBLAS
+through torch (TF32 disabled); everything else on the path is our own kernels.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+from torch.nn.parameter import Parameter
+
+from . import ops
+from .kernel_points import load_kernels
+
+LRELU_SLOPE = 0.1
+IN_EPS = 1e-5  # nn.InstanceNorm1d default eps
+
+
+def max_pool(x, inds):
+    """Pools features with the maximum over each pooling neighbourhood (shadow index -> zero row)."""
+    return ops.max_pool(x, inds)
+
+
+class KPConv(nn.Module):
+    """Rigid kernel-point convolution (linear influence, sum aggregation).
+
+    Same constructor signature as the reference (kpconv_blocks.py:177-179).  Modes no shipped configuration
+    uses raise NotImplementedError.
+    """
+
+    def __init__(self, kernel_size, p_dim, in_channels, out_channels, KP_extent, radius,
+                 fixed_kernel_points='center', KP_influence='linear', aggregation_mode='sum',
+                 deformable=False, modulated=False):
+        super().__init__()
+        if deformable or modulated:
+            raise NotImplementedError("deformable / modulated KPConv is not used by any shipped configuration")
+        if KP_influence != 'linear':
+            raise NotImplementedError(f"KP_influence='{KP_influence}': only 'linear' is on the registration path")
+        if aggregation_mode != 'sum':
+            raise NotImplementedError(f"aggregation_mode='{aggregation_mode}': only 'sum' is on the registration path")
+        if p_dim != 3:
+            raise NotImplementedError("3-D points only")
+        self.K = kernel_size
+        self.p_dim = p_dim
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.radius = radius
+        self.KP_extent = KP_extent
+        self.fixed_kernel_points = fixed_kernel_points
+        self.KP_influence = KP_influence
+        self.aggregation_mode = aggregation_mode
+        self.deformable = deformable
+        self.modulated = modulated
+        self.mode = 0  # 0: fp32 CUDA-core contraction
+        self.weights = Parameter(torch.zeros((self.K, in_channels, out_channels), dtype=torch.float32))
+        nn.init.kaiming_uniform_(self.weights, a=math.sqrt(5))
+        kp = load_kernels(self.radius, self.K, dimension=self.p_dim, fixed=self.fixed_kernel_points)
+        self.kernel_points = Parameter(torch.tensor(kp, dtype=torch.float32), requires_grad=False)
+
+    def forward(self, q_pts, s_pts, neighb_inds, x):
+        return ops.kpconv_forward(q_pts, s_pts, neighb_inds, x, self.weights, self.kernel_points,
+                                  float(self.KP_extent), mode=self.mode)
+
+    def __repr__(self):
+        return (f'KPConv(radius: {self.radius:.2f}, extent: {self.KP_extent:.2f}, in_feat: {self.in_channels:d}, '
+                f'out_feat: {self.out_channels:d})')
+
+
+class BatchNormBlock(nn.Module):
+    """Per-cloud InstanceNorm (no affine, no running statistics) or, when `use_bn` is False, a bias."""
+
+    def __init__(self, in_dim, use_bn, bn_momentum):
+        super().__init__()
+        self.bn_momentum = bn_momentum
+        self.use_bn = use_bn
+        self.in_dim = in_dim
+        if not self.use_bn:
+            self.bias = Parameter(torch.zeros(in_dim, dtype=torch.float32))
+
+    def forward(self, x, stack_lengths, slope: float = 1.0, residual=None):
+        """`slope` / `residual` let callers fuse the LeakyReLU and the residual sum that always follow."""
+        # (the reference asserts x.shape[0] == stack_lengths.sum() here, :499 -- a device sync we do not pay)
+        if self.use_bn:
+            return ops.instance_norm_lrelu(x, stack_lengths, IN_EPS, slope, residual)
+        y = x + self.bias
+        if residual is not None:
+            y = y + residual
+        return y if slope == 1.0 else torch.nn.functional.leaky_relu(y, slope)
+
+    def __repr__(self):
+        return f'BatchNormBlock(in_feat: {self.in_dim:d}, momentum: {self.bn_momentum:.3f}, only_bias: {not self.use_bn})'
+
+
+class UnaryBlock(nn.Module):
+    """Linear (no bias) -> per-cloud InstanceNorm -> optional LeakyReLU(0.1)."""
+
+    def __init__(self, in_dim, out_dim, use_bn, bn_momentum, no_relu=False):
+        super().__init__()
+        self.bn_momentum = bn_momentum
+        self.use_bn = use_bn
+        self.no_relu = no_relu
+        self.in_dim = in_dim
+        self.out_dim = out_dim
+        self.mlp = nn.Linear(in_dim, out_dim, bias=False)
+        self.batch_norm = BatchNormBlock(out_dim, self.use_bn, self.bn_momentum)
+
+    def forward(self, x, stack_lengths=None, residual=None, slope=None):
+        if slope is None:
+            slope = 1.0 if self.no_relu else LRELU_SLOPE
+        return self.batch_norm(self.mlp(x), stack_lengths, slope=slope, residual=residual)
+
+    def __repr__(self):
+        return (f'UnaryBlock(in_feat: {self.in_dim:d}, out_feat: {self.out_dim:d}, BN: {self.use_bn}, '
+                f'ReLU: {not self.no_relu})')
+
+
+def _level_io(batch, layer_ind: int, strided: bool):
+    if strided:
+        return (batch['points'][layer_ind + 1], batch['points'][layer_ind], batch['pools'][layer_ind],
+                batch['stack_lengths'][layer_ind + 1])
+    return (batch['points'][layer_ind], batch['points'][layer_ind], batch['neighbors'][layer_ind],
+            batch['stack_lengths'][layer_ind])
+
+
+class SimpleBlock(nn.Module):
+    """KPConv -> InstanceNorm -> LeakyReLU (kpconv_blocks.py:590-646)."""
+
+    def __init__(self, block_name, in_dim, out_dim, radius, layer_ind, config):
+        super().__init__()
+        self.bn_momentum = config.batch_norm_momentum
+        self.use_bn = config.use_batch_norm
+        self.layer_ind = layer_ind
+        self.block_name = block_name
+        self.in_dim = in_dim
+        self.out_dim = out_dim
+        extent = radius * config.KP_extent / config.conv_radius
+        self.KPConv = KPConv(config.num_kernel_points, config.in_points_dim, in_dim, out_dim // 2, extent, radius,
+                             fixed_kernel_points=config.fixed_kernel_points, KP_influence=config.KP_influence,
+                             aggregation_mode=config.aggregation_mode, deformable='deform' in block_name,
+                             modulated=config.modulated)
+        self.batch_norm = BatchNormBlock(out_dim // 2, self.use_bn, self.bn_momentum)
+
+    def forward(self, x, batch):
+        q_pts, s_pts, inds, lengths = _level_io(batch, self.layer_ind, 'strided' in self.block_name)
+        x = self.KPConv(q_pts, s_pts, inds, x)
+        return self.batch_norm(x, lengths, slope=LRELU_SLOPE)
+
+
+class ResnetBottleneckBlock(nn.Module):
+    """unary1 -> KPConv -> norm -> lrelu -> unary2 ; (+) shortcut ; lrelu   (kpconv_blocks.py:649-741)."""
+
+    def __init__(self, block_name, in_dim, out_dim, radius, layer_ind, config):
+        super().__init__()
+        self.bn_momentum = config.batch_norm_momentum
+        self.use_bn = config.use_batch_norm
+        self.block_name = block_name
+        self.layer_ind = layer_ind
+        self.in_dim = in_dim
+        self.out_dim = out_dim
+        mid = out_dim // 4
+        extent = radius * config.KP_extent / config.conv_radius
+        self.unary1 = UnaryBlock(in_dim, mid, self.use_bn, self.bn_momentum) if in_dim != mid else nn.Identity()
+        self.KPConv = KPConv(config.num_kernel_points, config.in_points_dim, mid, mid, extent, radius,
+                             fixed_kernel_points=config.fixed_kernel_points, KP_influence=config.KP_influence,
+                             aggregation_mode=config.aggregation_mode, deformable='deform' in block_name,
+                             modulated=config.modulated)
+        self.batch_norm_conv = BatchNormBlock(mid, self.use_bn, self.bn_momentum)
+        self.unary2 = UnaryBlock(mid, out_dim, self.use_bn, self.bn_momentum, no_relu=True)
+        self.unary_shortcut = (UnaryBlock(in_dim, out_dim, self.use_bn, self.bn_momentum, no_relu=True)
+                               if in_dim != out_dim else nn.Identity())
+
+    def forward(self, features, batch):
+        strided = 'strided' in self.block_name
+        pre_lengths = batch['stack_lengths'][self.layer_ind]
+        q_pts, s_pts, inds, post_lengths = _level_io(batch, self.layer_ind, strided)
+
+        x = self.unary1(features, pre_lengths) if isinstance(self.unary1, UnaryBlock) else features
+        x = self.KPConv(q_pts, s_pts, inds, x)
+        x = self.batch_norm_conv(x, post_lengths, slope=LRELU_SLOPE)
+
+        shortcut = max_pool(features, inds) if strided else features
+        if isinstance(self.unary_shortcut, UnaryBlock):
+            shortcut = self.unary_shortcut(shortcut, post_lengths)
+        # unary2 has no activation of its own: its norm, the residual sum and the block's final LeakyReLU
+        # (kpconv_blocks.py:730-741) run as one kernel.
+        return self.unary2(x, post_lengths, residual=shortcut, slope=LRELU_SLOPE)
+
+
+def block_decider(block_name, radius, in_dim, out_dim, layer_ind, config):
+    if block_name == 'unary':
+        return UnaryBlock(in_dim, out_dim, config.use_batch_norm, config.batch_norm_momentum)
+    if block_name in ('simple', 'simple_strided'):
+        return SimpleBlock(block_name, in_dim, out_dim, radius, layer_ind, config)
+    if block_name in ('resnetb', 'resnetb_strided'):
+        return ResnetBottleneckBlock(block_name, in_dim, out_dim, radius, layer_ind, config)
+    if any(t in block_name for t in ('deformable', 'invariant', 'equivariant', 'max_pool', 'global_average',
+                                     'nearest_upsample', 'unary2')):
+        raise NotImplementedError(f"block '{block_name}' is not used by the registration encoder")
+    raise ValueError('Unknown block name in the architecture definition : ' + block_name)

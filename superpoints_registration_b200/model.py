@@ -1,0 +1,298 @@
+"""The registration forward pass (hot path only) on B200.
+
+Mirrors models/qk_regtr_full.py of the reference: `RegTR.forward` (:126-311) and
+`RegTR.softmax_correlation` (:423-672), with the same sub-module names so that a reference checkpoint
+loads key for key (`kpf_encoder.*`, `feat_proj.*`, `transformer_encoder.*`, `overlap_predictor.*`,
+`alpha`, `beta`).  Training-only members (losses, metrics, optimiser plumbing) are out of scope.
+
+What runs where:
+  preprocessor, kpf_encoder, superpoint matching, Sinkhorn, pose solve  -> our sm_100a kernels (libspr_b200.so)
+  unary Linear layers, feat_proj, the 6-layer cross-attention transformer  -> PyTorch fp32 (cuBLAS / SDPA);
+  the transformer is on the path but outside north_star's change list.
+The per-pair Python loop of the reference (:445) is gone: all pairs of the batch go through the same launches.
+"""
+from __future__ import annotations
+
+import copy
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .kpconv import KPFEncoder, Preprocessor
+
+_UNSUPPORTED_FLAGS = ("use_ratio_test", "threshold_corr", "remove_outliers_overlap", "remove_points_from_val",
+                      "use_lgr", "use_ransac", "use_attn_affinity", "use_corr_affinity", "use_overlap_as_weights")
+
+
+# ------------------------------------------------------------------------------------------------
+# sequence helpers (utils/seq_manipulation.py:6-48)
+# ------------------------------------------------------------------------------------------------
+
+def split_src_tgt(feats, stack_lengths, dim=0):
+    if isinstance(stack_lengths, torch.Tensor):
+        stack_lengths = stack_lengths.tolist()
+    half = len(stack_lengths) // 2
+    parts = torch.split(feats, stack_lengths, dim=dim)
+    return parts[:half], parts[half:]
+
+
+def pad_sequence(sequences, require_padding_mask=False, require_lens=False, batch_first=False):
+    padded = nn.utils.rnn.pad_sequence(sequences, batch_first=batch_first)
+    mask = None
+    if require_padding_mask:
+        lens = torch.tensor([s.shape[0] for s in sequences], device=padded.device)
+        steps = padded.shape[1] if batch_first else padded.shape[0]
+        mask = torch.arange(steps, device=padded.device)[None, :] >= lens[:, None]
+    lens_out = [s.shape[0] for s in sequences] if require_lens else None
+    return padded, mask, lens_out
+
+
+def unpad_sequences(padded, seq_lens):
+    return [padded[..., :seq_lens[b], b, :] for b in range(len(seq_lens))]
+
+
+# ------------------------------------------------------------------------------------------------
+# transformer (models/transformer/position_embedding.py:7-50, transformers.py:18-259) -- PyTorch
+# ------------------------------------------------------------------------------------------------
+
+class PositionEmbeddingCoordsSine(nn.Module):
+    def __init__(self, n_dim: int = 1, d_model: int = 256, temperature=10000, scale=None):
+        super().__init__()
+        self.n_dim = n_dim
+        self.num_pos_feats = d_model // n_dim // 2 * 2
+        self.temperature = temperature
+        self.padding = d_model - self.num_pos_feats * self.n_dim
+        self.scale = (1.0 if scale is None else scale) * 2 * math.pi
+
+    def forward(self, xyz: torch.Tensor) -> torch.Tensor:
+        assert xyz.shape[-1] == self.n_dim
+        k = torch.arange(self.num_pos_feats, dtype=torch.float32, device=xyz.device)
+        freq = self.temperature ** (2 * torch.div(k, 2, rounding_mode='trunc') / self.num_pos_feats)
+        ang = (xyz * self.scale).unsqueeze(-1) / freq
+        emb = torch.stack([ang[..., 0::2].sin(), ang[..., 1::2].cos()], dim=-1).reshape(*xyz.shape[:-1], -1)
+        return F.pad(emb, (0, self.padding))
+
+
+class TransformerCrossEncoderLayer(nn.Module):
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu", normalize_before=False,
+                 sa_val_has_pos_emb=False, ca_val_has_pos_emb=False, attention_type='dot_prod', batch_first=False):
+        super().__init__()
+        if attention_type != 'dot_prod':
+            raise NotImplementedError
+        if dropout != 0.0:
+            raise NotImplementedError("inference path: dropout must be 0 (as in every shipped config)")
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout, batch_first=batch_first)
+        self.multihead_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout, batch_first=batch_first)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.norm3 = nn.LayerNorm(d_model)
+        self.activation = {"relu": F.relu, "gelu": F.gelu}[activation]
+        self.normalize_before = normalize_before
+        self.sa_val_has_pos_emb = sa_val_has_pos_emb
+        self.ca_val_has_pos_emb = ca_val_has_pos_emb
+
+    @staticmethod
+    def _pe(x, pos):
+        return x if pos is None else x + pos
+
+    def _sa(self, x, pos, mask):
+        xp = self._pe(x, pos)
+        return self.self_attn(xp, xp, value=xp if self.sa_val_has_pos_emb else x, key_padding_mask=mask,
+                              need_weights=False)[0]
+
+    def _ca(self, q, q_pos, kv, kv_pos, kv_mask):
+        kp = self._pe(kv, kv_pos)
+        return self.multihead_attn(query=self._pe(q, q_pos), key=kp, value=kp if self.ca_val_has_pos_emb else kv,
+                                   key_padding_mask=kv_mask, need_weights=False)[0]
+
+    def _ffn(self, x):
+        return self.linear2(self.activation(self.linear1(x)))
+
+    def forward(self, src, tgt, src_key_padding_mask=None, tgt_key_padding_mask=None, src_pos=None, tgt_pos=None):
+        sm, tm = src_key_padding_mask, tgt_key_padding_mask
+        if self.normalize_before:  # transformers.py:184-245
+            src = src + self._sa(self.norm1(src), src_pos, sm)
+            tgt = tgt + self._sa(self.norm1(tgt), tgt_pos, tm)
+            s2, t2 = self.norm2(src), self.norm2(tgt)
+            src, tgt = src + self._ca(s2, src_pos, t2, tgt_pos, tm), tgt + self._ca(t2, tgt_pos, s2, src_pos, sm)
+            src = src + self._ffn(self.norm3(src))
+            tgt = tgt + self._ffn(self.norm3(tgt))
+            return src, tgt
+        # post-norm, transformers.py:117-182
+        src = self.norm1(src + self._sa(src, src_pos, sm))
+        tgt = self.norm1(tgt + self._sa(tgt, tgt_pos, tm))
+        s3, t3 = self._ca(src, src_pos, tgt, tgt_pos, tm), self._ca(tgt, tgt_pos, src, src_pos, sm)
+        src, tgt = self.norm2(src + s3), self.norm2(tgt + t3)
+        src = self.norm3(src + self._ffn(src))
+        tgt = self.norm3(tgt + self._ffn(tgt))
+        return src, tgt
+
+
+class TransformerCrossEncoder(nn.Module):
+    def __init__(self, cross_encoder_layer, num_layers, norm=None, return_intermediate=False):
+        super().__init__()
+        if return_intermediate:
+            raise NotImplementedError
+        self.layers = nn.ModuleList([copy.deepcopy(cross_encoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+        self.norm = norm
+
+    def forward(self, src, tgt, src_key_padding_mask=None, tgt_key_padding_mask=None, src_pos=None, tgt_pos=None):
+        for layer in self.layers:
+            src, tgt = layer(src, tgt, src_key_padding_mask=src_key_padding_mask,
+                             tgt_key_padding_mask=tgt_key_padding_mask, src_pos=src_pos, tgt_pos=tgt_pos)
+        if self.norm is not None:
+            src, tgt = self.norm(src), self.norm(tgt)
+        return src.unsqueeze(0), tgt.unsqueeze(0)
+
+
+# ------------------------------------------------------------------------------------------------
+# model
+# ------------------------------------------------------------------------------------------------
+
+class RegTR(nn.Module):
+    """Inference-path twin of models/qk_regtr_full.RegTR."""
+
+    def __init__(self, cfg, *args, **kwargs):
+        super().__init__()
+        self.cfg = cfg
+        for flag in _UNSUPPORTED_FLAGS:
+            if cfg.get(flag, False):
+                raise NotImplementedError(f"{flag}=True: optional refinement, off in every shipped configuration")
+        self.preprocessor = Preprocessor(cfg)
+        self.kpf_encoder = KPFEncoder(cfg, cfg.d_embed)
+        self.feat_proj = nn.Linear(self.kpf_encoder.encoder_skip_dims[-1], cfg.d_embed, bias=True)
+        if cfg.get('pos_emb_type', 'sine') != 'sine':
+            raise NotImplementedError("learned position embedding")
+        self.pos_embed = PositionEmbeddingCoordsSine(3, cfg.d_embed, scale=cfg.get('pos_emb_scaling', 1.0))
+        layer = TransformerCrossEncoderLayer(
+            cfg.d_embed, cfg.nhead, cfg.d_feedforward, cfg.dropout, activation=cfg.transformer_act,
+            normalize_before=cfg.pre_norm, sa_val_has_pos_emb=cfg.sa_val_has_pos_emb,
+            ca_val_has_pos_emb=cfg.ca_val_has_pos_emb, attention_type=cfg.attention_type)
+        self.transformer_encoder = TransformerCrossEncoder(
+            layer, cfg.num_encoder_layers, nn.LayerNorm(cfg.d_embed) if cfg.pre_norm else None)
+        self.beta = nn.Parameter(torch.tensor(1.0))
+        self.alpha = nn.Parameter(torch.tensor(1.0))
+        self.overlap_predictor = nn.Linear(cfg.d_embed, 1)
+        self.dual_normalization = True  # hard-coded in the reference (:120)
+        self.return_attn = True          # outputs['attn'] (:295); set False to skip materialising N x M matrices
+
+    def load_reference_state_dict(self, state_dict):
+        """Load a reference checkpoint; training-only keys (loss modules) are ignored."""
+        own = self.state_dict()
+        picked = {k: v for k, v in state_dict.items() if k in own}
+        missing = [k for k in own if k not in picked]
+        if missing:
+            raise RuntimeError(f"reference state_dict lacks keys: {missing[:5]}...")
+        self.load_state_dict(picked, strict=True)
+
+    # -------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, batch):
+        cfg = self.cfg
+        B = len(batch['src_xyz'])
+        meta = self.preprocessor(list(batch['src_xyz']) + list(batch['tgt_xyz']))
+        batch['kpconv_meta'] = meta
+        slens_c = meta['stack_lengths'][-1].tolist()
+        src_slens_c, tgt_slens_c = slens_c[:B], slens_c[B:]
+        pts_c = meta['points'][-1]
+        feats0 = torch.ones_like(meta['points'][0][:, 0:1])
+
+        feats_un, _ = self.kpf_encoder(feats0, meta)
+        both = self.feat_proj(feats_un)
+        src_feats_un, tgt_feats_un = split_src_tgt(both, slens_c)
+        src_xyz_c, tgt_xyz_c = split_src_tgt(pts_c, slens_c)
+        src_pe, tgt_pe = split_src_tgt(self.pos_embed(pts_c), slens_c)
+        src_pe_pad, _, _ = pad_sequence(src_pe)
+        tgt_pe_pad, _, _ = pad_sequence(tgt_pe)
+        src_pad, src_mask, _ = pad_sequence(src_feats_un, require_padding_mask=True)
+        tgt_pad, tgt_mask, _ = pad_sequence(tgt_feats_un, require_padding_mask=True)
+        use_pe = cfg.transformer_encoder_has_pos_emb
+        src_cond, tgt_cond = self.transformer_encoder(
+            src_pad, tgt_pad, src_key_padding_mask=src_mask, tgt_key_padding_mask=tgt_mask,
+            src_pos=src_pe_pad if use_pe else None, tgt_pos=tgt_pe_pad if use_pe else None)
+
+        src_overlap = torch.sigmoid(self.overlap_predictor(src_cond))
+        tgt_overlap = torch.sigmoid(self.overlap_predictor(tgt_cond))
+        src_overlap_list = unpad_sequences(src_overlap, src_slens_c)
+        tgt_overlap_list = unpad_sequences(tgt_overlap, tgt_slens_c)
+        src_cond_list = unpad_sequences(src_cond, src_slens_c)
+        tgt_cond_list = unpad_sequences(tgt_cond, tgt_slens_c)
+
+        # packed (sum N, D) features in pair order for the batched matching kernels
+        src_packed = src_cond[0].transpose(0, 1)[~src_mask]
+        tgt_packed = tgt_cond[0].transpose(0, 1)[~tgt_mask]
+        pose, attn_list, val_list, ind_list, src_pts_list, tgt_pts_list = self._match_and_solve(
+            src_packed, tgt_packed, pts_c, src_slens_c, tgt_slens_c)
+
+        return {
+            'pose': pose, 'attn': attn_list, 'src_feat': src_cond_list, 'tgt_feat': tgt_cond_list,
+            'src_kp': src_xyz_c, 'tgt_kp': tgt_xyz_c, 'src_corr': src_pts_list, 'tgt_corr': tgt_pts_list,
+            'src_overlap': src_overlap_list, 'tgt_overlap': tgt_overlap_list,
+            'overlap_prob_list': val_list, 'ind_list': ind_list,
+        }
+
+    # -------------------------------------------------------------------------------------------
+    def softmax_correlation(self, src_feats, tgt_feats, src_xyz, tgt_xyz, src_overlap_list=None, tgt_overlap_list=None):
+        """Reference signature (:423): lists of (1,N,D)/(1,M,D) features and (N,3)/(M,3) coordinates."""
+        src_lens = [f.shape[-2] for f in src_feats]
+        tgt_lens = [f.shape[-2] for f in tgt_feats]
+        src_packed = torch.cat([f.reshape(-1, f.shape[-1]) for f in src_feats], dim=0)
+        tgt_packed = torch.cat([f.reshape(-1, f.shape[-1]) for f in tgt_feats], dim=0)
+        pts = torch.cat(list(src_xyz) + list(tgt_xyz), dim=0)
+        return self._match_and_solve(src_packed, tgt_packed, pts, src_lens, tgt_lens)
+
+    def _affinity_scalars(self):
+        """softplus(alpha), exp(beta) as host floats, cached per parameter version (one sync per weight load)."""
+        key = (self.alpha._version, self.beta._version, self.alpha.data_ptr())
+        if getattr(self, '_aff_key', None) != key:
+            self._aff_val = (float(F.softplus(self.alpha.detach())), float(torch.exp(self.beta.detach())))
+            self._aff_key = key
+        return self._aff_val
+
+    def _match_and_solve(self, src_packed, tgt_packed, pts_c, src_lens, tgt_lens):
+        cfg = self.cfg
+        dev = src_packed.device
+        pairs = ops.PackedPairs(src_lens, tgt_lens, dev)
+        total_src = pairs.total_src
+        src_xyz_packed, tgt_xyz_packed = pts_c[:total_src], pts_c[total_src:]
+        corr, attn, val, ind = ops.dual_softmax_match(src_packed, tgt_packed, pairs, want_attn=self.return_attn)
+
+        P = pairs.P
+        attn_list = ([attn[pairs.h_co[p]:pairs.h_co[p + 1]].view(1, src_lens[p], tgt_lens[p]) for p in range(P)]
+                     if attn is not None else [None] * P)
+        val_list = [val[pairs.h_oo[p]:pairs.h_oo[p + 1]] for p in range(P)]
+        ind_list = [ind[pairs.h_oo[p]:pairs.h_oo[p + 1]] for p in range(P)]
+
+        if cfg.use_sinkhorn:
+            # :532-536 / :641-647 -- all source points against Sinkhorn-weighted targets
+            sp_alpha, e_beta = self._affinity_scalars()
+            wt, w = ops.sinkhorn_weighted_targets(corr, pairs, tgt_xyz_packed, sp_alpha, e_beta, int(cfg.sinkhorn_itr),
+                                                  bool(cfg.slack))
+            pose = ops.weighted_procrustes(src_xyz_packed, wt, w, pairs.so)
+            src_pts_list = [src_xyz_packed[pairs.h_so[p]:pairs.h_so[p + 1]] for p in range(P)]
+            tgt_pts_list = [tgt_xyz_packed[pairs.h_to[p]:pairs.h_to[p + 1]] for p in range(P)]
+        else:
+            # :478,548 (N > M: one source per target) / :589,653 (one target per source)
+            gather_from_src = torch.tensor([1 if n > m else 0 for n, m in zip(src_lens, tgt_lens)], device=dev)
+            rows_per_pair = torch.tensor([pairs.h_oo[p + 1] - pairs.h_oo[p] for p in range(P)], device=dev)
+            pair_of_row = torch.repeat_interleave(torch.arange(P, device=dev), rows_per_pair)
+            from_src = gather_from_src[pair_of_row].bool()
+            base = torch.where(from_src, pairs.so[:-1][pair_of_row], pairs.to[:-1][pair_of_row] + total_src)
+            picked = ops.gather_rows3(pts_c, ind, base.to(torch.int32))
+            # the side that is NOT gathered is simply that pair's full cloud, in order
+            local = torch.arange(pairs.total_out, device=dev) - pairs.oo[:-1][pair_of_row]
+            other_base = torch.where(from_src, pairs.to[:-1][pair_of_row] + total_src, pairs.so[:-1][pair_of_row])
+            other = pts_c[(other_base + local).long()]
+            a = torch.where(from_src[:, None], picked, other)  # source-side points
+            b = torch.where(from_src[:, None], other, picked)  # target-side points
+            pose = ops.weighted_procrustes(a, b, val, pairs.oo)
+            src_pts_list = [a[pairs.h_oo[p]:pairs.h_oo[p + 1]] for p in range(P)]
+            tgt_pts_list = [b[pairs.h_oo[p]:pairs.h_oo[p + 1]] for p in range(P)]
+        return pose, attn_list, val_list, ind_list, src_pts_list, tgt_pts_list

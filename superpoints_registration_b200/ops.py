@@ -1,0 +1,262 @@
+"""Functional wrappers: torch CUDA tensors in, torch CUDA tensors out, every byte of compute in libspr_b200.so.
+
+PyTorch is used here for device memory (allocation through its caching allocator) and for the current
+stream only.  Inputs must already live on a CUDA device: there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the B200 hot path has no CPU fallback")
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    _need_cuda(t, name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _i32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    _need_cuda(t, name)
+    if t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    return t.contiguous()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------
+# preprocessing
+# ------------------------------------------------------------------------------------------------
+
+def grid_subsample_batch(points: torch.Tensor, lengths: torch.Tensor, sample_dl: float
+                         ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Barycentre voxel subsampling of stacked clouds. -> (points f32[M,3], lengths i32[B]) on device.
+
+    One host synchronisation (reading M), as in the reference where the lengths come back as a NumPy array
+    (cpp_subsampling/wrapper.cpp:300-322).
+    """
+    L = _lib.lib()
+    pts = _f32c(points, "points")
+    lens = _i32c(lengths, "lengths")
+    n, b = pts.shape[0], lens.shape[0]
+    if pts.dim() != 2 or pts.shape[1] != 3:
+        raise RuntimeError("points must have shape (N, 3)")
+    out = torch.empty((max(n, 1), 3), dtype=torch.float32, device=pts.device)
+    meta = torch.empty(b + 1, dtype=torch.int32, device=pts.device)  # [lengths..., total]
+    wsb = L.spr_grid_subsample_workspace_bytes(n, b)
+    ws = _ws(wsb, pts.device)
+    rc = L.spr_grid_subsample_batch(pts.data_ptr(), lens.data_ptr(), n, b, float(sample_dl), out.data_ptr(),
+                                    meta.data_ptr(), meta.data_ptr() + 4 * b, ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "spr_grid_subsample_batch")
+    m = int(meta[b].item())
+    return out[:m], meta[:b]
+
+
+class CellGrid:
+    """Supports binned into a uniform cell list; answers radius queries (spr_cell_grid_build / spr_radius_query)."""
+
+    def __init__(self, supports: torch.Tensor, s_lengths: torch.Tensor, radius: float):
+        L = _lib.lib()
+        self.supports = _f32c(supports, "supports")
+        self.s_lengths = _i32c(s_lengths, "s_lengths")
+        self.radius = float(radius)
+        self.ns, self.b = self.supports.shape[0], self.s_lengths.shape[0]
+        self.ws = _ws(L.spr_cell_grid_workspace_bytes(self.ns, self.b), self.supports.device)
+        rc = L.spr_cell_grid_build(self.supports.data_ptr(), self.s_lengths.data_ptr(), self.ns, self.b, self.radius,
+                                   self.ws.data_ptr(), self.ws.numel(), _stream())
+        _lib.check(rc, "spr_cell_grid_build")
+
+    def query(self, queries: torch.Tensor, q_lengths: torch.Tensor, limit: int, radius: Optional[float] = None,
+              index_dtype: torch.dtype = torch.int64) -> Tuple[torch.Tensor, torch.Tensor]:
+        """-> (idx [Nq, limit] index_dtype, max_count i32[1] on device)."""
+        L = _lib.lib()
+        q = _f32c(queries, "queries")
+        ql = _i32c(q_lengths, "q_lengths")
+        if ql.shape[0] != self.b:
+            raise RuntimeError("q_batches and s_batches must have the same length")
+        r = self.radius if radius is None else float(radius)
+        if r > self.radius * (1 + 1e-6):
+            raise RuntimeError("query radius larger than the radius the grid was built for")
+        nq = q.shape[0]
+        idx = torch.empty((nq, limit), dtype=index_dtype, device=q.device)
+        mc = torch.empty(1, dtype=torch.int32, device=q.device)
+        rc = L.spr_radius_query(q.data_ptr(), ql.data_ptr(), nq, self.b, self.ws.data_ptr(), self.ns, r, int(limit),
+                                idx.data_ptr(), 1 if index_dtype == torch.int64 else 0, int(limit), mc.data_ptr(),
+                                _stream())
+        _lib.check(rc, "spr_radius_query")
+        return idx, mc
+
+
+def radius_neighbors_batch(queries, supports, q_lengths, s_lengths, radius: float, limit: int,
+                           index_dtype: torch.dtype = torch.int64):
+    grid = CellGrid(supports, s_lengths, radius)
+    return grid.query(queries, q_lengths, limit, index_dtype=index_dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# KPConv and the block epilogues
+# ------------------------------------------------------------------------------------------------
+
+def _idx_arg(idx: torch.Tensor):
+    _need_cuda(idx, "neighb_inds")
+    if idx.dtype not in (torch.int64, torch.int32):
+        idx = idx.long()
+    if idx.dim() != 2:
+        raise RuntimeError("neighb_inds must be 2-D")
+    if idx.stride(1) != 1:
+        idx = idx.contiguous()
+    return idx, (1 if idx.dtype == torch.int64 else 0), idx.stride(0), idx.shape[1]
+
+
+def kpconv_forward(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent: float, mode: int = 0):
+    L = _lib.lib()
+    q, s, xx = _f32c(q_pts, "q_pts"), _f32c(s_pts, "s_pts"), _f32c(x, "x")
+    w, kp = _f32c(weights, "weights"), _f32c(kernel_points, "kernel_points")
+    idx, is64, stride, H = _idx_arg(neighb_inds)
+    nq, ns = q.shape[0], s.shape[0]
+    K, cin, cout = w.shape
+    if xx.shape[0] != ns or xx.shape[1] != cin:
+        raise RuntimeError(f"x must have shape ({ns}, {cin}), got {tuple(xx.shape)}")
+    if idx.shape[0] != nq:
+        raise RuntimeError("neighb_inds must have one row per query point")
+    out = torch.empty((nq, cout), dtype=torch.float32, device=q.device)
+    ws = _ws(L.spr_kpconv_workspace_bytes(nq, ns, cin, cout, K), q.device)
+    rc = L.spr_kpconv_forward(q.data_ptr(), s.data_ptr(), idx.data_ptr(), is64, stride, H, xx.data_ptr(), cin,
+                              w.data_ptr(), cout, kp.data_ptr(), K, float(extent), out.data_ptr(), nq, ns, int(mode),
+                              ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "spr_kpconv_forward")
+    return out
+
+
+def instance_norm_lrelu(x, lengths, eps: float = 1e-5, slope: float = 1.0, residual=None, out=None):
+    """y = LeakyReLU_slope(InstanceNorm_per_cloud(x) [+ residual]);  slope=1 -> no activation."""
+    L = _lib.lib()
+    xx = _f32c(x, "x")
+    lens = _i32c(lengths, "stack_lengths")
+    n, c = xx.shape
+    res = None if residual is None else _f32c(residual, "residual")
+    if out is None:
+        out = torch.empty_like(xx)
+    ws = _ws(L.spr_instance_norm_workspace_bytes(n, lens.shape[0], c), xx.device)
+    rc = L.spr_instance_norm_lrelu(xx.data_ptr(), lens.data_ptr(), n, lens.shape[0], c, float(eps), float(slope),
+                                   _ptr(res), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "spr_instance_norm_lrelu")
+    return out
+
+
+def max_pool(x, inds):
+    L = _lib.lib()
+    xx = _f32c(x, "x")
+    idx, is64, stride, H = _idx_arg(inds)
+    nq, (ns, c) = idx.shape[0], xx.shape
+    out = torch.empty((nq, c), dtype=torch.float32, device=xx.device)
+    rc = L.spr_max_pool(xx.data_ptr(), idx.data_ptr(), is64, stride, H, nq, ns, c, out.data_ptr(), _stream())
+    _lib.check(rc, "spr_max_pool")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# matching and pose
+# ------------------------------------------------------------------------------------------------
+
+class PackedPairs:
+    """Offsets describing P pairs packed back to back: src rows, tgt rows, N_p x M_p matrices, outputs."""
+
+    def __init__(self, src_lens, tgt_lens, device):
+        self.src_lens = [int(v) for v in src_lens]
+        self.tgt_lens = [int(v) for v in tgt_lens]
+        self.P = len(self.src_lens)
+        so, to, co, oo = [0], [0], [0], [0]
+        for n, m in zip(self.src_lens, self.tgt_lens):
+            so.append(so[-1] + n)
+            to.append(to[-1] + m)
+            co.append(co[-1] + n * m)
+            oo.append(oo[-1] + (m if n > m else n))
+        self.total_src, self.total_tgt, self.total_corr, self.total_out = so[-1], to[-1], co[-1], oo[-1]
+        self.max_n, self.max_m = max(self.src_lens), max(self.tgt_lens)
+        self.h_so, self.h_to, self.h_co, self.h_oo = so, to, co, oo
+        self.so = torch.tensor(so, dtype=torch.int32, device=device)
+        self.to = torch.tensor(to, dtype=torch.int32, device=device)
+        self.co = torch.tensor(co, dtype=torch.int64, device=device)
+        self.oo = torch.tensor(oo, dtype=torch.int32, device=device)
+
+
+def dual_softmax_match(src_feats, tgt_feats, pairs: PackedPairs, want_attn: bool = False):
+    """-> corr (packed), attn (packed or None), val f32[total_out], ind i64[total_out]."""
+    L = _lib.lib()
+    s, t = _f32c(src_feats, "src_feats"), _f32c(tgt_feats, "tgt_feats")
+    D = s.shape[1]
+    dev = s.device
+    corr = torch.empty(pairs.total_corr, dtype=torch.float32, device=dev)
+    attn = torch.empty(pairs.total_corr, dtype=torch.float32, device=dev) if want_attn else None
+    val = torch.empty(pairs.total_out, dtype=torch.float32, device=dev)
+    ind = torch.empty(pairs.total_out, dtype=torch.int64, device=dev)
+    ws = _ws(L.spr_match_workspace_bytes(pairs.total_src, pairs.total_tgt, pairs.P), dev)
+    rc = L.spr_dual_softmax_match(s.data_ptr(), t.data_ptr(), pairs.so.data_ptr(), pairs.to.data_ptr(),
+                                  pairs.co.data_ptr(), pairs.oo.data_ptr(), pairs.P, pairs.total_src, pairs.total_tgt, D,
+                                  pairs.max_n, pairs.max_m, corr.data_ptr(), _ptr(attn), val.data_ptr(), ind.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "spr_dual_softmax_match")
+    return corr, attn, val, ind
+
+
+def sinkhorn_weighted_targets(corr, pairs: PackedPairs, tgt_xyz, softplus_alpha: float, exp_beta: float, n_iters: int,
+                              slack: bool = True):
+    """-> weighted_tgt f32[total_src,3], weights f32[total_src]."""
+    L = _lib.lib()
+    txyz = _f32c(tgt_xyz, "tgt_xyz")
+    dev = txyz.device
+    wt = torch.empty((pairs.total_src, 3), dtype=torch.float32, device=dev)
+    w = torch.empty(pairs.total_src, dtype=torch.float32, device=dev)
+    ws = _ws(L.spr_sinkhorn_workspace_bytes(pairs.total_src, pairs.total_tgt, pairs.P), dev)
+    rc = L.spr_sinkhorn_weighted_targets(corr.data_ptr(), pairs.co.data_ptr(), pairs.so.data_ptr(), pairs.to.data_ptr(),
+                                         pairs.P, pairs.total_src, pairs.total_tgt, pairs.max_n, pairs.max_m,
+                                         txyz.data_ptr(), float(softplus_alpha), float(exp_beta), int(n_iters),
+                                         1 if slack else 0, wt.data_ptr(), w.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         _stream())
+    _lib.check(rc, "spr_sinkhorn_weighted_targets")
+    return wt, w
+
+
+def weighted_procrustes(a, b, w, offsets: torch.Tensor) -> torch.Tensor:
+    """Packed correspondences -> poses f32[P,3,4]."""
+    L = _lib.lib()
+    aa, bb = _f32c(a, "a"), _f32c(b, "b")
+    ww = None if w is None else _f32c(w, "weights")
+    offs = _i32c(offsets, "offsets")
+    P = offs.shape[0] - 1
+    out = torch.empty((P, 3, 4), dtype=torch.float32, device=aa.device)
+    rc = L.spr_weighted_procrustes(aa.data_ptr(), bb.data_ptr(), _ptr(ww), offs.data_ptr(), P, out.data_ptr(), _stream())
+    _lib.check(rc, "spr_weighted_procrustes")
+    return out
+
+
+def gather_rows3(src, ind, row_base) -> torch.Tensor:
+    L = _lib.lib()
+    s = _f32c(src, "src")
+    _need_cuda(ind, "ind")
+    ii = ind.long().contiguous()
+    rb = _i32c(row_base, "row_base")
+    out = torch.empty((ii.shape[0], 3), dtype=torch.float32, device=s.device)
+    rc = L.spr_gather_rows3(s.data_ptr(), ii.data_ptr(), rb.data_ptr(), ii.shape[0], out.data_ptr(), _stream())
+    _lib.check(rc, "spr_gather_rows3")
+    return out

@@ -1,0 +1,247 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference.
+
+Run in the authoring container only (needs /root/reference):
+    python tests/golden/make_golden.py
+What runs: the reference's own PyTorch modules imported from /root/reference/src (oracle/ref_torch.py) with
+its own C++ preprocessing core compiled in place (oracle/_ref).  Nothing from superpoints_registration_b200 or
+from the C/NumPy restatement is involved, so these files pin both our oracle and our CUDA path.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import oracle  # noqa: E402
+from oracle import ref_torch  # noqa: E402
+from superpoints_registration_b200 import synthetic  # noqa: E402  (data generator only)
+from weights import filled_state  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def t2n(t):
+    return t.detach().cpu().numpy()
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def load_weights(model, seed):
+    sd = model.state_dict()
+    shapes = {k: tuple(v.shape) for k, v in sd.items()}
+    vals = filled_state(shapes, seed)
+    new = {k: (torch.from_numpy(vals[k]) if k in vals else v) for k, v in sd.items()}
+    model.load_state_dict(new)
+    return {k: t2n(v) for k, v in sd.items() if k.endswith("kernel_points")}
+
+
+def pyramid_arrays(meta, prefix=""):
+    out = {}
+    for key in ("points", "neighbors", "pools", "upsamples", "stack_lengths"):
+        for l, t in enumerate(meta[key]):
+            a = t2n(t)
+            if a.dtype == np.int64 and key != "stack_lengths":
+                a = a.astype(np.int32)
+            out[f"{prefix}{key}_{l}"] = a
+    out[f"{prefix}n_levels"] = np.asarray(len(meta["points"]))
+    return out
+
+
+def gen_preprocess(ref):
+    cases = [
+        ("3dmatch", "qk_regtr_full_3dmatch.yaml", synthetic.make_batch("3dmatch", 1, seed=11, n_points=1200)),
+        ("kitti", "qk_regtr_full_kitti.yaml", synthetic.make_batch("kitti", 1, seed=12, n_points=800)),
+        ("modelnet", "qk_regtr_full_modelnet.yaml", synthetic.make_batch("modelnet", 2, seed=13)),
+    ]
+    for name, yaml_name, data in cases:
+        cfg = ref_torch.load_cfg(yaml_name)
+        pre = ref.kpconv.Preprocessor(cfg)
+        clouds = [torch.from_numpy(c) for c in data["src_xyz"] + data["tgt_xyz"]]
+        meta = pre(clouds)
+        arrays = pyramid_arrays(meta)
+        arrays["n_clouds"] = np.asarray(len(clouds))
+        for i, c in enumerate(clouds):
+            arrays[f"cloud_{i}"] = t2n(c)
+        save(f"preprocess_{name}.npz", **arrays)
+
+
+def gen_kpconv(ref):
+    """Single KPConv layers (reference module) on a reference pyramid."""
+    cfg = ref_torch.load_cfg("qk_regtr_full_3dmatch.yaml")
+    data = synthetic.make_batch("3dmatch", 1, seed=21, n_points=300)
+    clouds = [torch.from_numpy(c) for c in data["src_xyz"] + data["tgt_xyz"]]
+    meta = ref.kpconv.Preprocessor(cfg)(clouds)
+    arrays = {}
+    torch.manual_seed(5)
+    np.random.seed(5)
+    specs = [  # (tag, level, strided, cin, cout)
+        ("c1", 0, False, 1, 64), ("c32", 0, False, 32, 32), ("c32s", 0, True, 32, 32), ("c64", 1, False, 64, 64),
+        ("c128", 2, False, 128, 128),
+    ]
+    for tag, lvl, strided, cin, cout in specs:
+        r = cfg.first_subsampling_dl * cfg.conv_radius * 2 ** lvl
+        extent = r * cfg.KP_extent / cfg.conv_radius
+        with ref_torch.ref_cwd():
+            conv = ref.kpconv_blocks.KPConv(cfg.num_kernel_points, 3, cin, cout, extent, r)
+        # weights come from the shared deterministic filler (kept out of the fixture): seed = 100 + cin
+        wname = f"{tag}.KPConv.weights"
+        conv.weights.data.copy_(torch.from_numpy(filled_state({wname: (15, cin, cout)}, 100 + cin)[wname]))
+        if strided:
+            q, s, idx = meta["points"][lvl + 1], meta["points"][lvl], meta["pools"][lvl]
+        else:
+            q, s, idx = meta["points"][lvl], meta["points"][lvl], meta["neighbors"][lvl]
+        if cin == 1:
+            x = torch.ones(s.shape[0], 1)
+        else:
+            # leaky-relu'd normal features: mixed signs, some rows with a non-positive sum (exercises neighbor_num)
+            x = torch.nn.functional.leaky_relu(torch.randn(s.shape[0], cin) + 0.15, 0.1)
+        with torch.no_grad():
+            out = conv(q, s, idx, x)
+        arrays.update({f"{tag}_q": t2n(q), f"{tag}_s": t2n(s), f"{tag}_idx": t2n(idx).astype(np.int32), f"{tag}_x": t2n(x),
+                       f"{tag}_kp": t2n(conv.kernel_points),
+                       f"{tag}_extent": np.asarray(extent, np.float32), f"{tag}_out": t2n(out)})
+    arrays["tags"] = np.asarray([s[0] for s in specs])
+    save("kpconv_layers.npz", **arrays)
+
+
+def gen_blocks(ref):
+    """UnaryBlock-style instance norm and max_pool from the reference modules."""
+    torch.manual_seed(6)
+    lens = torch.tensor([300, 2, 211, 64], dtype=torch.int32)
+    n = int(lens.sum())
+    x = torch.randn(n, 64) * 2 + 0.3
+    bn = ref.kpconv_blocks.BatchNormBlock(64, True, 0.02)
+    with torch.no_grad():
+        y = bn(x, lens)
+    idx = torch.randint(0, n + 1, (150, 12))
+    mp = ref.kpconv_blocks.max_pool(x, idx)
+    save("blocks.npz", x=t2n(x), lens=t2n(lens), inorm=t2n(y), pool_idx=t2n(idx).astype(np.int32), pool_out=t2n(mp))
+
+
+def gen_pose(ref):
+    rng = np.random.default_rng(31)
+    arrays = {}
+    cases = []
+    for i, (n, scale, kind) in enumerate([(500, 1.0, "generic"), (60, 60.0, "kitti_scale"), (300, 1.0, "planar"),
+                                          (3, 1.0, "minimal"), (200, 1.0, "reflection"), (100, 1.0, "unweighted")]):
+        a = rng.normal(size=(n, 3)) * scale
+        if kind == "planar":
+            a[:, 2] = 0.3
+        R = synthetic._random_rotation(rng, 170.0)
+        t = rng.normal(size=3) * scale
+        b = a @ R.T + t + rng.normal(size=(n, 3)) * 0.01 * scale
+        if kind == "reflection":
+            b = b * np.array([1, 1, -1.0])  # best orthogonal map is a reflection -> exercises the det<=0 branch
+        w = rng.uniform(0, 1, size=n)
+        if kind == "kitti_scale":
+            a += np.array([40.0, -25.0, 1.0])
+        a32, b32, w32 = a.astype(np.float32), b.astype(np.float32), w.astype(np.float32)
+        with torch.no_grad():
+            T = ref.se3_torch.compute_rigid_transform(torch.from_numpy(a32), torch.from_numpy(b32),
+                                                      None if kind == "unweighted" else torch.from_numpy(w32))
+        arrays[f"a_{i}"], arrays[f"b_{i}"], arrays[f"w_{i}"], arrays[f"T_{i}"] = a32, b32, w32, t2n(T)
+        cases.append(kind)
+    arrays["kinds"] = np.asarray(cases)
+    # batched call ([B, N, 3]) as used at se3_torch.py:231
+    a = rng.normal(size=(4, 120, 3)).astype(np.float32)
+    b = rng.normal(size=(4, 120, 3)).astype(np.float32)
+    w = rng.uniform(0, 1, size=(4, 120)).astype(np.float32)
+    with torch.no_grad():
+        T = ref.se3_torch.compute_rigid_transform(torch.from_numpy(a), torch.from_numpy(b), torch.from_numpy(w))
+    arrays.update(batched_a=a, batched_b=b, batched_w=w, batched_T=t2n(T))
+    save("procrustes.npz", **arrays)
+
+
+def gen_matching(ref):
+    """softmax_correlation of the reference model on synthetic conditioned features, both N > M and N <= M,
+    with the 3DMatch (Sinkhorn) and the KITTI/ModelNet (argmax + Procrustes) settings."""
+    rng = np.random.default_rng(41)
+    arrays = {}
+    for tag, yaml_name in (("sinkhorn", "qk_regtr_full_3dmatch.yaml"), ("argmax", "qk_regtr_full_kitti.yaml")):
+        cfg = ref_torch.load_cfg(yaml_name)
+        model = ref_torch.build_model(cfg, seed=0)
+        shapes = [(95, 70), (60, 101), (33, 33)]
+        src_f, tgt_f, src_xyz, tgt_xyz = [], [], [], []
+        for n, m in shapes:
+            # structured features: tgt rows are noisy copies of a subset of src rows so that matches are meaningful
+            base = rng.normal(size=(max(n, m), 256)).astype(np.float32) * 2.0
+            sf = base[:n] + 0.1 * rng.normal(size=(n, 256)).astype(np.float32)
+            tf = base[rng.permutation(max(n, m))[:m]] + 0.1 * rng.normal(size=(m, 256)).astype(np.float32)
+            src_f.append(torch.from_numpy(sf)[None])
+            tgt_f.append(torch.from_numpy(tf)[None])
+            src_xyz.append(torch.from_numpy(rng.normal(size=(n, 3)).astype(np.float32)))
+            tgt_xyz.append(torch.from_numpy(rng.normal(size=(m, 3)).astype(np.float32)))
+        with torch.no_grad():
+            pose, attn, val, ind, sp, tp = model.softmax_correlation(src_f, tgt_f, src_xyz, tgt_xyz, None, None)
+        arrays[f"{tag}_alpha"] = t2n(model.alpha)
+        arrays[f"{tag}_beta"] = t2n(model.beta)
+        arrays[f"{tag}_pose"] = t2n(pose)
+        for i in range(len(shapes)):
+            arrays[f"{tag}_src_f_{i}"] = t2n(src_f[i][0])
+            arrays[f"{tag}_tgt_f_{i}"] = t2n(tgt_f[i][0])
+            arrays[f"{tag}_src_xyz_{i}"] = t2n(src_xyz[i])
+            arrays[f"{tag}_tgt_xyz_{i}"] = t2n(tgt_xyz[i])
+            arrays[f"{tag}_attn_{i}"] = t2n(attn[i][0]).astype(np.float32)
+            arrays[f"{tag}_val_{i}"] = t2n(val[i])
+            arrays[f"{tag}_ind_{i}"] = t2n(ind[i])
+        arrays[f"{tag}_n_pairs"] = np.asarray(len(shapes))
+    save("matching.npz", **arrays)
+
+
+def gen_forward(ref):
+    """Encoder features and the full forward of the reference model (weights from tests/golden/weights.py)."""
+    for tag, yaml_name, data in (
+            ("3dmatch", "qk_regtr_full_3dmatch.yaml", synthetic.make_batch("3dmatch", 2, seed=51, n_points=800)),
+            ("modelnet", "qk_regtr_full_modelnet.yaml", synthetic.make_batch("modelnet", 1, seed=52))):
+        cfg = ref_torch.load_cfg(yaml_name)
+        model = ref_torch.build_model(cfg, seed=0)
+        kps = load_weights(model, seed=1234)
+        batch = {"src_xyz": [torch.from_numpy(c) for c in data["src_xyz"]],
+                 "tgt_xyz": [torch.from_numpy(c) for c in data["tgt_xyz"]]}
+        with torch.no_grad():
+            out = model(batch)
+            meta = batch["kpconv_meta"]
+            feats0 = torch.ones_like(meta["points"][0][:, 0:1])
+            enc, _ = model.kpf_encoder(feats0, meta)
+        arrays = pyramid_arrays(meta, prefix="meta_")
+        arrays.update({f"kp::{k}": v for k, v in kps.items()})
+        B = len(batch["src_xyz"])
+        for i in range(B):
+            arrays[f"src_{i}"] = data["src_xyz"][i]
+            arrays[f"tgt_{i}"] = data["tgt_xyz"][i]
+            arrays[f"src_feat_{i}"] = t2n(out["src_feat"][i][0])
+            arrays[f"tgt_feat_{i}"] = t2n(out["tgt_feat"][i][0])
+            arrays[f"val_{i}"] = t2n(out["overlap_prob_list"][i])
+            arrays[f"ind_{i}"] = t2n(out["ind_list"][i])
+        if tag == "3dmatch":
+            arrays["encoder_out"] = t2n(enc)
+        arrays["pose"] = t2n(out["pose"])
+        arrays["n_pairs"] = np.asarray(B)
+        arrays["weight_seed"] = np.asarray(1234)
+        save(f"forward_{tag}.npz", **arrays)
+
+
+def main():
+    oracle.build()
+    ref = ref_torch.load()
+    gen_preprocess(ref)
+    gen_kpconv(ref)
+    gen_blocks(ref)
+    gen_pose(ref)
+    gen_matching(ref)
+    gen_forward(ref)
+
+
+if __name__ == "__main__":
+    main()

@@ -231,7 +231,7 @@ def test_pyramid_full_size_properties():
         r2 = np.float32(r) * np.float32(r)
         assert np.all(d2[valid] < r2)                                     # every neighbour is inside the radius
         assert np.all(idx[rows][:, 0] == rows)                            # nearest neighbour of a point is itself
-        assert np.all(np.diff(np.where(valid, d2, np.inf), axis=1) >= 0)  # ascending distances, padding last
+        assert np.all(np.diff(np.where(valid, d2, np.float32(1e30)), axis=1) >= 0)  # ascending distances, padding last
         same_cloud = cloud[np.minimum(idx[rows], n - 1)] == cloud[rows][:, None]
         assert np.all(same_cloud | ~valid)                                # neighbours never cross clouds
         # exact counts against a brute force on a few rows

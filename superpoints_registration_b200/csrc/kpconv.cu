@@ -16,6 +16,8 @@
 // Nothing but q, s, idx, x, W are read and out written: no intermediate ever reaches global memory.
 #include "spr_common.cuh"
 
+#include <cstdlib>
+
 namespace spr {
 namespace {
 
@@ -52,6 +54,18 @@ __device__ __forceinline__ float influence(float cx, float cy, float cz, float k
   const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
   const float v = 1.f - __fdiv_rn(__fsqrt_rn(d2), extent);
   return fmaxf(v, 0.f);
+}
+
+// Same quantity on the fast path of the fused kernel: FMA-contracted distance, MUFU.RSQ square root and a
+// multiplication by 1/extent.  Differs from the exactly-rounded expression by a few ulp of the influence
+// (<= ~3e-7 absolute on values in [0,1]), far inside the feature tolerance, and costs ~10 instructions
+// instead of ~28 (IEEE sqrt and division are multi-instruction sequences).
+__device__ __forceinline__ float influence_fast(float cx, float cy, float cz, float kx, float ky, float kz,
+                                                float inv_extent) {
+  const float dx = cx - kx, dy = cy - ky, dz = cz - kz;
+  const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  const float d = d2 * rsqrtf(fmaxf(d2, 1e-30f));
+  return fmaxf(fmaf(-d, inv_extent, 1.f), 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -110,26 +124,33 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------
 // main fused kernel, Cin = Cout = C in {32, 64, 128, 256}
 // ---------------------------------------------------------------------------------------------
-template <int C>
+// V selects the tile shape: V = 0 -> one big CTA per SM (TQ rows, 512 threads for C >= 64),
+//                           V = 1 -> half-size tiles, 256 threads, two CTAs per SM (phases of different CTAs overlap).
+template <int C, int V>
 struct Cfg {
   static constexpr int CT = C > 128 ? 128 : C;       // channels per pass
   static constexpr int PASSES = C / CT;
   static constexpr int CPL = CT / 32;                 // channels per lane in phase 1
-  static constexpr int TQ = CT == 128 ? 16 : 32;      // queries per tile
+  static constexpr int TQ0 = CT == 128 ? 16 : 32;
+  static constexpr int TQ = V == 0 ? TQ0 : TQ0 / 2;   // queries per tile
   static constexpr int KC = KP * CT;                  // contraction length per pass
   static constexpr int AS = KC + 4;                   // A row stride (floats)
-  static constexpr int THREADS = 256;
+  static constexpr int THREADS = (V == 0 && C >= 64) ? 512 : 256;
+  static constexpr int MIN_BLOCKS = (V == 1 || C == 32) ? 2 : 1;
+  static constexpr int UNROLL = CPL >= 4 ? 4 : 8;     // neighbour rows in flight per warp in phase 1b
   static constexpr int WARPS = THREADS / 32;
-  static constexpr int RQ = 8, RC = 4;                // phase-2 register tile
+  static constexpr int RQ = (C == 32 && V == 1) ? 4 : 8, RC = 4;  // phase-2 register tile
   static constexpr int TILE_THREADS = (TQ / RQ) * (C / RC);
   static constexpr int G = THREADS / TILE_THREADS;    // split-K groups
   static constexpr int KC_G = KC / G;
+  static_assert(TQ % RQ == 0, "tile rows");
   static_assert(TILE_THREADS <= THREADS && THREADS % TILE_THREADS == 0, "tile/threads mismatch");
   static_assert(KC % G == 0 && KC_G % 4 == 0, "split-K must be a multiple of 4");
   static constexpr size_t SMEM_A = (size_t)TQ * AS * 4;
   static constexpr size_t SMEM_W = (size_t)WARPS * 32 * kWStride * 4;
   static constexpr size_t SMEM_RED = (size_t)G * TQ * C * 4;
-  static constexpr size_t SMEM = (SMEM_A > SMEM_RED ? SMEM_A : SMEM_RED) + SMEM_W + 64 * 4 + KP * 3 * 4 + 64;
+  static constexpr size_t SMEM_J = (size_t)WARPS * 32 * 4;
+  static constexpr size_t SMEM = (SMEM_A > SMEM_RED ? SMEM_A : SMEM_RED) + SMEM_W + SMEM_J + 64 * 4 + KP * 3 * 4 + 64;
 };
 
 template <int CPL>
@@ -157,28 +178,52 @@ struct VecLoad<4> {
   }
 };
 
-template <int C, typename IdxT>
-__global__ void __launch_bounds__(Cfg<C>::THREADS, 1)
+template <int C, int V, typename IdxT>
+__global__ void __launch_bounds__(Cfg<C, V>::THREADS, Cfg<C, V>::MIN_BLOCKS)
     k_kpconv_fused(const float* __restrict__ q, const float* __restrict__ s, const IdxT* __restrict__ idx,
                    int row_stride, int H, const float* __restrict__ x, const float* __restrict__ w,
                    const float* __restrict__ kp, const unsigned char* __restrict__ rowflag, float extent,
                    float* __restrict__ out, int nq, int ns, int n_tiles) {
-  using K = Cfg<C>;
+  using K = Cfg<C, V>;
   constexpr int CT = K::CT, CPL = K::CPL, TQ = K::TQ, AS = K::AS, G = K::G, RQ = K::RQ, RC = K::RC;
+  constexpr int QROWS = TQ / RQ;  // thread rows of the phase-2 tile; a thread owns rows ty, ty+QROWS, ...
+  const float inv_extent = 1.0f / extent;
   extern __shared__ __align__(16) float smem[];
   float* sA = smem;                                                          // [TQ][AS]   (aliased by the split-K reduction)
-  float* sW = smem + (K::SMEM_A > K::SMEM_RED ? K::SMEM_A : K::SMEM_RED) / 4;  // [WARPS][32][kWStride]
-  float* sInv = sW + K::WARPS * 32 * kWStride;                               // [TQ] 1/neighbour_num  (64 reserved)
+  float* sW = smem + (K::SMEM_A > K::SMEM_RED ? K::SMEM_A : K::SMEM_RED) / 4;  // [WARPS][32][kWStride] influences
+  int* sJ = reinterpret_cast<int*>(sW + K::WARPS * 32 * kWStride);           // [WARPS][32] compacted neighbour ids
+  float* sInv = reinterpret_cast<float*>(sJ + K::WARPS * 32);                // [TQ] 1/neighbour_num  (64 reserved)
   float* sKp = sInv + 64;                                                    // [KP*3]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < KP * 3; i += K::THREADS) sKp[i] = kp[i];
   __syncthreads();
   float* wbuf = sW + warp * 32 * kWStride;
+  int* jbuf = sJ + warp * 32;
 
   // phase-2 coordinates
   const int grp = tid / K::TILE_THREADS;
   const int tt = tid % K::TILE_THREADS;
   const int tx = tt % (C / RC), ty = tt / (C / RC);
+
+  // Software prefetch of the first neighbour round of this warp's FIRST query of the next tile: the index is
+  // requested before phase 2 and the support coordinates after it, so both global latencies are hidden behind
+  // the contraction of the current tile.
+  int pf_j = ns;
+  float pf_x = 0.f, pf_y = 0.f, pf_z = 0.f;
+  auto prefetch_idx = [&](int tile) {
+    pf_j = ns;
+    const int n = tile * TQ + warp;
+    if (tile < n_tiles && warp < TQ && n < nq && lane < H) pf_j = load_idx(idx + (size_t)n * row_stride + lane);
+  };
+  auto prefetch_xyz = [&]() {
+    if (pf_j >= 0 && pf_j < ns) {
+      pf_x = __ldg(s + 3 * (size_t)pf_j);
+      pf_y = __ldg(s + 3 * (size_t)pf_j + 1);
+      pf_z = __ldg(s + 3 * (size_t)pf_j + 2);
+    }
+  };
+  prefetch_idx(blockIdx.x);
+  prefetch_xyz();
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int q0 = tile * TQ;
@@ -203,45 +248,74 @@ __global__ void __launch_bounds__(Cfg<C>::THREADS, 1)
         if (n < nq) {
           const float qx = __ldg(q + 3 * (size_t)n), qy = __ldg(q + 3 * (size_t)n + 1),
                       qz = __ldg(q + 3 * (size_t)n + 2);
+          const bool use_pf = (ql == warp) && (pass == 0);
           for (int h0 = 0; h0 < H; h0 += 32) {
             const int h = h0 + lane;
             int j = ns;
-            if (h < H) j = load_idx(idx + (size_t)n * row_stride + h);
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            if (use_pf && h0 == 0) {
+              j = pf_j;
+              sx = pf_x;
+              sy = pf_y;
+              sz = pf_z;
+            } else {
+              if (h < H) j = load_idx(idx + (size_t)n * row_stride + h);
+              if (j >= 0 && j < ns) {
+                sx = __ldg(s + 3 * (size_t)j);
+                sy = __ldg(s + 3 * (size_t)j + 1);
+                sz = __ldg(s + 3 * (size_t)j + 2);
+              }
+            }
             const bool valid = j >= 0 && j < ns;
+            if (!__any_sync(kFull, valid)) break;  // rows are padded at the end: nothing valid from here on
             bool active = false;
+            float wv[16];
             if (valid) {
-              const float cx = __ldg(s + 3 * (size_t)j) - qx, cy = __ldg(s + 3 * (size_t)j + 1) - qy,
-                          cz = __ldg(s + 3 * (size_t)j + 2) - qz;
-              float wv[16];
+              const float cx = sx - qx, cy = sy - qy, cz = sz - qz;
 #pragma unroll
               for (int k = 0; k < KP; ++k) {
-                wv[k] = influence(cx, cy, cz, sKp[3 * k], sKp[3 * k + 1], sKp[3 * k + 2], extent);
+                wv[k] = influence_fast(cx, cy, cz, sKp[3 * k], sKp[3 * k + 1], sKp[3 * k + 2], inv_extent);
                 active |= wv[k] > 0.f;
               }
               wv[15] = 0.f;
-              float4* dst = reinterpret_cast<float4*>(wbuf + lane * kWStride);
+            }
+            nn += __popc(__ballot_sync(kFull, valid && rowflag[j] != 0));
+            const unsigned am = __ballot_sync(kFull, active);
+            const int na = __popc(am);
+            if (active) {  // compacted: slot = number of active lanes below this one
+              const int pos = __popc(am & ((1u << lane) - 1u));
+              float4* dst = reinterpret_cast<float4*>(wbuf + pos * kWStride);
               dst[0] = make_float4(wv[0], wv[1], wv[2], wv[3]);
               dst[1] = make_float4(wv[4], wv[5], wv[6], wv[7]);
               dst[2] = make_float4(wv[8], wv[9], wv[10], wv[11]);
               dst[3] = make_float4(wv[12], wv[13], wv[14], wv[15]);
+              jbuf[pos] = j;
             }
-            nn += __popc(__ballot_sync(kFull, valid && rowflag[j] != 0));
-            unsigned am = __ballot_sync(kFull, active);
             __syncwarp();
-            while (am) {
-              const int a = __ffs(am) - 1;
-              am &= am - 1;
-              const int ja = __shfl_sync(kFull, j, a);
-              float xv[CPL];
-              VecLoad<CPL>::ld(x + (size_t)ja * C + cbase + lane * CPL, xv);
-              const float4* wp = reinterpret_cast<const float4*>(wbuf + a * kWStride);
-              const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
-              const float wk[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
-                                    w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+            // Batches of UNROLL active neighbours: all feature-row loads of a batch are issued before the first
+            // FMA consumes one, so a warp keeps UNROLL independent L2 requests in flight.
+            for (int a0 = 0; a0 < na; a0 += K::UNROLL) {
+              float xv[K::UNROLL][CPL];
 #pragma unroll
-              for (int k = 0; k < KP; ++k)
+              for (int u = 0; u < K::UNROLL; ++u) {
+                if (a0 + u < na) {
+                  const int ja = jbuf[a0 + u];
+                  VecLoad<CPL>::ld(x + (size_t)ja * C + cbase + lane * CPL, xv[u]);
+                }
+              }
 #pragma unroll
-                for (int c = 0; c < CPL; ++c) acc[k][c] = fmaf(wk[k], xv[c], acc[k][c]);
+              for (int u = 0; u < K::UNROLL; ++u) {
+                if (a0 + u < na) {
+                  const float4* wp = reinterpret_cast<const float4*>(wbuf + (a0 + u) * kWStride);
+                  const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+                  const float wk[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
+                                        w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+                  for (int k = 0; k < KP; ++k)
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) acc[k][c] = fmaf(wk[k], xv[u][c], acc[k][c]);
+                }
+              }
             }
             __syncwarp();
           }
@@ -261,40 +335,53 @@ __global__ void __launch_bounds__(Cfg<C>::THREADS, 1)
         }
         if (pass == 0 && lane == 0) sInv[ql] = 1.f / (float)max(nn, 1);
       }
-      __syncthreads();
       // ------------------------------ phase 2 ------------------------------
+      // W[k][cin][cout] row-major: contraction row kc of this pass is global row (kc / CT) * C + cbase + kc % CT.
+      // Four consecutive kc never straddle a kernel point (CT % 4 == 0).  The W rows of step kk+4 are loaded
+      // while step kk is multiplied (register double buffer); the first step is requested before the barrier.
+      const int kc0 = grp * K::KC_G;
+      const float* wcol = w + (size_t)tx * RC;
+      auto wrow_ptr = [&](int kc) { return wcol + ((size_t)(kc / CT) * C + cbase + (kc % CT)) * C; };
+      float4 wn[4];
       {
-        const int kc0 = grp * K::KC_G;
-        const float* wrow = w + ((size_t)0) + (size_t)tx * RC;  // W[k][cin][cout] row-major: row (k*C + cin)
+        const float* wp = wrow_ptr(kc0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wn[i] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)i * C));
+      }
+      if (pass == K::PASSES - 1) prefetch_idx(tile + gridDim.x);
+      __syncthreads();
 #pragma unroll 2
-        for (int kk = 0; kk < K::KC_G; kk += 4) {
-          const int kc = kc0 + kk;                  // index inside this pass: k*CT + c
-          const int kidx = kc / CT, cc = kc % CT;   // 4 consecutive kc never straddle a kernel point (CT % 4 == 0)
-          const float* wp = wrow + ((size_t)kidx * C + cbase + cc) * C;
-          float4 wv[4];
+      for (int kk = 0; kk < K::KC_G; kk += 4) {
+        const int kc = kc0 + kk;
+        float4 wv[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) wv[i] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)i * C));
+        for (int i = 0; i < 4; ++i) wv[i] = wn[i];
+        if (kk + 4 < K::KC_G) {
+          const float* wp = wrow_ptr(kc + 4);
 #pragma unroll
-          for (int a = 0; a < RQ; ++a) {
-            const float4 av = *reinterpret_cast<const float4*>(sA + (ty * RQ + a) * AS + kc);
-            const float ar[4] = {av.x, av.y, av.z, av.w};
+          for (int i = 0; i < 4; ++i) wn[i] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)i * C));
+        }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              acc2[a][0] = fmaf(ar[i], wv[i].x, acc2[a][0]);
-              acc2[a][1] = fmaf(ar[i], wv[i].y, acc2[a][1]);
-              acc2[a][2] = fmaf(ar[i], wv[i].z, acc2[a][2]);
-              acc2[a][3] = fmaf(ar[i], wv[i].w, acc2[a][3]);
-            }
+        for (int a = 0; a < RQ; ++a) {
+          const float4 av = *reinterpret_cast<const float4*>(sA + (a * QROWS + ty) * AS + kc);
+          const float ar[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc2[a][0] = fmaf(ar[i], wv[i].x, acc2[a][0]);
+            acc2[a][1] = fmaf(ar[i], wv[i].y, acc2[a][1]);
+            acc2[a][2] = fmaf(ar[i], wv[i].z, acc2[a][2]);
+            acc2[a][3] = fmaf(ar[i], wv[i].w, acc2[a][3]);
           }
         }
       }
+      if (pass == K::PASSES - 1) prefetch_xyz();
       __syncthreads();  // A tile free for the next pass / the reduction
     }
     // ------------------------------ split-K reduction + epilogue ------------------------------
     float* sRed = smem;  // [G][TQ][C]
 #pragma unroll
     for (int a = 0; a < RQ; ++a)
-      *reinterpret_cast<float4*>(sRed + ((size_t)grp * TQ + ty * RQ + a) * C + tx * RC) =
+      *reinterpret_cast<float4*>(sRed + ((size_t)grp * TQ + a * QROWS + ty) * C + tx * RC) =
           make_float4(acc2[a][0], acc2[a][1], acc2[a][2], acc2[a][3]);
     __syncthreads();
     for (int e = tid; e < TQ * C / 4; e += K::THREADS) {
@@ -322,22 +409,39 @@ __global__ void __launch_bounds__(Cfg<C>::THREADS, 1)
   }
 }
 
-template <int C, typename IdxT>
+template <int C, int V, typename IdxT>
 int launch_fused(const float* q, const float* s, const void* idx, int row_stride, int H, const float* x, const float* w,
                  const float* kp, const unsigned char* rowflag, float extent, float* out, int nq, int ns,
                  cudaStream_t stream) {
-  using K = Cfg<C>;
+  using K = Cfg<C, V>;
   const int n_tiles = (nq + K::TQ - 1) / K::TQ;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    SPR_CUDA(cudaFuncSetAttribute(k_kpconv_fused<C, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+    SPR_CUDA(cudaFuncSetAttribute(k_kpconv_fused<C, V, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)K::SMEM));
     attr_set = true;
   }
-  const int grid = n_tiles;  // one tile per CTA; the hardware scheduler balances ragged tiles
-  k_kpconv_fused<C, IdxT><<<grid, K::THREADS, K::SMEM, stream>>>(q, s, static_cast<const IdxT*>(idx), row_stride, H, x,
-                                                                 w, kp, rowflag, extent, out, nq, ns, n_tiles);
+  // persistent CTAs: one (or MIN_BLOCKS) per SM, tiles dealt round-robin, so that the next tile's first loads
+  // can be prefetched behind the current tile's contraction
+  const int resident = kNumSMs * K::MIN_BLOCKS;
+  const int grid = n_tiles < resident ? n_tiles : resident;
+  k_kpconv_fused<C, V, IdxT><<<grid, K::THREADS, K::SMEM, stream>>>(q, s, static_cast<const IdxT*>(idx), row_stride, H,
+                                                                    x, w, kp, rowflag, extent, out, nq, ns, n_tiles);
   SPR_LAUNCH_CHECK("k_kpconv_fused");
   return SPR_OK;
+}
+
+// Tile-shape choice per channel count (measured on B200, profiles/): overridable for experiments with
+// SPR_KPCONV_VARIANT=<0|1>.
+int pick_variant(int c) {
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("SPR_KPCONV_VARIANT");
+    forced = e ? atoi(e) : -1;
+  }
+  if (forced >= 0) return forced;
+  (void)c;
+  return 0;
 }
 
 }  // namespace
@@ -399,18 +503,21 @@ extern "C" int spr_kpconv_forward(const float* d_q, const float* d_s, const void
   unsigned char* rowflag = static_cast<unsigned char*>(d_workspace);
   k_rowsum_flags<<<(ns + 1 + 7) / 8, 256, 0, stream>>>(d_x, ns, cin, rowflag);
   SPR_LAUNCH_CHECK("k_rowsum_flags");
-#define SPR_DISPATCH(CC)                                                                                          \
-  case CC:                                                                                                        \
-    return idx_is_64 ? launch_fused<CC, long long>(d_q, d_s, d_idx, row_stride, H, d_x, d_w, d_kp, rowflag, extent, \
-                                                   d_out, nq, ns, stream)                                         \
-                     : launch_fused<CC, int>(d_q, d_s, d_idx, row_stride, H, d_x, d_w, d_kp, rowflag, extent,     \
-                                             d_out, nq, ns, stream);
+#define SPR_DISPATCH2(CC, VV)                                                                                       \
+  (idx_is_64 ? launch_fused<CC, VV, long long>(d_q, d_s, d_idx, row_stride, H, d_x, d_w, d_kp, rowflag, extent, d_out, \
+                                               nq, ns, stream)                                                         \
+             : launch_fused<CC, VV, int>(d_q, d_s, d_idx, row_stride, H, d_x, d_w, d_kp, rowflag, extent, d_out, nq,   \
+                                         ns, stream))
+#define SPR_DISPATCH(CC) \
+  case CC:               \
+    return pick_variant(CC) == 1 ? SPR_DISPATCH2(CC, 1) : SPR_DISPATCH2(CC, 0);
   switch (cin) {
     SPR_DISPATCH(32)
     SPR_DISPATCH(64)
     SPR_DISPATCH(128)
     SPR_DISPATCH(256)
   }
+#undef SPR_DISPATCH2
 #undef SPR_DISPATCH
   return SPR_EUNSUPPORTED;
 }

@@ -451,10 +451,10 @@ using namespace spr;
 
 extern "C" size_t spr_kpconv_workspace_bytes(int nq, int ns, int cin, int cout, int n_kernel_points) {
   (void)nq;
-  (void)cin;
-  (void)cout;
   (void)n_kernel_points;
-  return align_up((size_t)(ns > 0 ? ns : 0) + 1, 256) + 256;
+  const size_t simt = align_up((size_t)(ns > 0 ? ns : 0) + 1, 256) + 256;
+  const size_t tc = cin == cout ? kpconv_tc_workspace_bytes(ns > 0 ? ns : 0, cin) : 0;
+  return simt > tc ? simt : tc;
 }
 
 extern "C" int spr_kpconv_forward(const float* d_q, const float* d_s, const void* d_idx, int idx_is_64, int row_stride,
@@ -471,7 +471,7 @@ extern "C" int spr_kpconv_forward(const float* d_q, const float* d_s, const void
     set_error("kpconv_forward: only %d kernel points are supported (got %d)", KP, n_kernel_points);
     return SPR_EUNSUPPORTED;
   }
-  if (mode != 0) {
+  if (mode != 0 && mode != 1) {
     set_error("kpconv_forward: mode %d not built in", mode);
     return SPR_EUNSUPPORTED;
   }
@@ -500,6 +500,9 @@ extern "C" int spr_kpconv_forward(const float* d_q, const float* d_s, const void
     set_error("kpconv_forward: workspace too small");
     return SPR_ENOSPACE;
   }
+  if (mode == 1)
+    return kpconv_tc_forward(d_q, d_s, d_idx, idx_is_64, row_stride, H, d_x, cin, d_w, d_kp, extent, d_out, nq, ns,
+                             d_workspace, stream);
   unsigned char* rowflag = static_cast<unsigned char*>(d_workspace);
   k_rowsum_flags<<<(ns + 1 + 7) / 8, 256, 0, stream>>>(d_x, ns, cin, rowflag);
   SPR_LAUNCH_CHECK("k_rowsum_flags");

@@ -1,0 +1,508 @@
+// kpconv_tc.cu -- fused KPConv forward with the (K*Cin) x Cout contraction on the Blackwell tensor cores
+// (tcgen05.mma, accumulators in tensor memory, weights streamed by the TMA engine).  mode 1 of
+// spr_kpconv_forward; same mathematics as kpconv.cu (reference: kpconv_blocks.py:269-414).
+//
+// Work decomposition (one persistent CTA per SM, 18 warps):
+//   warps 0-15  producers.  One warp per query and pass of 32 input channels:
+//                    wf[k][c] = sum_h infl[h][k] * x[idx[h]][c]
+//               is a 16 x H x 32 matrix product done with warp-level mma.sync (3xTF32 split operands, fp32
+//               accumulate); each lane evaluates exactly the influences of its A fragment and loads its B
+//               fragments as 16-byte pieces of the gathered feature rows, so nothing is staged or broadcast.
+//               The 15 x 32 block is split into fp16 (hi, lo) pairs and written to the A tile in shared memory
+//               (canonical K-major SWIZZLE_128B layout): row 2*ql holds hi, row 2*ql+1 holds lo, so a tile of
+//               up to 64 queries fills the M = 128 rows of one tcgen05.mma.
+//   warp 16     one thread issues the MMAs:  D[128 x 2C] += A[128 x 512] * B'[2C x 512]^T per pass of 32 input
+//               channels, B' = [W_hi | W_lo] (fp16 pairs of the fp32 weights), so that
+//                    out = hi*W_hi + hi*W_lo + lo*W_hi (+ lo*W_lo)
+//               carries ~22 significant bits per operand: fp32-level accuracy from fp16 tensor-core products
+//               accumulated in fp32.  D stays in TMEM across the C/32 passes of a tile.
+//   warp 17     one thread streams the pre-swizzled weight image through a 3-stage shared-memory ring with bulk
+//               async copies (TMA engine), completion on mbarriers.
+//   epilogue    producers read D with tcgen05.ld, add the hi/lo rows (adjacent lanes) and the two column
+//               halves, scale by 1/neighbour_count and store.
+// Operand scaling: fp16 has a 5-bit exponent, so wf is computed pre-multiplied by a power of two derived from
+// H*max|x| (kept <= 2^15) and W by one derived from max|W|; both are exact and undone in the epilogue.
+// Synchronisation is mbarrier-only in steady state: a_full (16 producer warps -> MMA), mma_done (MMA -> producers,
+// frees the A tile and publishes D), full/empty per ring stage.  The MMAs of pass p run while the producers
+// already gather and accumulate the first queries of pass p+1; they only wait before overwriting the A tile.
+#include "spr_common.cuh"
+#include "tc05.cuh"
+
+namespace spr {
+
+namespace {
+
+using namespace tc;
+
+constexpr int KP = 15;
+
+struct TcScales {
+  unsigned int amax_x_bits;  // max |x| as float bits (atomicMax on non-negative floats)
+  unsigned int amax_w_bits;
+};
+
+// power-of-two exponent e such that v * 2^e <= 2^target (v > 0 finite); 0 otherwise
+__device__ __forceinline__ int scale_exp(float v, int target) {
+  if (!(v > 0.f) || !isfinite(v)) return 0;
+  int ex;
+  frexpf(v, &ex);  // v = m * 2^ex, m in [0.5, 1)
+  int e = target - ex;
+  return e < -60 ? -60 : (e > 60 ? 60 : e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pre-pass 1: row-sum flags of x (the reference's neighbour_num mask, :409-412), max|x| and max|W|
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_flags_absmax(const float* __restrict__ x, int ns, int cin,
+                                                       unsigned char* __restrict__ flag, const float* __restrict__ w,
+                                                       int n_w, int n_xblocks, TcScales* __restrict__ sc) {
+  const int lane = threadIdx.x & 31;
+  if ((int)blockIdx.x >= n_xblocks) {  // weights
+    float m = 0.f;
+    for (int i = (blockIdx.x - n_xblocks) * blockDim.x + threadIdx.x; i < n_w; i += (gridDim.x - n_xblocks) * blockDim.x)
+      m = fmaxf(m, fabsf(w[i]));
+    m = warp_maxf(m);
+    if (lane == 0 && m > 0.f) atomicMax(&sc->amax_w_bits, __float_as_uint(m));
+    return;
+  }
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row > ns) return;
+  if (row == ns) {
+    if (lane == 0) flag[ns] = 0;
+    return;
+  }
+  float acc = 0.f, m = 0.f;
+  for (int c = lane; c < cin; c += 32) {
+    const float v = x[(size_t)row * cin + c];
+    acc += v;
+    m = fmaxf(m, fabsf(v));
+  }
+  acc = warp_sum(acc);
+  m = warp_maxf(m);
+  if (lane == 0) {
+    flag[row] = acc > 0.f ? 1 : 0;
+    if (m > 0.f) atomicMax(&sc->amax_x_bits, __float_as_uint(m));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pre-pass 2: weight image.  Block (pass, atom, sub) = NS rows x 128 B in the SWIZZLE_128B K-major layout the
+// MMA reads: row r <-> column n' = sub*NS + r of B' = [W_hi | W_lo], K element kk of the atom <-> kernel point
+// 2*atom + kk/32 (kernel point 15 is zero padding), input channel pass*32 + kk%32.  One thread per 16-byte chunk.
+// ---------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) k_weight_image(const float* __restrict__ w, const TcScales* __restrict__ sc,
+                                                       unsigned char* __restrict__ img) {
+  constexpr int NCOL = 2 * C, NS = NCOL < 128 ? NCOL : 128, NSUB = NCOL / NS;
+  constexpr int CHUNKS = (C / 32) * 8 * NSUB * NS * 8;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= CHUNKS) return;
+  const int j = t & 7;
+  const int r = (t >> 3) % NS;
+  const int blk = t / (8 * NS);
+  const int sub = blk % NSUB;
+  const int atom = (blk / NSUB) & 7;
+  const int pass = blk / (NSUB * 8);
+  const int ncol = sub * NS + r;
+  const bool lo_part = ncol >= C;
+  const int o = lo_part ? ncol - C : ncol;
+  const int k = atom * 2 + (j >> 2);  // kernel point of this chunk (15 = zero padding)
+  const float tscale = ldexpf(1.f, scale_exp(__uint_as_float(sc->amax_w_bits), 14));
+  __align__(16) __half h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int cin = pass * 32 + (j & 3) * 8 + e;
+    float v = 0.f;
+    if (k < KP) v = __ldg(w + ((size_t)k * C + cin) * C + o) * tscale;
+    const __half hi = __float2half_rn(v);
+    h[e] = lo_part ? __float2half_rn(v - __half2float(hi)) : hi;
+  }
+  *reinterpret_cast<uint4*>(img + (size_t)blk * (NS * 128) + sw128_offset(r, j)) = *reinterpret_cast<const uint4*>(h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+template <int C>
+struct TcCfg {
+  static constexpr int PASSES = C / 32;
+  static constexpr int NCOL = 2 * C;
+  static constexpr int NS = NCOL < 128 ? NCOL : 128;  // N of one MMA = rows of one ring stage
+  static constexpr int NSUB = NCOL / NS;
+  static constexpr int STAGE_BYTES = NS * 128;
+  static constexpr int NSTAGES = C == 32 ? 4 : 3;
+  static constexpr int BLOCKS_PER_PASS = 8 * NSUB;    // 8 K atoms of 64 fp16 per pass
+  static constexpr int TQ = 64;
+  static constexpr int WORKERS = 16;
+  static constexpr int THREADS = (WORKERS + 2) * 32;
+  static constexpr int A_ATOM_BYTES = 128 * 128;
+  static constexpr int A_BYTES = 8 * A_ATOM_BYTES;
+  static constexpr int WBUF_BYTES = 0;
+  static constexpr int TMEM_COLS = NCOL < 32 ? 32 : NCOL;
+  static constexpr int OFF_RING = A_BYTES;
+  static constexpr int OFF_WBUF = OFF_RING + NSTAGES * STAGE_BYTES;
+  static constexpr int OFF_MISC = OFF_WBUF + WBUF_BYTES;
+  static constexpr int MISC_BYTES = 16 * 8 + 16 + 2 * TQ * 4 + 48 * 4;
+  static constexpr size_t SMEM = 1024 + OFF_MISC + MISC_BYTES;
+  static constexpr size_t IMG_BYTES = (size_t)PASSES * BLOCKS_PER_PASS * STAGE_BYTES;
+};
+
+__device__ __forceinline__ float influence_fast(float cx, float cy, float cz, float kx, float ky, float kz,
+                                                float inv_extent) {
+  const float dx = cx - kx, dy = cy - ky, dz = cz - kz;
+  const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  const float d = d2 * rsqrtf(fmaxf(d2, 1e-30f));
+  return fmaxf(fmaf(-d, inv_extent, 1.f), 0.f);
+}
+
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+// d[16x8] += a[16x8] * b[8x8], TF32 operands, fp32 accumulate (warp-level tensor path)
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <typename IdxT>
+__device__ __forceinline__ int load_idx(const IdxT* __restrict__ p) {
+  return (int)__ldg(p);
+}
+
+template <int C, typename IdxT>
+__global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
+    k_kpconv_tc(const float* __restrict__ q, const float* __restrict__ s, const IdxT* __restrict__ idx, int row_stride,
+                int H, const float* __restrict__ x, const unsigned char* __restrict__ wimg,
+                const float* __restrict__ kp, const unsigned char* __restrict__ rowflag,
+                const TcScales* __restrict__ sc, float extent, float* __restrict__ out, int nq, int ns, int tq,
+                int n_tiles) {
+  using K = TcCfg<C>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem =
+      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sA = smem;
+  unsigned char* sRing = smem + K::OFF_RING;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::OFF_MISC);
+  uint64_t* bar_full = bars;                 // [NSTAGES]
+  uint64_t* bar_empty = bars + 4;            // [NSTAGES]
+  uint64_t* bar_afull = bars + 8;
+  uint64_t* bar_done = bars + 9;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
+  float* sInv = reinterpret_cast<float*>(s_tmem + 4);  // [2][TQ]
+  float* sKp = sInv + 2 * K::TQ;                       // [45]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) {
+    for (int i = 0; i < K::NSTAGES; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    mbar_init(bar_afull, K::WORKERS);
+    mbar_init(bar_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == K::WORKERS) tmem_alloc(s_tmem, K::TMEM_COLS);
+  for (int i = tid; i < KP * 3; i += K::THREADS) sKp[i] = kp[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  const int es = scale_exp((float)H * __uint_as_float(sc->amax_x_bits), 15);
+  const int et = scale_exp(__uint_as_float(sc->amax_w_bits), 14);
+
+  if (warp < K::WORKERS) {
+    // =========================================== producers ===========================================
+    // Phase 1 of a query is itself a small matrix product, wf[16 x 32] = Infl^T[16 x H] * X[H x 32], done with
+    // warp-level mma.sync.m16n8k8 (TF32 operands split hi/lo -> 3 MMAs, fp32 accumulate): rows = kernel points,
+    // K = neighbours in blocks of 8, N = 4 tiles of 8 channels.  With g = lane / 4, t = lane % 4 a lane evaluates
+    // the influences of kernel points g and g+8 on neighbours t and t+4 of the block (exactly its A fragment) and
+    // loads channels 4g..4g+3 of those two neighbours' feature rows as one 16-byte vector (its B fragments for
+    // the four channel tiles: tile i pairs column g with channel 4g+i).  Nothing is staged in shared memory.
+    const float inv_extent = 1.0f / extent;
+    const float a_scale = ldexpf(1.f, es);
+    const float o_scale = ldexpf(1.f, -(es + et));
+    const int g = lane >> 2, t = lane & 3;
+    const float k0x = sKp[3 * g], k0y = sKp[3 * g + 1], k0z = sKp[3 * g + 2];
+    const float k1x = g < 7 ? sKp[3 * (g + 8)] : 0.f, k1y = g < 7 ? sKp[3 * (g + 8) + 1] : 0.f,
+                k1z = g < 7 ? sKp[3 * (g + 8) + 2] : 0.f;
+    const float k1_on = g < 7 ? a_scale : 0.f;  // row 15 of the fragment is padding
+    const int nblk = (H + 7) >> 3;
+    uint32_t seq = 0;
+    int titer = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
+      const int q0 = tile * tq;
+      const int q_end = min(nq, q0 + tq);
+      float* inv_buf = sInv + (titer & 1) * K::TQ;
+#pragma unroll 1
+      for (int pass = 0; pass < K::PASSES; ++pass, ++seq) {
+        const float* xcol = x + pass * 32 + 4 * g;
+        bool first = true;
+        for (int ql = warp; ql < tq; ql += K::WORKERS) {
+          const int n = q0 + ql;
+          float d[4][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) d[i][e] = 0.f;
+          int nn = 0;
+          if (n < q_end) {
+            const float qx = __ldg(q + 3 * (size_t)n), qy = __ldg(q + 3 * (size_t)n + 1),
+                        qz = __ldg(q + 3 * (size_t)n + 2);
+            // neighbour row, lanes = slots (coalesced); slot s of the row lives in jr[s / 32], lane s % 32
+            int jr[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const int h = 32 * i + lane;
+              int j = ns;
+              if (h < H) j = load_idx(idx + (size_t)n * row_stride + h);
+              const bool valid = j >= 0 && j < ns;
+              jr[i] = valid ? j : -1;
+              if (pass == 0 && 32 * i < H) nn += __popc(__ballot_sync(kFull, valid && rowflag[j] != 0));
+            }
+            for (int b = 0; b < nblk; ++b) {
+              const int src = (b & 3) * 8 + t;
+              const int jsel = (b >> 2) == 0 ? jr[0] : ((b >> 2) == 1 ? jr[1] : jr[2]);
+              const int ja = __shfl_sync(kFull, jsel, src);
+              const int jb = __shfl_sync(kFull, jsel, src + 4);
+              if (!__any_sync(kFull, ja >= 0 || jb >= 0)) continue;  // whole block is padding
+              const bool va = ja >= 0, vb = jb >= 0;
+              const size_t ra = va ? (size_t)ja : 0, rb = vb ? (size_t)jb : 0;
+              const float4 xa = __ldg(reinterpret_cast<const float4*>(xcol + ra * C));
+              const float4 xb = __ldg(reinterpret_cast<const float4*>(xcol + rb * C));
+              const float ax = __ldg(s + 3 * ra) - qx, ay = __ldg(s + 3 * ra + 1) - qy, az = __ldg(s + 3 * ra + 2) - qz;
+              const float bx = __ldg(s + 3 * rb) - qx, by = __ldg(s + 3 * rb + 1) - qy, bz = __ldg(s + 3 * rb + 2) - qz;
+              const float sa = va ? a_scale : 0.f, sa1 = va ? k1_on : 0.f;
+              const float sb = vb ? a_scale : 0.f, sb1 = vb ? k1_on : 0.f;
+              float af[4];
+              af[0] = influence_fast(ax, ay, az, k0x, k0y, k0z, inv_extent) * sa;
+              af[1] = influence_fast(ax, ay, az, k1x, k1y, k1z, inv_extent) * sa1;
+              af[2] = influence_fast(bx, by, bz, k0x, k0y, k0z, inv_extent) * sb;
+              af[3] = influence_fast(bx, by, bz, k1x, k1y, k1z, inv_extent) * sb1;
+              uint32_t ah[4], al[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                ah[e] = to_tf32(af[e]);
+                al[e] = __float_as_uint(af[e] - __uint_as_float(ah[e]));
+              }
+              const float xav[4] = {xa.x, xa.y, xa.z, xa.w};
+              const float xbv[4] = {xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t b0h = to_tf32(xav[i]), b1h = to_tf32(xbv[i]);
+                const uint32_t b0l = __float_as_uint(xav[i] - __uint_as_float(b0h));
+                const uint32_t b1l = __float_as_uint(xbv[i] - __uint_as_float(b1h));
+                mma_tf32(d[i], al, b0h, b1h);
+                mma_tf32(d[i], ah, b0l, b1l);
+                mma_tf32(d[i], ah, b0h, b1h);
+              }
+            }
+          }
+          // the A tile still feeds the MMAs of the previous pass until bar_done completes
+          if (first) {
+            if (seq > 0) mbar_wait(bar_done, (seq - 1) & 1);
+            first = false;
+          }
+          if (n < q_end) {
+            // this lane holds wf[k][8t..8t+7] for k = g (d[i][0], d[i][1]) and k = g+8 (d[i][2], d[i][3]):
+            // one 16-byte chunk of fp16 each, K element = k * 32 + channel  ->  atom k / 2, chunk (k % 2) * 4 + t
+            const uint32_t r0 = 2 * ql, r1 = 2 * ql + 1;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int e0 = 2 * half;  // d[i][e0] = channel 8t+i, d[i][e0+1] = channel 8t+4+i
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int p2 = 0; p2 < 4; ++p2) {
+                const float v0 = d[(2 * p2) & 3][e0 + (p2 >> 1)], v1 = d[(2 * p2 + 1) & 3][e0 + (p2 >> 1)];
+                const __half2 hh = __floats2half2_rn(v0, v1);
+                const float2 hf = __half22float2(hh);
+                const __half2 ll = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                hi[p2] = *reinterpret_cast<const uint32_t*>(&hh);
+                lo[p2] = *reinterpret_cast<const uint32_t*>(&ll);
+              }
+              const int k = g + 8 * half;
+              unsigned char* atom = sA + (k >> 1) * K::A_ATOM_BYTES;
+              const uint32_t j = (k & 1) * 4 + t;
+              *reinterpret_cast<uint4*>(atom + sw128_offset(r0, j)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(atom + sw128_offset(r1, j)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            if (pass == 0 && lane == 0) inv_buf[ql] = 1.f / (float)max(nn, 1);
+          }
+        }
+        if (first && seq > 0) mbar_wait(bar_done, (seq - 1) & 1);  // warp without a query in this tile
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_afull);
+      }
+      // ------------------------------ epilogue ------------------------------
+      mbar_wait(bar_done, (seq - 1) & 1);
+      tc_fence_after();
+      {
+        const int qd = warp & 3, cg = warp >> 2;
+        const int ql = qd * 16 + (lane >> 1);
+        const int n = q0 + ql;
+        const bool ok = ql < tq && n < q_end;
+        const float scale = ok ? inv_buf[ql] * o_scale : 0.f;
+        const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16);
+#pragma unroll 1
+        for (int c0 = cg * (C / 4); c0 < (cg + 1) * (C / 4); c0 += 8) {
+          float v1[8], v2[8];
+          tmem_ld8(trow + c0, v1);
+          tmem_ld8(trow + C + c0, v2);
+          tmem_ld_wait();
+          float sum[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            sum[i] = v1[i] + v2[i];
+            sum[i] += __shfl_xor_sync(kFull, sum[i], 1);
+          }
+          if (ok) {
+            const int off = (lane & 1) * 4;
+            const float4 r = (lane & 1) ? make_float4(sum[4] * scale, sum[5] * scale, sum[6] * scale, sum[7] * scale)
+                                        : make_float4(sum[0] * scale, sum[1] * scale, sum[2] * scale, sum[3] * scale);
+            *reinterpret_cast<float4*>(out + (size_t)n * C + c0 + off) = r;
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  } else if (warp == K::WORKERS) {
+    // =========================================== MMA issuer ===========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_f16_f32(128, K::NS);
+      const uint64_t adesc0 = desc_sw128_kmajor(smem_u32(sA));
+      const uint64_t bdesc0 = desc_sw128_kmajor(smem_u32(sRing));
+      uint32_t seq = 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int pass = 0; pass < K::PASSES; ++pass, ++seq) {
+          mbar_wait(bar_afull, seq & 1);
+          tc_fence_after();
+          for (int a = 0; a < 8; ++a) {
+            for (int sub = 0; sub < K::NSUB; ++sub) {
+              mbar_wait(&bar_full[stage], phase);
+              tc_fence_after();
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t ad = adesc0 + (uint64_t)((a * K::A_ATOM_BYTES + kk * 32) >> 4);
+                const uint64_t bd = bdesc0 + (uint64_t)((stage * K::STAGE_BYTES + kk * 32) >> 4);
+                umma_f16(tmem + sub * K::NS, ad, bd, idesc, (pass | a | kk) != 0);
+              }
+              umma_commit(&bar_empty[stage]);
+              if (++stage == K::NSTAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+          umma_commit(bar_done);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================== weight stream ===========================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int blk = 0; blk < K::PASSES * K::BLOCKS_PER_PASS; ++blk) {
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bar_full[stage], K::STAGE_BYTES);
+          bulk_g2s(sRing + stage * K::STAGE_BYTES, wimg + (size_t)blk * K::STAGE_BYTES, K::STAGE_BYTES,
+                   &bar_full[stage]);
+          if (++stage == K::NSTAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == K::WORKERS) tmem_dealloc(tmem, K::TMEM_COLS);
+}
+
+template <int C, typename IdxT>
+int launch_tc(const float* q, const float* s, const void* idx, int row_stride, int H, const float* x, const float* w,
+              const float* kp, float extent, float* out, int nq, int ns, void* workspace, cudaStream_t stream) {
+  using K = TcCfg<C>;
+  SPR_CHECK_ARG(H <= 96, "kpconv_forward(mode 1): at most 96 neighbour columns are supported (got %d)", H);
+  Carver cv(workspace, (size_t)-1);
+  TcScales* sc = cv.take<TcScales>(1);
+  unsigned char* rowflag = cv.take<unsigned char>((size_t)ns + 1);
+  unsigned char* img = cv.take<unsigned char>(K::IMG_BYTES);
+
+  SPR_CUDA(cudaMemsetAsync(sc, 0, sizeof(TcScales), stream));
+  const int n_xblocks = (ns + 1 + 7) / 8;
+  k_flags_absmax<<<n_xblocks + 8, 256, 0, stream>>>(x, ns, C, rowflag, w, KP * C * C, n_xblocks, sc);
+  SPR_LAUNCH_CHECK("k_flags_absmax");
+  constexpr int chunks = (int)(K::IMG_BYTES / 16);
+  k_weight_image<C><<<(chunks + 255) / 256, 256, 0, stream>>>(w, sc, img);
+  SPR_LAUNCH_CHECK("k_weight_image");
+
+  // Tile size: the largest tq <= 64 that deals every SM the same number of tiles (a tile is the M extent of
+  // one MMA; short tiles only leave MMA rows unused, which costs nothing on the critical path).
+  int tq = K::TQ;
+  {
+    const int waves = (nq + kNumSMs * K::TQ - 1) / (kNumSMs * K::TQ);
+    const int per = (nq + kNumSMs * waves - 1) / (kNumSMs * waves);
+    tq = per < 16 ? 16 : (per > K::TQ ? K::TQ : per);
+  }
+  const int n_tiles = (nq + tq - 1) / tq;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPR_CUDA(cudaFuncSetAttribute(k_kpconv_tc<C, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+    attr_set = true;
+  }
+  const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+  k_kpconv_tc<C, IdxT><<<grid, K::THREADS, K::SMEM, stream>>>(q, s, static_cast<const IdxT*>(idx), row_stride, H, x, img,
+                                                              kp, rowflag, sc, extent, out, nq, ns, tq, n_tiles);
+  SPR_LAUNCH_CHECK("k_kpconv_tc");
+  return SPR_OK;
+}
+
+template <int C>
+size_t tc_ws(int ns) {
+  return 256 + align_up((size_t)ns + 1, 256) + 256 + TcCfg<C>::IMG_BYTES + 256;
+}
+
+}  // namespace
+
+size_t kpconv_tc_workspace_bytes(int ns, int c) {
+  switch (c) {
+    case 32: return tc_ws<32>(ns);
+    case 64: return tc_ws<64>(ns);
+    case 128: return tc_ws<128>(ns);
+    case 256: return tc_ws<256>(ns);
+  }
+  return 0;
+}
+
+int kpconv_tc_forward(const float* q, const float* s, const void* idx, int idx_is_64, int row_stride, int H,
+                      const float* x, int c, const float* w, const float* kp, float extent, float* out, int nq, int ns,
+                      void* workspace, cudaStream_t stream) {
+#define SPR_TC(CC)                                                                                                  \
+  case CC:                                                                                                          \
+    return idx_is_64 ? launch_tc<CC, long long>(q, s, idx, row_stride, H, x, w, kp, extent, out, nq, ns, workspace, \
+                                                stream)                                                             \
+                     : launch_tc<CC, int>(q, s, idx, row_stride, H, x, w, kp, extent, out, nq, ns, workspace, stream);
+  switch (c) {
+    SPR_TC(32)
+    SPR_TC(64)
+    SPR_TC(128)
+    SPR_TC(256)
+  }
+#undef SPR_TC
+  set_error("kpconv_forward(mode 1): unsupported channel count %d", c);
+  return SPR_EUNSUPPORTED;
+}
+
+}  // namespace spr

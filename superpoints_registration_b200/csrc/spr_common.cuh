@@ -128,4 +128,11 @@ int exclusive_scan_i32(const int32_t* d_in, int32_t* d_out, size_t n, int32_t* d
 // offs[0..B] = exclusive prefix of lens[0..B-1] (single small kernel).
 int cloud_offsets(const int32_t* d_lens, int B, int32_t* d_offs, cudaStream_t stream);
 
+
+// kpconv_tc.cu: tensor-core (tcgen05) KPConv path, Cin = Cout = c in {32, 64, 128, 256}
+size_t kpconv_tc_workspace_bytes(int ns, int c);
+int kpconv_tc_forward(const float* q, const float* s, const void* idx, int idx_is_64, int row_stride, int H,
+                      const float* x, int c, const float* w, const float* kp, float extent, float* out, int nq, int ns,
+                      void* workspace, cudaStream_t stream);
+
 }  // namespace spr

@@ -1,0 +1,116 @@
+// tc05.cuh -- thin inline-PTX layer over the Blackwell (sm_100a) tensor-core path used by the fused kernels:
+// mbarriers, bulk async copies (TMA engine, UBLKCP), tensor memory (TMEM) management, tcgen05.mma issue /
+// commit, tcgen05.ld, and the shared-memory matrix descriptors of the canonical K-major SWIZZLE_128B layout.
+//
+// Layout convention (both operands K-major, 128-byte swizzle):
+//   an operand tile of R rows x 64 fp16 (one "K atom" = 128 bytes per row) is stored as
+//     byte(r, chunk j of 16 B) = (r / 8) * 1024 + (r % 8) * 128 + ((j ^ (r % 8)) * 16)          (tile base 1024-B aligned)
+//   consecutive K atoms of the same rows are separate tiles R * 128 bytes apart.  One tcgen05.mma consumes
+//   K = 16 fp16 = 32 bytes of every row: the descriptor start address advances by 32 B per K step inside an atom.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace spr {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// generic-proxy shared-memory writes -> visible to the async proxy (tensor core / TMA reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- bulk async copy global -> shared (TMA engine, completes on an mbarrier) ---------------------------
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- tensor memory ---------------------------------------------------------------------------------------
+// whole warp; writes the TMEM base address (lane 0, column base) to *dst_smem
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 8 consecutive 32-bit columns: thread i of the warp receives row (lane field of taddr) + i
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- UMMA descriptors ------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: LBO = 1 (unused), SBO = 1024 B between 8-row groups,
+// descriptor version 1 (sm_100), layout type 2
+__device__ __forceinline__ uint64_t desc_sw128_kmajor(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor, kind::f16: A = B = fp16, D = fp32, both K-major, shape M x N (K = 16)
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int m, int n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread on behalf of the CTA
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// byte offset of 16-byte chunk j of row r inside a (rows x 128 B) SWIZZLE_128B tile
+__host__ __device__ constexpr uint32_t sw128_offset(uint32_t r, uint32_t j) {
+  return (r >> 3) * 1024u + (r & 7u) * 128u + ((j ^ (r & 7u)) << 4);
+}
+
+}  // namespace tc
+}  // namespace spr

@@ -63,7 +63,7 @@ class KPConv(nn.Module):
         self.aggregation_mode = aggregation_mode
         self.deformable = deformable
         self.modulated = modulated
-        self.mode = 0  # 0: fp32 CUDA-core contraction
+        self.mode = None  # None: ops.default_kpconv_mode (tcgen05 where available); 0 forces the fp32 CUDA-core contraction
         self.weights = Parameter(torch.zeros((self.K, in_channels, out_channels), dtype=torch.float32))
         nn.init.kaiming_uniform_(self.weights, a=math.sqrt(5))
         kp = load_kernels(self.radius, self.K, dimension=self.p_dim, fixed=self.fixed_kernel_points)

@@ -7,6 +7,8 @@ from __future__ import annotations
 
 from typing import Optional, Tuple
 
+import os
+
 import torch
 
 from . import _lib
@@ -127,7 +129,19 @@ def _idx_arg(idx: torch.Tensor):
     return idx, (1 if idx.dtype == torch.int64 else 0), idx.stride(0), idx.shape[1]
 
 
-def kpconv_forward(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent: float, mode: int = 0):
+_TC_CHANNELS = (32, 64, 128, 256)
+
+
+def default_kpconv_mode(cin: int, cout: int) -> int:
+    """1 (tcgen05 tensor-core contraction) where the layer shape has a tensor-core kernel, else 0 (fp32 CUDA-core
+    contraction: the Cin=1 stem).  SPR_KPCONV_MODE=0|1 forces one path for experiments."""
+    forced = os.environ.get("SPR_KPCONV_MODE")
+    if forced is not None:
+        return int(forced) if (cin == cout and cin in _TC_CHANNELS) else 0
+    return 1 if (cin == cout and cin in _TC_CHANNELS) else 0
+
+
+def kpconv_forward(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent: float, mode=None):
     L = _lib.lib()
     q, s, xx = _f32c(q_pts, "q_pts"), _f32c(s_pts, "s_pts"), _f32c(x, "x")
     w, kp = _f32c(weights, "weights"), _f32c(kernel_points, "kernel_points")
@@ -138,6 +152,8 @@ def kpconv_forward(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent:
         raise RuntimeError(f"x must have shape ({ns}, {cin}), got {tuple(xx.shape)}")
     if idx.shape[0] != nq:
         raise RuntimeError("neighb_inds must have one row per query point")
+    if mode is None:
+        mode = default_kpconv_mode(cin, cout)
     out = torch.empty((nq, cout), dtype=torch.float32, device=q.device)
     ws = _ws(L.spr_kpconv_workspace_bytes(nq, ns, cin, cout, K), q.device)
     rc = L.spr_kpconv_forward(q.data_ptr(), s.data_ptr(), idx.data_ptr(), is64, stride, H, xx.data_ptr(), cin,

@@ -28,7 +28,8 @@ def _t(a, dtype=None):
     return t if dtype is None else t.to(dtype)
 
 
-def test_kpconv_layers_against_golden_and_oracle(golden_dir):
+@pytest.mark.parametrize("mode", [0, 1])
+def test_kpconv_layers_against_golden_and_oracle(golden_dir, mode):
     g = np.load(os.path.join(golden_dir, "kpconv_layers.npz"))
     for tag in map(str, g["tags"]):
         q, s, idx, x, kp = g[f"{tag}_q"], g[f"{tag}_s"], g[f"{tag}_idx"], g[f"{tag}_x"], g[f"{tag}_kp"]
@@ -37,7 +38,8 @@ def test_kpconv_layers_against_golden_and_oracle(golden_dir):
         w = filled_state({wname: (15, cin, cout)}, 100 + cin)[wname]
         ext = float(g[f"{tag}_extent"])
         for idx_dtype in (torch.int64, torch.int32):
-            out = ops.kpconv_forward(_t(q), _t(s), _t(idx, idx_dtype), _t(x), _t(w), _t(kp), ext).cpu().numpy()
+            m = mode if cin == cout else 0
+            out = ops.kpconv_forward(_t(q), _t(s), _t(idx, idx_dtype), _t(x), _t(w), _t(kp), ext, mode=m).cpu().numpy()
             ref = g[f"{tag}_out"]                                   # the reference module's output
             exact = oracle.kpconv_forward(q, s, idx.astype(np.int64), x, w, kp, ext)  # fp64-accumulated oracle
             scale = np.abs(ref).max()
@@ -45,8 +47,9 @@ def test_kpconv_layers_against_golden_and_oracle(golden_dir):
             assert np.abs(out - ref).max() <= FEAT_RTOL * scale, (tag, np.abs(out - ref).max(), scale)
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("c", [32, 64, 128, 256])
-def test_kpconv_random_shapes_against_oracle(c):
+def test_kpconv_random_shapes_against_oracle(c, mode):
     rng = np.random.default_rng(c)
     ns, nq, H = 700, 333, 23                       # nq not a multiple of the tile, odd H
     s = rng.uniform(0, 1, size=(ns, 3)).astype(np.float32)
@@ -57,10 +60,46 @@ def test_kpconv_random_shapes_against_oracle(c):
     w = (rng.normal(size=(15, c, c)) / np.sqrt(15 * c)).astype(np.float32)
     kp = (rng.normal(size=(15, 3)) * 0.15).astype(np.float32)
     kp[0] = 0
-    out = ops.kpconv_forward(_t(q), _t(s), _t(idx), _t(x), _t(w), _t(kp), 0.3).cpu().numpy()
+    out = ops.kpconv_forward(_t(q), _t(s), _t(idx), _t(x), _t(w), _t(kp), 0.3, mode=mode).cpu().numpy()
+    exact = oracle.kpconv_forward(q, s, idx, x, w, kp, 0.3)
+    err = np.abs(out - exact).max()
+    print(f"C={c} mode={mode}: max err {err:.3e} = {err / np.abs(exact).max():.2e} x max|out|")
+    assert err <= FEAT_RTOL * np.abs(exact).max()
+    assert np.all(out[5] == 0)
+
+
+@pytest.mark.parametrize("scale_x,scale_w", [(1e-6, 1.0), (3e4, 1e-3), (1.0, 250.0)])
+def test_kpconv_tensor_core_operand_scaling(scale_x, scale_w):
+    """The tensor-core path splits fp32 operands into fp16 pairs after a power-of-two rescale derived from max|x| and
+    max|W|: accuracy must not depend on the magnitude of the inputs."""
+    rng = np.random.default_rng(11)
+    ns, nq, H, c = 900, 500, 30, 64
+    s = rng.uniform(0, 1, size=(ns, 3)).astype(np.float32)
+    q = s[:nq]
+    idx = rng.integers(0, ns + 1, size=(nq, H))
+    x = (rng.normal(size=(ns, c)) * scale_x).astype(np.float32)
+    w = (rng.normal(size=(15, c, c)) / np.sqrt(15 * c) * scale_w).astype(np.float32)
+    kp = (rng.normal(size=(15, 3)) * 0.15).astype(np.float32)
+    out = ops.kpconv_forward(_t(q), _t(s), _t(idx), _t(x), _t(w), _t(kp), 0.3, mode=1).cpu().numpy()
     exact = oracle.kpconv_forward(q, s, idx, x, w, kp, 0.3)
     assert np.abs(out - exact).max() <= FEAT_RTOL * np.abs(exact).max()
-    assert np.all(out[5] == 0)
+
+
+def test_kpconv_tensor_core_many_tiles_and_zero_input():
+    """More tiles than SMs (persistent loop, ring wrap-around) and an all-zero feature matrix (scale exponent guard)."""
+    rng = np.random.default_rng(12)
+    ns, H, c = 30000, 24, 32
+    nq = ns
+    s = rng.uniform(0, 3, size=(ns, 3)).astype(np.float32)
+    idx = rng.integers(0, ns + 1, size=(nq, H))
+    x = np.maximum(rng.normal(size=(ns, c)), 0).astype(np.float32)
+    w = (rng.normal(size=(15, c, c)) / np.sqrt(15 * c)).astype(np.float32)
+    kp = (rng.normal(size=(15, 3)) * 0.15).astype(np.float32)
+    out = ops.kpconv_forward(_t(s), _t(s), _t(idx), _t(x), _t(w), _t(kp), 0.3, mode=1)
+    ref = ops.kpconv_forward(_t(s), _t(s), _t(idx), _t(x), _t(w), _t(kp), 0.3, mode=0)
+    assert (out - ref).abs().max().item() <= FEAT_RTOL * ref.abs().max().item()
+    z = ops.kpconv_forward(_t(s), _t(s), _t(idx), _t(np.zeros_like(x)), _t(w), _t(kp), 0.3, mode=1)
+    assert torch.count_nonzero(z).item() == 0
 
 
 def test_kpconv_strided_view_indices():
@@ -75,9 +114,11 @@ def test_kpconv_strided_view_indices():
     kp = (rng.normal(size=(15, 3)) * 0.15).astype(np.float32)
     view = _t(full)[:, :17]
     assert not view.is_contiguous()
-    out = ops.kpconv_forward(_t(q), _t(s), view, _t(x), _t(w), _t(kp), 0.3).cpu().numpy()
+    out = ops.kpconv_forward(_t(q), _t(s), view, _t(x), _t(w), _t(kp), 0.3, mode=1).cpu().numpy()
+    out0 = ops.kpconv_forward(_t(q), _t(s), view, _t(x), _t(w), _t(kp), 0.3, mode=0).cpu().numpy()
     exact = oracle.kpconv_forward(q, s, full[:, :17].copy(), x, w, kp, 0.3)
     assert np.abs(out - exact).max() <= FEAT_RTOL * np.abs(exact).max()
+    assert np.abs(out0 - exact).max() <= FEAT_RTOL * np.abs(exact).max()
 
 
 def test_kpconv_module_surface_and_errors():

@@ -18,6 +18,7 @@ ap.add_argument("--pairs", type=int, default=2)
 ap.add_argument("--points", type=int, default=20000)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--cfg", default="3dmatch")
+ap.add_argument("--mode", type=int, default=None)
 args = ap.parse_args()
 dev = "cuda:0"
 cfg = {"3dmatch": spr.threedmatch_config, "kitti": spr.kitti_config, "modelnet": spr.modelnet_config}[args.cfg]()
@@ -52,7 +53,7 @@ for (l, strided, c) in shapes:
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.kpconv_forward(q, s, idx, x, w, kp, ext)
+        ops.kpconv_forward(q, s, idx, x, w, kp, ext, mode=args.mode)
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))

@@ -51,6 +51,27 @@ __global__ void __launch_bounds__(256) k_ffma(float* out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// packed fp32 FMA (Blackwell fma.rn.f32x2 -> FFMA2): two FMAs per lane per instruction
+__global__ void __launch_bounds__(256) k_ffma2(float* out, int iters) {
+  unsigned long long c[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float lo = threadIdx.x * 0.001f + i, hi = lo + 0.5f;
+    c[i] = ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
+  }
+  const float af = 1.0001f, bf = 0.5f;
+  unsigned long long a = ((unsigned long long)__float_as_uint(af) << 32) | __float_as_uint(af);
+  unsigned long long b = ((unsigned long long)__float_as_uint(bf) << 32) | __float_as_uint(bf);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(c[i]) : "l"(a), "l"(b));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += __uint_as_float((unsigned)(c[i] & 0xffffffffu)) + __uint_as_float((unsigned)(c[i] >> 32));
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int main() {
   int sms = 0, clk = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -62,13 +83,14 @@ int main() {
   cudaEventCreate(&e1);
   const int iters = 20000;
   for (int blocks_per_sm = 1; blocks_per_sm <= 4; blocks_per_sm *= 2) {
-    for (int kind = 0; kind < 3; ++kind) {
+    for (int kind = 0; kind < 4; ++kind) {
       float best = 1e9f;
       for (int rep = 0; rep < 3; ++rep) {
         cudaEventRecord(e0);
         if (kind == 0) k_mma<0><<<sms * blocks_per_sm, 256>>>(out, iters);
         else if (kind == 1) k_mma<1><<<sms * blocks_per_sm, 256>>>(out, iters);
-        else k_ffma<<<sms * blocks_per_sm, 256>>>(out, iters);
+        else if (kind == 2) k_ffma<<<sms * blocks_per_sm, 256>>>(out, iters);
+        else k_ffma2<<<sms * blocks_per_sm, 256>>>(out, iters);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms;
@@ -80,7 +102,7 @@ int main() {
                                                                                    : warps * iters * 16.0 * 32;
       const double per_s = macs / (best * 1e-3);
       printf("%s blocks/SM=%d: %.3f ms  %.1f TMAC/s  (%.0f MAC/clk/SM at the max clock %d MHz)\n",
-             kind == 0 ? "mma.m16n8k8.tf32 " : kind == 1 ? "mma.m16n8k16.bf16" : "ffma             ", blocks_per_sm, best,
+             kind == 0 ? "mma.m16n8k8.tf32 " : kind == 1 ? "mma.m16n8k16.bf16" : kind == 2 ? "ffma             " : "ffma2 (f32x2)    ", blocks_per_sm, best,
              per_s / 1e12, per_s / sms / (clk * 1e3), clk / 1000);
     }
   }

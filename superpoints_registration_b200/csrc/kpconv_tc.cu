@@ -51,26 +51,25 @@ __device__ __forceinline__ int scale_exp(float v, int target) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// pre-pass 1: row-sum flags of x (the reference's neighbour_num mask, :409-412), max|x| and max|W|
+// pre-pass 1 (one warp per support row): the feature row pre-split into fp16 (hi, lo) pairs of x * 2^e with a
+// per-row power-of-two scale; the packed support point (x, y, z, +-2^-e) whose sign carries rowsum(x) > 0 (the
+// reference's neighbour_num mask, :409-412); max|x| and max|W| for the global scales of the tcgen05 operands
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_flags_absmax(const float* __restrict__ x, int ns, int cin,
-                                                       unsigned char* __restrict__ flag, const float* __restrict__ w,
-                                                       int n_w, int n_xblocks, TcScales* __restrict__ sc) {
+__global__ void __launch_bounds__(256) k_flags_absmax(const float* __restrict__ x, const float* __restrict__ s, int ns,
+                                                       int cin, float4* __restrict__ pts4, uint32_t* __restrict__ x16,
+                                                       const float* __restrict__ w, int n_w, int n_xblocks,
+                                                       TcScales* __restrict__ sc) {
   const int lane = threadIdx.x & 31;
   if ((int)blockIdx.x >= n_xblocks) {  // weights
     float m = 0.f;
     for (int i = (blockIdx.x - n_xblocks) * blockDim.x + threadIdx.x; i < n_w; i += (gridDim.x - n_xblocks) * blockDim.x)
       m = fmaxf(m, fabsf(w[i]));
     m = warp_maxf(m);
-    if (lane == 0 && m > 0.f) atomicMax(&sc->amax_w_bits, __float_as_uint(m));
+    if (lane == 0 && __float_as_uint(m) > sc->amax_w_bits) atomicMax(&sc->amax_w_bits, __float_as_uint(m));
     return;
   }
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row > ns) return;
-  if (row == ns) {
-    if (lane == 0) flag[ns] = 0;
-    return;
-  }
+  if (row >= ns) return;
   float acc = 0.f, m = 0.f;
   for (int c = lane; c < cin; c += 32) {
     const float v = x[(size_t)row * cin + c];
@@ -79,9 +78,21 @@ __global__ void __launch_bounds__(256) k_flags_absmax(const float* __restrict__ 
   }
   acc = warp_sum(acc);
   m = warp_maxf(m);
+  // the row as (hi, lo) fp16 pairs of x * 2^e, e chosen per row so that max|x| * 2^e <= 2^14
+  const int e = scale_exp(m, 14);
+  const float rs = ldexpf(1.f, e);
+  for (int c = lane; c < cin; c += 32) {
+    const float v = x[(size_t)row * cin + c] * rs;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    x16[(size_t)row * cin + c] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+  }
   if (lane == 0) {
-    flag[row] = acc > 0.f ? 1 : 0;
-    if (m > 0.f) atomicMax(&sc->amax_x_bits, __float_as_uint(m));
+    const float inv = ldexpf(1.f, -e);
+    pts4[row] = make_float4(s[3 * (size_t)row], s[3 * (size_t)row + 1], s[3 * (size_t)row + 2], acc > 0.f ? inv : -inv);
+    // one address for the whole grid: only touch it when this row raises the running maximum
+    if (__float_as_uint(m) > *reinterpret_cast<volatile unsigned int*>(&sc->amax_x_bits))
+      atomicMax(&sc->amax_x_bits, __float_as_uint(m));
   }
 }
 
@@ -133,7 +144,7 @@ struct TcCfg {
   static constexpr int NSTAGES = C == 32 ? 4 : 3;
   static constexpr int BLOCKS_PER_PASS = 8 * NSUB;    // 8 K atoms of 64 fp16 per pass
   static constexpr int TQ = 64;
-  static constexpr int WORKERS = 16;
+  static constexpr int WORKERS = 18;
   static constexpr int THREADS = (WORKERS + 2) * 32;
   static constexpr int A_ATOM_BYTES = 128 * 128;
   static constexpr int A_BYTES = 8 * A_ATOM_BYTES;
@@ -142,7 +153,7 @@ struct TcCfg {
   static constexpr int OFF_RING = A_BYTES;
   static constexpr int OFF_WBUF = OFF_RING + NSTAGES * STAGE_BYTES;
   static constexpr int OFF_MISC = OFF_WBUF + WBUF_BYTES;
-  static constexpr int MISC_BYTES = 16 * 8 + 16 + 2 * TQ * 4 + 48 * 4;
+  static constexpr int MISC_BYTES = 16 * 8 + 32 + 2 * TQ * 4 + 48 * 4;
   static constexpr size_t SMEM = 1024 + OFF_MISC + MISC_BYTES;
   static constexpr size_t IMG_BYTES = (size_t)PASSES * BLOCKS_PER_PASS * STAGE_BYTES;
 };
@@ -151,7 +162,8 @@ __device__ __forceinline__ float influence_fast(float cx, float cy, float cz, fl
                                                 float inv_extent) {
   const float dx = cx - kx, dy = cy - ky, dz = cz - kz;
   const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-  const float d = d2 * rsqrtf(fmaxf(d2, 1e-30f));
+  float d;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(d2));  // MUFU.SQRT, rel. error ~2^-23, sqrt(0) = 0
   return fmaxf(fmaf(-d, inv_extent, 1.f), 0.f);
 }
 
@@ -168,16 +180,24 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<const uint32_t*>(&v); }
+// d[16x8] += a[16x8] * b[8x8], fp16 operands, fp32 accumulate (warp-level tensor path)
+__device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(b0));
+}
+
 template <typename IdxT>
 __device__ __forceinline__ int load_idx(const IdxT* __restrict__ p) {
   return (int)__ldg(p);
 }
 
-template <int C, typename IdxT>
+template <int C, typename IdxT, int HR>  // HR = ceil(H / 32): 32-slot rounds of a neighbour row
 __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
     k_kpconv_tc(const float* __restrict__ q, const float* __restrict__ s, const IdxT* __restrict__ idx, int row_stride,
-                int H, const float* __restrict__ x, const unsigned char* __restrict__ wimg,
-                const float* __restrict__ kp, const unsigned char* __restrict__ rowflag,
+                int H, const uint32_t* __restrict__ x16, const unsigned char* __restrict__ wimg,
+                const float* __restrict__ kp, const float4* __restrict__ pts4,
                 const TcScales* __restrict__ sc, float extent, float* __restrict__ out, int nq, int ns, int tq,
                 int n_tiles) {
   using K = TcCfg<C>;
@@ -192,7 +212,8 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
   uint64_t* bar_afull = bars + 8;
   uint64_t* bar_done = bars + 9;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
-  float* sInv = reinterpret_cast<float*>(s_tmem + 4);  // [2][TQ]
+  int* s_ctr = reinterpret_cast<int*>(s_tmem + 4);      // [4] query dispensers, indexed by pass sequence & 3
+  float* sInv = reinterpret_cast<float*>(s_tmem + 8);  // [2][TQ]
   float* sKp = sInv + 2 * K::TQ;                       // [45]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -204,6 +225,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
     mbar_init(bar_afull, K::WORKERS);
     mbar_init(bar_done, 1);
     fence_mbar_init();
+    for (int i = 0; i < 4; ++i) s_ctr[i] = 0;
   }
   if (warp == K::WORKERS) tmem_alloc(s_tmem, K::TMEM_COLS);
   for (int i = tid; i < KP * 3; i += K::THREADS) sKp[i] = kp[i];
@@ -230,84 +252,148 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
     const float k0x = sKp[3 * g], k0y = sKp[3 * g + 1], k0z = sKp[3 * g + 2];
     const float k1x = g < 7 ? sKp[3 * (g + 8)] : 0.f, k1y = g < 7 ? sKp[3 * (g + 8) + 1] : 0.f,
                 k1z = g < 7 ? sKp[3 * (g + 8) + 2] : 0.f;
-    const float k1_on = g < 7 ? a_scale : 0.f;  // row 15 of the fragment is padding
-    const int nblk = (H + 7) >> 3;
+    const float k1_on = g < 7 ? 1.f : 0.f;  // row 15 of the fragment is padding
     uint32_t seq = 0;
     int titer = 0;
+    // One "item" = one block of 8 neighbours of one query.  The loads of item i+1 (two packed support points and
+    // two 16-byte pieces of pre-split feature rows per lane) are in flight while item i is multiplied; the
+    // neighbour row of the warp's next query is requested when the current query starts.
+    struct Item {
+      float4 pa, pb;   // packed support points of neighbours 2t, 2t+1: x, y, z, w = +-2^-e (sign = rowsum flag)
+      uint4 xa, xb;    // their feature pieces: channels 4g..4g+3 as (hi, lo) fp16 pairs scaled by 2^e
+    };  // an absent neighbour has pa/pb = 0: w = 0 zeroes its influences
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
       const int q0 = tile * tq;
-      const int q_end = min(nq, q0 + tq);
+      const int cnt = min(nq, q0 + tq) - q0;  // queries in this tile
       float* inv_buf = sInv + (titer & 1) * K::TQ;
 #pragma unroll 1
       for (int pass = 0; pass < K::PASSES; ++pass, ++seq) {
-        const float* xcol = x + pass * 32 + 4 * g;
+        const uint32_t* xcol = x16 + pass * 32 + 4 * g;
         bool first = true;
-        for (int ql = warp; ql < tq; ql += K::WORKERS) {
-          const int n = q0 + ql;
+        // queries are dealt to the warps dynamically (neighbourhood sizes vary); the dispenser of pass seq+2 is
+        // reset by whoever draws query 0 of pass seq (no warp can still be in pass seq-2, see bar_done)
+        int* ctr = s_ctr + (seq & 3);
+        auto grab = [&]() {
+          int v = 0;
+          if (lane == 0) v = atomicAdd(ctr, 1);
+          return __shfl_sync(kFull, v, 0);
+        };
+        int ql = grab();
+        if (ql == 0 && lane == 0) s_ctr[(seq + 2) & 3] = 0;
+        int ql_next = 0;
+        if (ql < cnt) {
+          int jr[HR];           // neighbour row of the query being issued (lanes = slots), -1 = padding
+          int jrn[HR];          // raw row of the next query (loads in flight)
+          float qx, qy, qz;     // query point, issue side
+          float qnx = 0.f, qny = 0.f, qnz = 0.f;
+          unsigned bm;          // blocks of the row still to issue
+          bool row_pending = false, new_query = true;
           float d[4][4];
+          float fcount = 0.f;
+          float cqx, cqy, cqz;  // query point of the item being multiplied
+          auto issue_row = [&](int qq) {
+            const int n = q0 + qq;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) d[i][e] = 0.f;
-          int nn = 0;
-          if (n < q_end) {
-            const float qx = __ldg(q + 3 * (size_t)n), qy = __ldg(q + 3 * (size_t)n + 1),
-                        qz = __ldg(q + 3 * (size_t)n + 2);
-            // neighbour row, lanes = slots (coalesced); slot s of the row lives in jr[s / 32], lane s % 32
-            int jr[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
+            for (int i = 0; i < HR; ++i) {
               const int h = 32 * i + lane;
-              int j = ns;
-              if (h < H) j = load_idx(idx + (size_t)n * row_stride + h);
-              const bool valid = j >= 0 && j < ns;
-              jr[i] = valid ? j : -1;
-              if (pass == 0 && 32 * i < H) nn += __popc(__ballot_sync(kFull, valid && rowflag[j] != 0));
+              jrn[i] = -1;
+              if (h < H) jrn[i] = load_idx(idx + (size_t)n * row_stride + h);
             }
-            for (int b = 0; b < nblk; ++b) {
-              const int src = (b & 3) * 8 + t;
-              const int jsel = (b >> 2) == 0 ? jr[0] : ((b >> 2) == 1 ? jr[1] : jr[2]);
-              const int ja = __shfl_sync(kFull, jsel, src);
-              const int jb = __shfl_sync(kFull, jsel, src + 4);
-              if (!__any_sync(kFull, ja >= 0 || jb >= 0)) continue;  // whole block is padding
-              const bool va = ja >= 0, vb = jb >= 0;
-              const size_t ra = va ? (size_t)ja : 0, rb = vb ? (size_t)jb : 0;
-              const float4 xa = __ldg(reinterpret_cast<const float4*>(xcol + ra * C));
-              const float4 xb = __ldg(reinterpret_cast<const float4*>(xcol + rb * C));
-              const float ax = __ldg(s + 3 * ra) - qx, ay = __ldg(s + 3 * ra + 1) - qy, az = __ldg(s + 3 * ra + 2) - qz;
-              const float bx = __ldg(s + 3 * rb) - qx, by = __ldg(s + 3 * rb + 1) - qy, bz = __ldg(s + 3 * rb + 2) - qz;
-              const float sa = va ? a_scale : 0.f, sa1 = va ? k1_on : 0.f;
-              const float sb = vb ? a_scale : 0.f, sb1 = vb ? k1_on : 0.f;
-              float af[4];
-              af[0] = influence_fast(ax, ay, az, k0x, k0y, k0z, inv_extent) * sa;
-              af[1] = influence_fast(ax, ay, az, k1x, k1y, k1z, inv_extent) * sa1;
-              af[2] = influence_fast(bx, by, bz, k0x, k0y, k0z, inv_extent) * sb;
-              af[3] = influence_fast(bx, by, bz, k1x, k1y, k1z, inv_extent) * sb1;
-              uint32_t ah[4], al[4];
+            qnx = __ldg(q + 3 * (size_t)n);
+            qny = __ldg(q + 3 * (size_t)n + 1);
+            qnz = __ldg(q + 3 * (size_t)n + 2);
+          };
+          auto consume_row = [&]() {
+            bm = 0;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                ah[e] = to_tf32(af[e]);
-                al[e] = __float_as_uint(af[e] - __uint_as_float(ah[e]));
+            for (int i = 0; i < HR; ++i) {
+              jr[i] = -1;
+              if (32 * i < H) {
+                const bool valid = jrn[i] >= 0 && jrn[i] < ns;
+                jr[i] = valid ? jrn[i] : -1;
+                const unsigned m = __ballot_sync(kFull, valid);
+                const unsigned b4 = ((m & 0xffu) ? 1u : 0u) | ((m & 0xff00u) ? 2u : 0u) | ((m & 0xff0000u) ? 4u : 0u) |
+                                    ((m & 0xff000000u) ? 8u : 0u);
+                bm |= b4 << (4 * i);
               }
-              const float xav[4] = {xa.x, xa.y, xa.z, xa.w};
-              const float xbv[4] = {xb.x, xb.y, xb.z, xb.w};
+            }
+            if (bm == 0) bm = 1;  // a query without neighbours still runs one (all-padding) block
+            qx = qnx;
+            qy = qny;
+            qz = qnz;
+          };
+          auto issue_item = [&](Item& it) {
+            const int b = __ffs(bm) - 1;
+            bm &= bm - 1;
+            const int src = (b & 3) * 8 + 2 * t;
+            int jsel = jr[0];
+#pragma unroll
+            for (int i = 1; i < HR; ++i)
+              if ((b >> 2) == i) jsel = jr[i];
+            const int ja = __shfl_sync(kFull, jsel, src);
+            const int jb = __shfl_sync(kFull, jsel, src + 1);
+            const size_t ra = ja >= 0 ? (size_t)ja : 0, rb = jb >= 0 ? (size_t)jb : 0;
+            it.pa = make_float4(0.f, 0.f, 0.f, 0.f);
+            it.pb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ja >= 0) it.pa = __ldg(pts4 + ra);
+            if (jb >= 0) it.pb = __ldg(pts4 + rb);
+            it.xa = __ldg(reinterpret_cast<const uint4*>(xcol + ra * C));
+            it.xb = __ldg(reinterpret_cast<const uint4*>(xcol + rb * C));
+          };
+          // multiply `cur` while `nxt` loads; returns true when the warp has finished its queries of this pass
+          auto step = [&](const Item& cur, Item& nxt) -> bool {
+            if (new_query) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) d[i][e] = 0.f;
+              fcount = 0.f;
+              ql_next = grab();
+              row_pending = ql_next < cnt;
+              if (row_pending) issue_row(ql_next);
+              new_query = false;
+            }
+            const bool last = bm == 0;  // cur is the last block of its query
+            if (!last) {
+              issue_item(nxt);
+            } else if (row_pending) {
+              consume_row();
+              issue_item(nxt);
+            }
+            {
+              const float ax = cur.pa.x - cqx, ay = cur.pa.y - cqy, az = cur.pa.z - cqz;
+              const float bx = cur.pb.x - cqx, by = cur.pb.y - cqy, bz = cur.pb.z - cqz;
+              const float sa = fabsf(cur.pa.w) * a_scale;
+              const float sb = fabsf(cur.pb.w) * a_scale;
+              if (pass == 0) fcount += (cur.pa.w > 0.f ? 1.f : 0.f) + (cur.pb.w > 0.f ? 1.f : 0.f);
+              // A fragment: a0 = (k = g; h = 2t, 2t+1), a1 = (k = g+8; h = 2t, 2t+1), fp16 hi + lo
+              const float f00 = influence_fast(ax, ay, az, k0x, k0y, k0z, inv_extent) * sa;
+              const float f01 = influence_fast(bx, by, bz, k0x, k0y, k0z, inv_extent) * sb;
+              const float f10 = influence_fast(ax, ay, az, k1x, k1y, k1z, inv_extent) * (sa * k1_on);
+              const float f11 = influence_fast(bx, by, bz, k1x, k1y, k1z, inv_extent) * (sb * k1_on);
+              const __half2 h0 = __floats2half2_rn(f00, f01), h1 = __floats2half2_rn(f10, f11);
+              const float2 h0f = __half22float2(h0), h1f = __half22float2(h1);
+              const __half2 l0 = __floats2half2_rn(f00 - h0f.x, f01 - h0f.y), l1 = __floats2half2_rn(f10 - h1f.x, f11 - h1f.y);
+              const uint32_t ah0 = h2_bits(h0), ah1 = h2_bits(h1), al0 = h2_bits(l0), al1 = h2_bits(l1);
+              const uint32_t xa[4] = {cur.xa.x, cur.xa.y, cur.xa.z, cur.xa.w};
+              const uint32_t xb[4] = {cur.xb.x, cur.xb.y, cur.xb.z, cur.xb.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const uint32_t b0h = to_tf32(xav[i]), b1h = to_tf32(xbv[i]);
-                const uint32_t b0l = __float_as_uint(xav[i] - __uint_as_float(b0h));
-                const uint32_t b1l = __float_as_uint(xbv[i] - __uint_as_float(b1h));
-                mma_tf32(d[i], al, b0h, b1h);
-                mma_tf32(d[i], ah, b0l, b1l);
-                mma_tf32(d[i], ah, b0h, b1h);
+                // B fragment of channel tile i: (h = 2t, 2t+1; channel 4g+i)
+                const uint32_t bh = __byte_perm(xa[i], xb[i], 0x5410);  // (hi_a, hi_b)
+                const uint32_t bl = __byte_perm(xa[i], xb[i], 0x7632);  // (lo_a, lo_b)
+                mma_f16(d[i], al0, al1, bh);
+                mma_f16(d[i], ah0, ah1, bl);
+                mma_f16(d[i], ah0, ah1, bh);
               }
             }
-          }
-          // the A tile still feeds the MMAs of the previous pass until bar_done completes
-          if (first) {
-            if (seq > 0) mbar_wait(bar_done, (seq - 1) & 1);
-            first = false;
-          }
-          if (n < q_end) {
+            if (!last) return false;
+            // ---- the query is complete: split to fp16 pairs and store its two A rows ----
+            // the A tile still feeds the MMAs of the previous pass until bar_done completes
+            if (first) {
+              if (seq > 0) mbar_wait_sleep(bar_done, (seq - 1) & 1);
+              first = false;
+            }
             // this lane holds wf[k][8t..8t+7] for k = g (d[i][0], d[i][1]) and k = g+8 (d[i][2], d[i][3]):
             // one 16-byte chunk of fp16 each, K element = k * 32 + channel  ->  atom k / 2, chunk (k % 2) * 4 + t
             const uint32_t r0 = 2 * ql, r1 = 2 * ql + 1;
@@ -321,8 +407,8 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
                 const __half2 hh = __floats2half2_rn(v0, v1);
                 const float2 hf = __half22float2(hh);
                 const __half2 ll = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-                hi[p2] = *reinterpret_cast<const uint32_t*>(&hh);
-                lo[p2] = *reinterpret_cast<const uint32_t*>(&ll);
+                hi[p2] = h2_bits(hh);
+                lo[p2] = h2_bits(ll);
               }
               const int k = g + 8 * half;
               unsigned char* atom = sA + (k >> 1) * K::A_ATOM_BYTES;
@@ -330,22 +416,46 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
               *reinterpret_cast<uint4*>(atom + sw128_offset(r0, j)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<uint4*>(atom + sw128_offset(r1, j)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-            if (pass == 0 && lane == 0) inv_buf[ql] = 1.f / (float)max(nn, 1);
+            if (pass == 0) {
+              // a neighbour is replicated over g: count the g == 0 copies (lanes 0..3)
+              float c = g == 0 ? fcount : 0.f;
+              c += __shfl_xor_sync(kFull, c, 1);
+              c += __shfl_xor_sync(kFull, c, 2);
+              if (lane == 0) inv_buf[ql] = 1.f / fmaxf(c, 1.f);
+            }
+            ql = ql_next;
+            new_query = true;
+            cqx = qx;  // consume_row has already moved the issue side to the next query
+            cqy = qy;
+            cqz = qz;
+            return ql >= cnt;
+          };
+
+          issue_row(ql);
+          consume_row();
+          cqx = qx;
+          cqy = qy;
+          cqz = qz;
+          Item ia, ib;
+          issue_item(ia);
+          while (true) {
+            if (step(ia, ib)) break;
+            if (step(ib, ia)) break;
           }
         }
-        if (first && seq > 0) mbar_wait(bar_done, (seq - 1) & 1);  // warp without a query in this tile
+        if (first && seq > 0) mbar_wait_sleep(bar_done, (seq - 1) & 1);  // warp without a query in this tile
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_afull);
       }
       // ------------------------------ epilogue ------------------------------
-      mbar_wait(bar_done, (seq - 1) & 1);
+      mbar_wait_sleep(bar_done, (seq - 1) & 1);
       tc_fence_after();
-      {
+      if (warp < 16) {  // 4 TMEM lane quadrants x 4 column groups
         const int qd = warp & 3, cg = warp >> 2;
         const int ql = qd * 16 + (lane >> 1);
         const int n = q0 + ql;
-        const bool ok = ql < tq && n < q_end;
+        const bool ok = ql < cnt;
         const float scale = ok ? inv_buf[ql] * o_scale : 0.f;
         const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16);
 #pragma unroll 1
@@ -381,11 +491,11 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int pass = 0; pass < K::PASSES; ++pass, ++seq) {
-          mbar_wait(bar_afull, seq & 1);
+          mbar_wait_sleep(bar_afull, seq & 1);
           tc_fence_after();
           for (int a = 0; a < 8; ++a) {
             for (int sub = 0; sub < K::NSUB; ++sub) {
-              mbar_wait(&bar_full[stage], phase);
+              mbar_wait_sleep(&bar_full[stage], phase);
               tc_fence_after();
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
@@ -412,7 +522,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int blk = 0; blk < K::PASSES * K::BLOCKS_PER_PASS; ++blk) {
-          mbar_wait(&bar_empty[stage], phase ^ 1);
+          mbar_wait_sleep(&bar_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bar_full[stage], K::STAGE_BYTES);
           bulk_g2s(sRing + stage * K::STAGE_BYTES, wimg + (size_t)blk * K::STAGE_BYTES, K::STAGE_BYTES,
                    &bar_full[stage]);
@@ -437,12 +547,13 @@ int launch_tc(const float* q, const float* s, const void* idx, int row_stride, i
   SPR_CHECK_ARG(H <= 96, "kpconv_forward(mode 1): at most 96 neighbour columns are supported (got %d)", H);
   Carver cv(workspace, (size_t)-1);
   TcScales* sc = cv.take<TcScales>(1);
-  unsigned char* rowflag = cv.take<unsigned char>((size_t)ns + 1);
+  float4* pts4 = cv.take<float4>((size_t)ns);
+  uint32_t* x16 = cv.take<uint32_t>((size_t)ns * C);
   unsigned char* img = cv.take<unsigned char>(K::IMG_BYTES);
 
   SPR_CUDA(cudaMemsetAsync(sc, 0, sizeof(TcScales), stream));
-  const int n_xblocks = (ns + 1 + 7) / 8;
-  k_flags_absmax<<<n_xblocks + 8, 256, 0, stream>>>(x, ns, C, rowflag, w, KP * C * C, n_xblocks, sc);
+  const int n_xblocks = (ns + 7) / 8;
+  k_flags_absmax<<<n_xblocks + 8, 256, 0, stream>>>(x, s, ns, C, pts4, x16, w, KP * C * C, n_xblocks, sc);
   SPR_LAUNCH_CHECK("k_flags_absmax");
   constexpr int chunks = (int)(K::IMG_BYTES / 16);
   k_weight_image<C><<<(chunks + 255) / 256, 256, 0, stream>>>(w, sc, img);
@@ -459,19 +570,29 @@ int launch_tc(const float* q, const float* s, const void* idx, int row_stride, i
   const int n_tiles = (nq + tq - 1) / tq;
   static bool attr_set = false;
   if (!attr_set) {
-    SPR_CUDA(cudaFuncSetAttribute(k_kpconv_tc<C, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+    SPR_CUDA(cudaFuncSetAttribute(k_kpconv_tc<C, IdxT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+    SPR_CUDA(cudaFuncSetAttribute(k_kpconv_tc<C, IdxT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+    SPR_CUDA(cudaFuncSetAttribute(k_kpconv_tc<C, IdxT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
     attr_set = true;
   }
   const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-  k_kpconv_tc<C, IdxT><<<grid, K::THREADS, K::SMEM, stream>>>(q, s, static_cast<const IdxT*>(idx), row_stride, H, x, img,
-                                                              kp, rowflag, sc, extent, out, nq, ns, tq, n_tiles);
+  const IdxT* idx_t = static_cast<const IdxT*>(idx);
+  if (H <= 32)
+    k_kpconv_tc<C, IdxT, 1><<<grid, K::THREADS, K::SMEM, stream>>>(q, s, idx_t, row_stride, H, x16, img, kp, pts4, sc,
+                                                                   extent, out, nq, ns, tq, n_tiles);
+  else if (H <= 64)
+    k_kpconv_tc<C, IdxT, 2><<<grid, K::THREADS, K::SMEM, stream>>>(q, s, idx_t, row_stride, H, x16, img, kp, pts4, sc,
+                                                                   extent, out, nq, ns, tq, n_tiles);
+  else
+    k_kpconv_tc<C, IdxT, 3><<<grid, K::THREADS, K::SMEM, stream>>>(q, s, idx_t, row_stride, H, x16, img, kp, pts4, sc,
+                                                                   extent, out, nq, ns, tq, n_tiles);
   SPR_LAUNCH_CHECK("k_kpconv_tc");
   return SPR_OK;
 }
 
 template <int C>
 size_t tc_ws(int ns) {
-  return 256 + align_up((size_t)ns + 1, 256) + 256 + TcCfg<C>::IMG_BYTES + 256;
+  return 256 + align_up((size_t)ns * 16, 256) + align_up((size_t)ns * C * 4, 256) + 256 + TcCfg<C>::IMG_BYTES + 256;
 }
 
 }  // namespace

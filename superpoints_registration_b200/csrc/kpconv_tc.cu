@@ -2,27 +2,27 @@
 // (tcgen05.mma, accumulators in tensor memory, weights streamed by the TMA engine).  mode 1 of
 // spr_kpconv_forward; same mathematics as kpconv.cu (reference: kpconv_blocks.py:269-414).
 //
-// Work decomposition (one persistent CTA per SM, 18 warps):
-//   warps 0-15  producers.  One warp per query and pass of 32 input channels:
+// Work decomposition (one persistent CTA per SM, 20 warps):
+//   warps 0-17  producers.  One warp per query and pass of 32 input channels:
 //                    wf[k][c] = sum_h infl[h][k] * x[idx[h]][c]
-//               is a 16 x H x 32 matrix product done with warp-level mma.sync (3xTF32 split operands, fp32
+//               is a 16 x H x 32 matrix product done with warp-level mma.sync on fp16 (hi, lo) pairs (fp32
 //               accumulate); each lane evaluates exactly the influences of its A fragment and loads its B
-//               fragments as 16-byte pieces of the gathered feature rows, so nothing is staged or broadcast.
+//               fragments as 16-byte pieces of the gathered, pre-split feature rows: nothing staged or broadcast.
 //               The 15 x 32 block is split into fp16 (hi, lo) pairs and written to the A tile in shared memory
 //               (canonical K-major SWIZZLE_128B layout): row 2*ql holds hi, row 2*ql+1 holds lo, so a tile of
 //               up to 64 queries fills the M = 128 rows of one tcgen05.mma.
-//   warp 16     one thread issues the MMAs:  D[128 x 2C] += A[128 x 512] * B'[2C x 512]^T per pass of 32 input
+//   warp 18     one thread issues the MMAs:  D[128 x 2C] += A[128 x 512] * B'[2C x 512]^T per pass of 32 input
 //               channels, B' = [W_hi | W_lo] (fp16 pairs of the fp32 weights), so that
 //                    out = hi*W_hi + hi*W_lo + lo*W_hi (+ lo*W_lo)
 //               carries ~22 significant bits per operand: fp32-level accuracy from fp16 tensor-core products
 //               accumulated in fp32.  D stays in TMEM across the C/32 passes of a tile.
-//   warp 17     one thread streams the pre-swizzled weight image through a 3-stage shared-memory ring with bulk
+//   warp 19     one thread streams the pre-swizzled weight image through a 3-stage shared-memory ring with bulk
 //               async copies (TMA engine), completion on mbarriers.
 //   epilogue    producers read D with tcgen05.ld, add the hi/lo rows (adjacent lanes) and the two column
-//               halves, scale by 1/neighbour_count and store.
+//               halves, scale by 1/neighbour_count and store -- deferred into the next tile so that it never waits.
 // Operand scaling: fp16 has a 5-bit exponent, so wf is computed pre-multiplied by a power of two derived from
 // H*max|x| (kept <= 2^15) and W by one derived from max|W|; both are exact and undone in the epilogue.
-// Synchronisation is mbarrier-only in steady state: a_full (16 producer warps -> MMA), mma_done (MMA -> producers,
+// Synchronisation is mbarrier-only in steady state: a_full (18 producer warps -> MMA), mma_done (MMA -> producers,
 // frees the A tile and publishes D), full/empty per ring stage.  The MMAs of pass p run while the producers
 // already gather and accumulate the first queries of pass p+1; they only wait before overwriting the A tile.
 #include "spr_common.cuh"
@@ -43,57 +43,83 @@ struct TcScales {
 
 // power-of-two exponent e such that v * 2^e <= 2^target (v > 0 finite); 0 otherwise
 __device__ __forceinline__ int scale_exp(float v, int target) {
-  if (!(v > 0.f) || !isfinite(v)) return 0;
-  int ex;
-  frexpf(v, &ex);  // v = m * 2^ex, m in [0.5, 1)
-  int e = target - ex;
+  const int ef = (int)((__float_as_uint(v) >> 23) & 0xffu);
+  if (!(v > 0.f) || ef == 0 || ef == 255) return 0;  // zero, denormal, inf, nan
+  const int e = target - (ef - 126);                  // v = m * 2^(ef-126), m in [0.5, 1)
   return e < -60 ? -60 : (e > 60 ? 60 : e);
 }
+__device__ __forceinline__ float pow2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }  // |e| <= 126
 
 // ---------------------------------------------------------------------------------------------
 // pre-pass 1 (one warp per support row): the feature row pre-split into fp16 (hi, lo) pairs of x * 2^e with a
 // per-row power-of-two scale; the packed support point (x, y, z, +-2^-e) whose sign carries rowsum(x) > 0 (the
 // reference's neighbour_num mask, :409-412); max|x| and max|W| for the global scales of the tcgen05 operands
 // ---------------------------------------------------------------------------------------------
+template <int C>
 __global__ void __launch_bounds__(256) k_flags_absmax(const float* __restrict__ x, const float* __restrict__ s, int ns,
-                                                       int cin, float4* __restrict__ pts4, uint32_t* __restrict__ x16,
+                                                       float4* __restrict__ pts4, uint32_t* __restrict__ x16,
                                                        const float* __restrict__ w, int n_w, int n_xblocks,
                                                        TcScales* __restrict__ sc) {
   const int lane = threadIdx.x & 31;
-  if ((int)blockIdx.x >= n_xblocks) {  // weights
+  if ((int)blockIdx.x >= n_xblocks) {  // weights: 4 floats per thread
+    const int i = ((blockIdx.x - n_xblocks) * blockDim.x + threadIdx.x) * 4;
     float m = 0.f;
-    for (int i = (blockIdx.x - n_xblocks) * blockDim.x + threadIdx.x; i < n_w; i += (gridDim.x - n_xblocks) * blockDim.x)
-      m = fmaxf(m, fabsf(w[i]));
+    if (i + 3 < n_w) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(w + i));
+      m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    } else {
+      for (int k = i; k < n_w; ++k) m = fmaxf(m, fabsf(w[k]));
+    }
     m = warp_maxf(m);
-    if (lane == 0 && __float_as_uint(m) > sc->amax_w_bits) atomicMax(&sc->amax_w_bits, __float_as_uint(m));
+    if (lane == 0 && __float_as_uint(m) > *reinterpret_cast<volatile unsigned int*>(&sc->amax_w_bits))
+      atomicMax(&sc->amax_w_bits, __float_as_uint(m));
     return;
   }
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= ns) return;
+  // a group of G = min(C/4, 32) lanes owns one row, each lane 4 consecutive channels per step of 4*G
+  constexpr int G = C / 4 < 32 ? C / 4 : 32;
+  constexpr int RPW = 32 / G;  // rows per warp
+  constexpr int STEPS = C / (4 * G);
+  const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / G;
+  const int gl = lane % G;
+  const bool live = row < ns;
+  float4 v[STEPS];
   float acc = 0.f, m = 0.f;
-  for (int c = lane; c < cin; c += 32) {
-    const float v = x[(size_t)row * cin + c];
-    acc += v;
-    m = fmaxf(m, fabsf(v));
+#pragma unroll
+  for (int i = 0; i < STEPS; ++i) {
+    v[i] = live ? __ldg(reinterpret_cast<const float4*>(x + (size_t)row * C + (i * G + gl) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    acc += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
   }
-  acc = warp_sum(acc);
-  m = warp_maxf(m);
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(kFull, acc, o);
+    m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+  }
   // the row as (hi, lo) fp16 pairs of x * 2^e, e chosen per row so that max|x| * 2^e <= 2^14
   const int e = scale_exp(m, 14);
-  const float rs = ldexpf(1.f, e);
-  for (int c = lane; c < cin; c += 32) {
-    const float v = x[(size_t)row * cin + c] * rs;
-    const __half hi = __float2half_rn(v);
-    const __half lo = __float2half_rn(v - __half2float(hi));
-    x16[(size_t)row * cin + c] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+  const float rs = pow2i(e);
+  if (live) {
+#pragma unroll
+    for (int i = 0; i < STEPS; ++i) {
+      const float a[4] = {v[i].x * rs, v[i].y * rs, v[i].z * rs, v[i].w * rs};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __half hi = __float2half_rn(a[k]);
+        const __half lo = __float2half_rn(a[k] - __half2float(hi));
+        o[k] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+      }
+      *reinterpret_cast<uint4*>(x16 + (size_t)row * C + (i * G + gl) * 4) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (gl == 0) {
+      const float inv = pow2i(-e);
+      pts4[row] = make_float4(s[3 * (size_t)row], s[3 * (size_t)row + 1], s[3 * (size_t)row + 2], acc > 0.f ? inv : -inv);
+    }
   }
-  if (lane == 0) {
-    const float inv = ldexpf(1.f, -e);
-    pts4[row] = make_float4(s[3 * (size_t)row], s[3 * (size_t)row + 1], s[3 * (size_t)row + 2], acc > 0.f ? inv : -inv);
-    // one address for the whole grid: only touch it when this row raises the running maximum
-    if (__float_as_uint(m) > *reinterpret_cast<volatile unsigned int*>(&sc->amax_x_bits))
-      atomicMax(&sc->amax_x_bits, __float_as_uint(m));
-  }
+  // one address for the whole grid: reduce over the warp and only touch it when the running maximum rises
+  m = warp_maxf(m);
+  if (lane == 0 && __float_as_uint(m) > *reinterpret_cast<volatile unsigned int*>(&sc->amax_x_bits))
+    atomicMax(&sc->amax_x_bits, __float_as_uint(m));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -118,7 +144,7 @@ __global__ void __launch_bounds__(256) k_weight_image(const float* __restrict__ 
   const bool lo_part = ncol >= C;
   const int o = lo_part ? ncol - C : ncol;
   const int k = atom * 2 + (j >> 2);  // kernel point of this chunk (15 = zero padding)
-  const float tscale = ldexpf(1.f, scale_exp(__uint_as_float(sc->amax_w_bits), 14));
+  const float tscale = pow2i(scale_exp(__uint_as_float(sc->amax_w_bits), 14));
   __align__(16) __half h[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -141,7 +167,7 @@ struct TcCfg {
   static constexpr int NS = NCOL < 128 ? NCOL : 128;  // N of one MMA = rows of one ring stage
   static constexpr int NSUB = NCOL / NS;
   static constexpr int STAGE_BYTES = NS * 128;
-  static constexpr int NSTAGES = C == 32 ? 4 : 3;
+  static constexpr int NSTAGES = 3;
   static constexpr int BLOCKS_PER_PASS = 8 * NSUB;    // 8 K atoms of 64 fp16 per pass
   static constexpr int TQ = 64;
   static constexpr int WORKERS = 18;
@@ -180,10 +206,11 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<const uint32_t*>(&v); }
 // d[16x8] += a[16x8] * b[8x8], fp16 operands, fp32 accumulate (warp-level tensor path)
 __device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a0), "r"(a1), "r"(b0));
 }
@@ -240,14 +267,15 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
   if (warp < K::WORKERS) {
     // =========================================== producers ===========================================
     // Phase 1 of a query is itself a small matrix product, wf[16 x 32] = Infl^T[16 x H] * X[H x 32], done with
-    // warp-level mma.sync.m16n8k8 (TF32 operands split hi/lo -> 3 MMAs, fp32 accumulate): rows = kernel points,
+    // warp-level mma.sync.m16n8k8 on fp16 (hi, lo) pairs (3 MMAs, fp32 accumulate): rows = kernel points,
     // K = neighbours in blocks of 8, N = 4 tiles of 8 channels.  With g = lane / 4, t = lane % 4 a lane evaluates
-    // the influences of kernel points g and g+8 on neighbours t and t+4 of the block (exactly its A fragment) and
-    // loads channels 4g..4g+3 of those two neighbours' feature rows as one 16-byte vector (its B fragments for
-    // the four channel tiles: tile i pairs column g with channel 4g+i).  Nothing is staged in shared memory.
+    // the influences of kernel points g and g+8 on neighbours 2t and 2t+1 of the block (exactly its A fragment)
+    // and loads channels 4g..4g+3 of those two neighbours' pre-split feature rows as one 16-byte vector (its B
+    // fragments for the four channel tiles: tile i pairs column g with channel 4g+i).  Nothing is staged in
+    // shared memory and nothing is broadcast.
     const float inv_extent = 1.0f / extent;
-    const float a_scale = ldexpf(1.f, es);
-    const float o_scale = ldexpf(1.f, -(es + et));
+    const float a_scale = pow2i(es);
+    const float o_scale = pow2i(-(es + et));
     const int g = lane >> 2, t = lane & 3;
     const float k0x = sKp[3 * g], k0y = sKp[3 * g + 1], k0z = sKp[3 * g + 2];
     const float k1x = g < 7 ? sKp[3 * (g + 8)] : 0.f, k1y = g < 7 ? sKp[3 * (g + 8) + 1] : 0.f,
@@ -262,6 +290,41 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
       float4 pa, pb;   // packed support points of neighbours 2t, 2t+1: x, y, z, w = +-2^-e (sign = rowsum flag)
       uint4 xa, xb;    // their feature pieces: channels 4g..4g+3 as (hi, lo) fp16 pairs scaled by 2^e
     };  // an absent neighbour has pa/pb = 0: w = 0 zeroes its influences
+    // Epilogue of a finished tile: D (TMEM) -> registers, add the hi/lo rows (adjacent lanes) and the two column
+    // halves, scale, store.  Run DEFERRED: a warp executes it for tile t-1 just before its first A-tile store of
+    // tile t, when the MMAs of tile t-1 have long completed, so no producer ever idles on the tensor pipe.
+    auto epilogue = [&](int q0, int cnt, const float* inv_buf) {
+      tc_fence_after();
+      if (warp < 16) {  // 4 TMEM lane quadrants x 4 column groups
+        const int qd = warp & 3, cg = warp >> 2;
+        const int ql = qd * 16 + (lane >> 1);
+        const int n = q0 + ql;
+        const bool ok = ql < cnt;
+        const float scale = ok ? inv_buf[ql] * o_scale : 0.f;
+        const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16);
+#pragma unroll 1
+        for (int c0 = cg * (C / 4); c0 < (cg + 1) * (C / 4); c0 += 8) {
+          float v1[8], v2[8];
+          tmem_ld8(trow + c0, v1);
+          tmem_ld8(trow + C + c0, v2);
+          tmem_ld_wait();
+          float sum[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            sum[i] = v1[i] + v2[i];
+            sum[i] += __shfl_xor_sync(kFull, sum[i], 1);
+          }
+          if (ok) {
+            const int off = (lane & 1) * 4;
+            const float4 r = (lane & 1) ? make_float4(sum[4] * scale, sum[5] * scale, sum[6] * scale, sum[7] * scale)
+                                        : make_float4(sum[0] * scale, sum[1] * scale, sum[2] * scale, sum[3] * scale);
+            *reinterpret_cast<float4*>(out + (size_t)n * C + c0 + off) = r;
+          }
+        }
+      }
+      tc_fence_before();
+    };
+    int prev_q0 = 0, prev_cnt = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
       const int q0 = tile * tq;
       const int cnt = min(nq, q0 + tq) - q0;  // queries in this tile
@@ -311,6 +374,10 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
               if (32 * i < H) {
                 const bool valid = jrn[i] >= 0 && jrn[i] < ns;
                 jr[i] = valid ? jrn[i] : -1;
+                if (valid) {  // lanes = slots: two instructions pull the whole neighbourhood towards L1
+                  prefetch_l1(pts4 + jrn[i]);
+                  prefetch_l1(xcol - 4 * g + (size_t)jrn[i] * C);
+                }
                 const unsigned m = __ballot_sync(kFull, valid);
                 const unsigned b4 = ((m & 0xffu) ? 1u : 0u) | ((m & 0xff00u) ? 2u : 0u) | ((m & 0xff0000u) ? 4u : 0u) |
                                     ((m & 0xff000000u) ? 8u : 0u);
@@ -377,21 +444,27 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
               const uint32_t ah0 = h2_bits(h0), ah1 = h2_bits(h1), al0 = h2_bits(l0), al1 = h2_bits(l1);
               const uint32_t xa[4] = {cur.xa.x, cur.xa.y, cur.xa.z, cur.xa.w};
               const uint32_t xb[4] = {cur.xb.x, cur.xb.y, cur.xb.z, cur.xb.w};
+              // B fragment of channel tile i: (h = 2t, 2t+1; channel 4g+i).  Product-major order: consecutive
+              // MMAs write different accumulators, so they pipeline instead of waiting on each other.
+              uint32_t bh[4], bl[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                // B fragment of channel tile i: (h = 2t, 2t+1; channel 4g+i)
-                const uint32_t bh = __byte_perm(xa[i], xb[i], 0x5410);  // (hi_a, hi_b)
-                const uint32_t bl = __byte_perm(xa[i], xb[i], 0x7632);  // (lo_a, lo_b)
-                mma_f16(d[i], al0, al1, bh);
-                mma_f16(d[i], ah0, ah1, bl);
-                mma_f16(d[i], ah0, ah1, bh);
+                bh[i] = __byte_perm(xa[i], xb[i], 0x5410);  // (hi_a, hi_b)
+                bl[i] = __byte_perm(xa[i], xb[i], 0x7632);  // (lo_a, lo_b)
               }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) mma_f16(d[i], al0, al1, bh[i]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) mma_f16(d[i], ah0, ah1, bl[i]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) mma_f16(d[i], ah0, ah1, bh[i]);
             }
             if (!last) return false;
             // ---- the query is complete: split to fp16 pairs and store its two A rows ----
             // the A tile still feeds the MMAs of the previous pass until bar_done completes
             if (first) {
               if (seq > 0) mbar_wait_sleep(bar_done, (seq - 1) & 1);
+              if (pass == 0 && titer > 0) epilogue(prev_q0, prev_cnt, sInv + ((titer - 1) & 1) * K::TQ);
               first = false;
             }
             // this lane holds wf[k][8t..8t+7] for k = g (d[i][0], d[i][1]) and k = g+8 (d[i][2], d[i][3]):
@@ -443,42 +516,20 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
             if (step(ib, ia)) break;
           }
         }
-        if (first && seq > 0) mbar_wait_sleep(bar_done, (seq - 1) & 1);  // warp without a query in this tile
+        if (first) {  // warp without a query in this pass
+          if (seq > 0) mbar_wait_sleep(bar_done, (seq - 1) & 1);
+          if (pass == 0 && titer > 0) epilogue(prev_q0, prev_cnt, sInv + ((titer - 1) & 1) * K::TQ);
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_afull);
       }
-      // ------------------------------ epilogue ------------------------------
+      prev_q0 = q0;
+      prev_cnt = cnt;
+    }
+    if (titer > 0) {  // the last tile's epilogue
       mbar_wait_sleep(bar_done, (seq - 1) & 1);
-      tc_fence_after();
-      if (warp < 16) {  // 4 TMEM lane quadrants x 4 column groups
-        const int qd = warp & 3, cg = warp >> 2;
-        const int ql = qd * 16 + (lane >> 1);
-        const int n = q0 + ql;
-        const bool ok = ql < cnt;
-        const float scale = ok ? inv_buf[ql] * o_scale : 0.f;
-        const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16);
-#pragma unroll 1
-        for (int c0 = cg * (C / 4); c0 < (cg + 1) * (C / 4); c0 += 8) {
-          float v1[8], v2[8];
-          tmem_ld8(trow + c0, v1);
-          tmem_ld8(trow + C + c0, v2);
-          tmem_ld_wait();
-          float sum[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            sum[i] = v1[i] + v2[i];
-            sum[i] += __shfl_xor_sync(kFull, sum[i], 1);
-          }
-          if (ok) {
-            const int off = (lane & 1) * 4;
-            const float4 r = (lane & 1) ? make_float4(sum[4] * scale, sum[5] * scale, sum[6] * scale, sum[7] * scale)
-                                        : make_float4(sum[0] * scale, sum[1] * scale, sum[2] * scale, sum[3] * scale);
-            *reinterpret_cast<float4*>(out + (size_t)n * C + c0 + off) = r;
-          }
-        }
-      }
-      tc_fence_before();
+      epilogue(prev_q0, prev_cnt, sInv + ((titer - 1) & 1) * K::TQ);
     }
   } else if (warp == K::WORKERS) {
     // =========================================== MMA issuer ===========================================
@@ -552,8 +603,10 @@ int launch_tc(const float* q, const float* s, const void* idx, int row_stride, i
   unsigned char* img = cv.take<unsigned char>(K::IMG_BYTES);
 
   SPR_CUDA(cudaMemsetAsync(sc, 0, sizeof(TcScales), stream));
-  const int n_xblocks = (ns + 7) / 8;
-  k_flags_absmax<<<n_xblocks + 8, 256, 0, stream>>>(x, s, ns, C, pts4, x16, w, KP * C * C, n_xblocks, sc);
+  constexpr int rows_per_block = 8 * (C / 4 < 32 ? 32 / (C / 4) : 1);
+  const int n_xblocks = (ns + rows_per_block - 1) / rows_per_block;
+  const int n_wblocks = (KP * C * C + 1023) / 1024;
+  k_flags_absmax<C><<<n_xblocks + n_wblocks, 256, 0, stream>>>(x, s, ns, pts4, x16, w, KP * C * C, n_xblocks, sc);
   SPR_LAUNCH_CHECK("k_flags_absmax");
   constexpr int chunks = (int)(K::IMG_BYTES / 16);
   k_weight_image<C><<<(chunks + 255) / 256, 256, 0, stream>>>(w, sc, img);

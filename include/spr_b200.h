@@ -171,6 +171,47 @@ SPR_API int spr_weighted_procrustes(const float* d_a, const float* d_b, const fl
 SPR_API int spr_gather_rows3(const float* d_src, const int64_t* d_ind, const int32_t* d_row_pair_base, int n_rows, float* d_out,
                      void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Cross-encoder building blocks (reference: models/transformer/transformers.py:18-259, nn.MultiheadAttention
+ * with d_model 256 / 8 heads).  Tokens of all clouds are PACKED ([total_tokens, d]); the reference pads every
+ * cloud to the longest one and masks (utils/seq_manipulation.py:6-48).
+ *
+ * spr_split_f16: fp32 matrix -> fp16 (hi, lo) planes, x = hi + lo to ~22 bits; the first n_scaled columns are
+ *   multiplied by `scale` first (the query block of a packed QKV projection: log2(e)/sqrt(head_dim)).
+ * spr_attention_varlen: O[q, h] = softmax_k(Q[q,h] . K[k,h]) V[k,h] over the key segment of each query tile.
+ *   d_hi / d_lo: planes with `ld` halves per row holding Q (pre-scaled), K and V at column offsets q_col / k_col /
+ *   v_col (+ head * head_dim).  d_tiles: n_tiles x int32[4] = {first query row, query rows in the tile (<= 64),
+ *   first key row, key rows}.  d_out: fp32 [rows, out_ld].  Products are hi*hi + lo*hi + hi*lo on the tensor
+ *   cores with fp32 accumulation (fp32-level accuracy); the soft-max is online, nothing N x M is materialised.
+ * ------------------------------------------------------------------------------------------- */
+SPR_API int spr_split_f16(const float* d_x, int rows, int cols, int ld_in, void* d_hi, void* d_lo, int ld_out,
+                          int n_scaled, float scale, void* stream);
+SPR_API int spr_attention_varlen(const void* d_hi, const void* d_lo, int ld, int q_col, int k_col, int v_col,
+                                 int n_heads, int head_dim, const int32_t* d_tiles, int n_tiles, float* d_out,
+                                 int out_ld, void* d_out_img, float img_scale, void* stream);
+
+/* Dense layers on the tcgen05 tensor cores with fp32-level accuracy (nn.Linear of the cross-encoder:
+ * in/out projections of nn.MultiheadAttention and the FFN, transformers.py:184-245):
+ *     Y[T, N] = act( X[T, K] W[N, K]^T + b ) (+ residual)
+ * Operands are fp16 (hi, lo) pairs held in global memory as ready-made shared-memory images (K-major
+ * SWIZZLE_128B tiles) that the kernel fetches with bulk async copies:
+ *   A image (spr_gemm_a_image_bytes): written by spr_layernorm256_prepare (LayerNorm + positional embedding),
+ *     spr_gemm_prepare_input (plain fp32 rows), spr_attention_varlen (d_out_img) or a previous spr_gemm_tc
+ *     (out_mode 2); activations are multiplied by a power-of-two a_scale first.
+ *   W image (spr_gemm_w_image_bytes): spr_gemm_prepare_weight, once per weight, w_scale a power of two.
+ * spr_gemm_tc out_mode: 0 = fp32 rows [T, ld_out] (+ residual, ReLU), 1 = fp16 hi / lo planes [T, ld_out] with the
+ * first n_scaled columns multiplied by col_scale, 2 = A image of the next GEMM (K_next = N) scaled by next_scale.
+ * out_scale must be 1 / (a_scale * w_scale).  d_out may alias d_residual. */
+SPR_API size_t spr_gemm_a_image_bytes(int T, int K);
+SPR_API size_t spr_gemm_w_image_bytes(int N, int K);
+SPR_API int spr_gemm_prepare_weight(const float* d_w, int N, int K, float w_scale, void* d_img, void* stream);
+SPR_API int spr_gemm_prepare_input(const float* d_x, int T, int K, int ld, float a_scale, void* d_img, void* stream);
+SPR_API int spr_layernorm256_prepare(const float* d_x, const float* d_gamma, const float* d_beta, const float* d_pos,
+                                     int T, float eps, float a_scale, void* d_img, float* d_out_f32, void* stream);
+SPR_API int spr_gemm_tc(const void* d_a_img, const void* d_w_img, const float* d_bias, const float* d_residual,
+                        int ld_res, int T, int N, int K, float out_scale, int relu, int out_mode, void* d_out,
+                        void* d_out_lo, int ld_out, int n_scaled, float col_scale, float next_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,16 @@ _SIGNATURES = {
                                               c_float, c_int, c_int, c_fp, c_fp, c_fp, c_size_t, c_void_p]),
     "spr_weighted_procrustes": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_void_p]),
     "spr_gather_rows3": (c_int, [c_fp, c_fp, c_fp, c_int, c_fp, c_void_p]),
+    "spr_split_f16": (c_int, [c_fp, c_int, c_int, c_int, c_fp, c_fp, c_int, c_int, c_float, c_void_p]),
+    "spr_attention_varlen": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp, c_int, c_fp, c_int,
+                                     c_fp, c_float, c_void_p]),
+    "spr_gemm_a_image_bytes": (c_size_t, [c_int, c_int]),
+    "spr_gemm_w_image_bytes": (c_size_t, [c_int, c_int]),
+    "spr_gemm_prepare_weight": (c_int, [c_fp, c_int, c_int, c_float, c_fp, c_void_p]),
+    "spr_gemm_prepare_input": (c_int, [c_fp, c_int, c_int, c_int, c_float, c_fp, c_void_p]),
+    "spr_layernorm256_prepare": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_float, c_float, c_fp, c_fp, c_void_p]),
+    "spr_gemm_tc": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_fp, c_fp,
+                            c_int, c_int, c_float, c_float, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

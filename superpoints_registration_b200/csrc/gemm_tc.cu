@@ -1,0 +1,416 @@
+// gemm_tc.cu -- dense layers of the cross-encoder (and any Linear on the path) on the Blackwell tensor cores with
+// fp32-level accuracy:   Y[T, N] = act( X[T, K] W[N, K]^T + b ) (+ residual)
+// (reference: nn.Linear inside nn.MultiheadAttention in/out projections and the FFN, transformers.py:184-245).
+//
+// Operands are fp16 (hi, lo) pairs, x = hi + lo to ~22 bits.  The A operand stacks the two halves of a token as
+// adjacent rows (2r = hi, 2r+1 = lo), the B operand concatenates [W_hi | W_lo] along N, so ONE tcgen05.mma per
+// K step yields all four partial products; the epilogue adds the two rows (adjacent TMEM lanes -> one shuffle) and
+// the two column halves.  Both operands live in global memory as ready-made shared-memory images (canonical
+// K-major SWIZZLE_128B tiles, see tc05.cuh), so the producer is a bare bulk async copy per tile:
+//   A image : [m_tile = token / 64][k_atom = k / 64] x (128 rows x 128 B)         written by the previous kernel
+//   W image : [n_tile = n / 128][k_atom][sub = hi | lo] x (128 rows x 128 B)      built once per weight
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-5 = epilogue.
+// Two accumulator buffers (2 x 256 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// The epilogue can emit fp32 rows, fp16 hi/lo planes (for the attention kernel), or the A image of the next GEMM.
+#include "spr_common.cuh"
+#include "tc05.cuh"
+
+namespace spr {
+namespace {
+
+using namespace tc;
+
+constexpr int BM_TOK = 64;                 // tokens per tile (128 stacked rows)
+constexpr int BN = 128;                    // output columns per tile (256 B rows: hi | lo)
+constexpr int A_STAGE = 128 * 128;         // 16 KB
+constexpr int B_STAGE = 2 * 128 * 128;     // 32 KB
+constexpr int NSTAGES = 4;
+constexpr int GEMM_THREADS = 192;
+constexpr size_t GEMM_SMEM = 1024 + (size_t)NSTAGES * (A_STAGE + B_STAGE) + 256;
+
+enum { OUT_F32 = 0, OUT_PLANES = 1, OUT_AIMG = 2 };
+
+struct GemmArgs {
+  const unsigned char* a_img;
+  const unsigned char* w_img;
+  const float* bias;       // [N] or null
+  const float* residual;   // [T, ld_res] or null (OUT_F32 only)
+  float* out_f32;          // OUT_F32: [T, ld_out]
+  __half* out_hi;          // OUT_PLANES: [T, ld_out] ; OUT_AIMG: image base (as bytes)
+  __half* out_lo;          // OUT_PLANES only
+  int T, N, K;             // K padded to a multiple of 64 in both images
+  int ld_out, ld_res;
+  float out_scale;         // 1 / (a_scale * w_scale)
+  int relu;
+  int n_scaled;            // OUT_PLANES: columns < n_scaled are multiplied by col_scale (query pre-scaling)
+  float col_scale;
+  float next_scale;        // OUT_AIMG: activation scale of the next GEMM's A operand
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, int mode) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem =
+      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + NSTAGES * A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGES * (A_STAGE + B_STAGE));
+  uint64_t* bar_full = bars;            // [NSTAGES]
+  uint64_t* bar_empty = bars + 4;       // [NSTAGES]
+  uint64_t* bar_accf = bars + 8;        // [2] accumulator full
+  uint64_t* bar_acce = bars + 10;       // [2] accumulator empty
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 12);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int KA = g.K / 64;
+  const int m_tiles = (g.T + BM_TOK - 1) / BM_TOK, n_tiles = (g.N + BN - 1) / BN;
+  const int total = m_tiles * n_tiles;
+
+  if (tid == 0) {
+    for (int i = 0; i < NSTAGES; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_accf[i], 1);
+      mbar_init(&bar_acce[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int mt = tile / n_tiles, nt = tile % n_tiles;
+        for (int a = 0; a < KA; ++a) {
+          mbar_wait_sleep(&bar_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bar_full[stage], A_STAGE + B_STAGE);
+          bulk_g2s(sA + stage * A_STAGE, g.a_img + ((size_t)mt * KA + a) * A_STAGE, A_STAGE, &bar_full[stage]);
+          bulk_g2s(sB + stage * B_STAGE, g.w_img + ((size_t)nt * KA + a) * B_STAGE, B_STAGE, &bar_full[stage]);
+          if (++stage == NSTAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_f16_f32(128, 128);
+      const uint64_t adesc0 = desc_sw128_kmajor(smem_u32(sA));
+      const uint64_t bdesc0 = desc_sw128_kmajor(smem_u32(sB));
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait_sleep(&bar_acce[buf], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        for (int a = 0; a < KA; ++a) {
+          mbar_wait_sleep(&bar_full[stage], phase);
+          tc_fence_after();
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ad = adesc0 + (uint64_t)((stage * A_STAGE + kk * 32) >> 4);
+              const uint64_t bd = bdesc0 + (uint64_t)((stage * B_STAGE + sub * A_STAGE + kk * 32) >> 4);
+              umma_f16(tmem + buf * 256 + sub * 128, ad, bd, idesc, (a | kk) != 0);
+            }
+          umma_commit(&bar_empty[stage]);
+          if (++stage == NSTAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&bar_accf[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------ epilogue ------------------------------------
+    const int qd = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int row = qd * 32 + lane;                // stacked row: token 2r = hi, 2r+1 = lo
+    const int tok_l = row >> 1;
+    const int half_sel = lane & 1;                 // even lane stores columns c0..c0+3, odd lane c0+4..c0+7
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int mt = tile / n_tiles, nt = tile % n_tiles;
+      const int token = mt * BM_TOK + tok_l;
+      const bool tok_ok = token < g.T;
+      mbar_wait_sleep(&bar_accf[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16) + buf * 256;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 8) {
+        float v1[8], v2[8];
+        tmem_ld8(trow + c0, v1);
+        tmem_ld8(trow + 128 + c0, v2);
+        tmem_ld_wait();
+        float sum[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          sum[i] = v1[i] + v2[i];
+          sum[i] += __shfl_xor_sync(kFull, sum[i], 1);
+        }
+        const int n = nt * BN + c0 + half_sel * 4;
+        if (tok_ok && n < g.N) {
+          float y[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            y[i] = sum[half_sel * 4 + i] * g.out_scale;
+            if (g.bias) y[i] += __ldg(g.bias + n + i);
+          }
+          if (mode == OUT_F32) {
+            if (g.residual) {
+              const float4 r = *reinterpret_cast<const float4*>(g.residual + (size_t)token * g.ld_res + n);
+              y[0] += r.x;
+              y[1] += r.y;
+              y[2] += r.z;
+              y[3] += r.w;
+            }
+            if (g.relu) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) y[i] = fmaxf(y[i], 0.f);
+            }
+            *reinterpret_cast<float4*>(g.out_f32 + (size_t)token * g.ld_out + n) = make_float4(y[0], y[1], y[2], y[3]);
+          } else {
+            if (g.relu) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) y[i] = fmaxf(y[i], 0.f);
+            }
+            const float sc = mode == OUT_AIMG ? g.next_scale : (n < g.n_scaled ? g.col_scale : 1.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[i] *= sc;
+            const __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            const __half2 l0 = __floats2half2_rn(y[0] - f0.x, y[1] - f0.y), l1 = __floats2half2_rn(y[2] - f1.x, y[3] - f1.y);
+            const uint2 hv = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+            const uint2 lv = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+            if (mode == OUT_PLANES) {
+              *reinterpret_cast<uint2*>(g.out_hi + (size_t)token * g.ld_out + n) = hv;
+              *reinterpret_cast<uint2*>(g.out_lo + (size_t)token * g.ld_out + n) = lv;
+            } else {  // A image of the next GEMM, whose K is this N
+              const int KA2 = (g.N + 63) / 64;
+              unsigned char* blk = reinterpret_cast<unsigned char*>(g.out_hi) +
+                                   ((size_t)(token >> 6) * KA2 + (n >> 6)) * A_STAGE;
+              const uint32_t r2 = 2 * (token & 63), chunk = (n & 63) >> 3, inb = (n & 7) * 2;
+              *reinterpret_cast<uint2*>(blk + sw128_offset(r2, chunk) + inb) = hv;
+              *reinterpret_cast<uint2*>(blk + sw128_offset(r2 + 1, chunk) + inb) = lv;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_acce[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// LayerNorm over 256 channels (+ positional embedding) -> A image (scaled fp16 hi/lo stacked rows); one warp per token
+__global__ void __launch_bounds__(256) k_ln_to_aimg(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, const float* __restrict__ pos,
+                                                     int T, float eps, float a_scale, unsigned char* __restrict__ img,
+                                                     float* __restrict__ out_f32) {
+  const int lane = threadIdx.x & 31;
+  const int token = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (token >= T) return;
+  const float* xr = x + (size_t)token * 256 + lane * 8;
+  const float4 a = *reinterpret_cast<const float4*>(xr), b = *reinterpret_cast<const float4*>(xr + 4);
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.f / 256.f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] -= mean;
+    q += v[i] * v[i];
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / 256.f) + eps);
+  if (gamma) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = v[i] * rstd * __ldg(gamma + lane * 8 + i) + __ldg(beta + lane * 8 + i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= rstd;
+  }
+  if (pos) {
+    const float* pr = pos + (size_t)token * 256 + lane * 8;
+    const float4 pa = *reinterpret_cast<const float4*>(pr), pb = *reinterpret_cast<const float4*>(pr + 4);
+    v[0] += pa.x; v[1] += pa.y; v[2] += pa.z; v[3] += pa.w;
+    v[4] += pb.x; v[5] += pb.y; v[6] += pb.z; v[7] += pb.w;
+  }
+  if (out_f32) {
+    float* o = out_f32 + (size_t)token * 256 + lane * 8;
+    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (img) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float y0 = v[2 * i] * a_scale, y1 = v[2 * i + 1] * a_scale;
+      const __half2 hh = __floats2half2_rn(y0, y1);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+      hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
+      lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    // 256 channels = 4 K atoms; lane l owns chunk l % 8 of atom l / 8
+    unsigned char* blk = img + ((size_t)(token >> 6) * 4 + (lane >> 3)) * A_STAGE;
+    const uint32_t r2 = 2 * (token & 63);
+    *reinterpret_cast<uint4*>(blk + sw128_offset(r2, lane & 7)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(blk + sw128_offset(r2 + 1, lane & 7)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// fp32 rows -> A image (generic K, multiple of 8); one thread per 8 consecutive channels
+__global__ void __launch_bounds__(256) k_f32_to_aimg(const float* __restrict__ x, int T, int K, int ld, float a_scale,
+                                                      unsigned char* __restrict__ img) {
+  const int KA = (K + 63) / 64;
+  const int chunks_per_row = KA * 8;
+  const size_t total = (size_t)T * chunks_per_row;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int token = (int)(i / chunks_per_row), ch = (int)(i % chunks_per_row);
+    const int k0 = ch * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (k0 + e < K) ? x[(size_t)token * ld + k0 + e] * a_scale : 0.f;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+      hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    unsigned char* blk = img + ((size_t)(token >> 6) * KA + (ch >> 3)) * A_STAGE;
+    const uint32_t r2 = 2 * (token & 63);
+    *reinterpret_cast<uint4*>(blk + sw128_offset(r2, ch & 7)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(blk + sw128_offset(r2 + 1, ch & 7)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// W [N, K] fp32 -> W image (scaled fp16 hi | lo), one thread per 16-byte chunk
+__global__ void __launch_bounds__(256) k_weight_to_img(const float* __restrict__ w, int N, int K, float w_scale,
+                                                        unsigned char* __restrict__ img) {
+  const int KA = (K + 63) / 64, n_tiles = (N + BN - 1) / BN;
+  const size_t total = (size_t)n_tiles * KA * 2 * 128 * 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i & 7);
+    const int r = (int)((i >> 3) & 127);
+    const int sub = (int)((i >> 10) & 1);
+    const size_t blk = i >> 11;  // nt * KA + a
+    const int a = (int)(blk % KA), nt = (int)(blk / KA);
+    const int n = nt * BN + r;
+    __align__(16) __half h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = a * 64 + j * 8 + e;
+      const float v = (n < N && k < K) ? w[(size_t)n * K + k] * w_scale : 0.f;
+      const __half hi = __float2half_rn(v);
+      h[e] = sub ? __float2half_rn(v - __half2float(hi)) : hi;
+    }
+    *reinterpret_cast<uint4*>(img + blk * B_STAGE + (size_t)sub * A_STAGE + sw128_offset(r, j)) =
+        *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+}  // namespace
+}  // namespace spr
+
+using namespace spr;
+
+extern "C" size_t spr_gemm_a_image_bytes(int T, int K) {
+  return (size_t)((T + BM_TOK - 1) / BM_TOK) * ((K + 63) / 64) * A_STAGE;
+}
+extern "C" size_t spr_gemm_w_image_bytes(int N, int K) {
+  return (size_t)((N + BN - 1) / BN) * ((K + 63) / 64) * B_STAGE;
+}
+
+extern "C" int spr_gemm_prepare_weight(const float* d_w, int N, int K, float w_scale, void* d_img, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPR_CHECK_ARG(d_w && d_img && N > 0 && K > 0, "gemm_prepare_weight: bad arguments");
+  const size_t total = spr_gemm_w_image_bytes(N, K) / 16;
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  k_weight_to_img<<<grid, 256, 0, stream>>>(d_w, N, K, w_scale, static_cast<unsigned char*>(d_img));
+  SPR_LAUNCH_CHECK("k_weight_to_img");
+  return SPR_OK;
+}
+
+extern "C" int spr_gemm_prepare_input(const float* d_x, int T, int K, int ld, float a_scale, void* d_img, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPR_CHECK_ARG(d_x && d_img && T > 0 && K > 0 && ld >= K, "gemm_prepare_input: bad arguments");
+  const size_t total = (size_t)T * ((K + 63) / 64) * 8;
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  k_f32_to_aimg<<<grid, 256, 0, stream>>>(d_x, T, K, ld, a_scale, static_cast<unsigned char*>(d_img));
+  SPR_LAUNCH_CHECK("k_f32_to_aimg");
+  return SPR_OK;
+}
+
+extern "C" int spr_layernorm256_prepare(const float* d_x, const float* d_gamma, const float* d_beta, const float* d_pos,
+                                        int T, float eps, float a_scale, void* d_img, float* d_out_f32, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPR_CHECK_ARG(d_x && T > 0 && (d_img || d_out_f32), "layernorm256_prepare: bad arguments");
+  SPR_CHECK_ARG((d_gamma == nullptr) == (d_beta == nullptr), "layernorm256_prepare: gamma and beta go together");
+  k_ln_to_aimg<<<(T + 7) / 8, 256, 0, stream>>>(d_x, d_gamma, d_beta, d_pos, T, eps, a_scale,
+                                                static_cast<unsigned char*>(d_img), d_out_f32);
+  SPR_LAUNCH_CHECK("k_ln_to_aimg");
+  return SPR_OK;
+}
+
+extern "C" int spr_gemm_tc(const void* d_a_img, const void* d_w_img, const float* d_bias, const float* d_residual,
+                           int ld_res, int T, int N, int K, float out_scale, int relu, int out_mode, void* d_out,
+                           void* d_out_lo, int ld_out, int n_scaled, float col_scale, float next_scale, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPR_CHECK_ARG(d_a_img && d_w_img && d_out && T > 0 && N > 0 && K > 0, "gemm_tc: bad arguments");
+  SPR_CHECK_ARG((N & 3) == 0, "gemm_tc: N must be a multiple of 4 (got %d)", N);
+  SPR_CHECK_ARG(out_mode >= 0 && out_mode <= 2, "gemm_tc: unknown output mode %d", out_mode);
+  SPR_CHECK_ARG(out_mode != OUT_PLANES || d_out_lo, "gemm_tc: plane output needs both planes");
+  SPR_CHECK_ARG(out_mode == OUT_AIMG || (ld_out >= N && (ld_out & 3) == 0), "gemm_tc: bad output row stride");
+  SPR_CHECK_ARG(!d_residual || (out_mode == OUT_F32 && (ld_res & 3) == 0), "gemm_tc: residual only with fp32 output");
+  GemmArgs g;
+  g.a_img = static_cast<const unsigned char*>(d_a_img);
+  g.w_img = static_cast<const unsigned char*>(d_w_img);
+  g.bias = d_bias;
+  g.residual = d_residual;
+  g.out_f32 = static_cast<float*>(d_out);
+  g.out_hi = static_cast<__half*>(d_out);
+  g.out_lo = static_cast<__half*>(d_out_lo);
+  g.T = T;
+  g.N = N;
+  g.K = (K + 63) / 64 * 64;
+  g.ld_out = ld_out;
+  g.ld_res = ld_res;
+  g.out_scale = out_scale;
+  g.relu = relu;
+  g.n_scaled = n_scaled;
+  g.col_scale = col_scale;
+  g.next_scale = next_scale;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPR_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    attr_set = true;
+  }
+  const int total = ((T + BM_TOK - 1) / BM_TOK) * ((N + BN - 1) / BN);
+  const int grid = total < kNumSMs ? total : kNumSMs;
+  k_gemm_tc<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(g, out_mode);
+  SPR_LAUNCH_CHECK("k_gemm_tc");
+  return SPR_OK;
+}

@@ -114,6 +114,45 @@ class TransformerCrossEncoderLayer(nn.Module):
     def _ffn(self, x):
         return self.linear2(self.activation(self.linear1(x)))
 
+    # ---- packed-token path: our attention kernel, no padding, src and tgt clouds in one launch -------------
+    def _attend_packed(self, mha, xp, tiles):
+        d = xp.shape[1]
+        qkv = F.linear(xp, mha.in_proj_weight, mha.in_proj_bias)                     # [T, 3d]
+        hi, lo = ops.split_f16(qkv, n_scaled=d, scale=math.log2(math.e) / math.sqrt(d // mha.num_heads))
+        o = ops.attention_varlen(hi, lo, tiles, mha.num_heads, 0, d, 2 * d, d)
+        return F.linear(o, mha.out_proj.weight, mha.out_proj.bias)
+
+    def forward_packed(self, x, pos, sa_tiles, ca_tiles):
+        """x, pos: [total_tokens, d] with the clouds stacked [src_0..src_B-1, tgt_0..tgt_B-1]; same arithmetic as
+        forward_pre (transformers.py:184-245) with value = key (sa_val_has_pos_emb / ca_val_has_pos_emb = True)."""
+        if not (self.normalize_before and self.sa_val_has_pos_emb and self.ca_val_has_pos_emb):
+            raise NotImplementedError("packed cross-encoder: pre-norm with positional values only (every shipped config)")
+        xn = self.norm1(x)
+        x = x + self._attend_packed(self.self_attn, xn if pos is None else xn + pos, sa_tiles)
+        xn = self.norm2(x)
+        x = x + self._attend_packed(self.multihead_attn, xn if pos is None else xn + pos, ca_tiles)
+        return x + self._ffn(self.norm3(x))
+
+    def forward_fused(self, x, pos, sa_tiles, ca_tiles, img, img_ffn):
+        """Same arithmetic as forward_packed with every dense layer on the tcgen05 GEMM (ops.gemm_tc) and the
+        element-wise work folded into producers / epilogues: LayerNorm + positional embedding write the GEMM operand
+        image, the QKV projection writes the fp16 planes of the attention kernel, attention writes the operand image
+        of the output projection, the output projection / FFN2 add the residual, FFN1 applies ReLU and writes FFN2's
+        operand image.  x is updated in place; 11 launches per layer, no intermediate fp32 activation besides x."""
+        if self.activation is not F.relu:
+            raise NotImplementedError("fused cross-encoder: ReLU feed-forward only (every shipped config)")
+        T, d = x.shape
+        for mha, norm, tiles in ((self.self_attn, self.norm1, sa_tiles), (self.multihead_attn, self.norm2, ca_tiles)):
+            ops.layernorm256_prepare(x, norm.weight, norm.bias, pos, norm.eps, img)
+            hi, lo = ops.gemm_tc(img, ops.weight_image(mha.in_proj_weight), mha.in_proj_bias, T, ops.OUT_PLANES,
+                                 n_scaled=d, col_scale=math.log2(math.e) / math.sqrt(d // mha.num_heads))
+            ops.attention_varlen(hi, lo, tiles, mha.num_heads, 0, d, 2 * d, d, out_image=img, image_scale=ops.A_SCALE)
+            ops.gemm_tc(img, ops.weight_image(mha.out_proj.weight), mha.out_proj.bias, T, ops.OUT_F32, residual=x, out=x)
+        ops.layernorm256_prepare(x, self.norm3.weight, self.norm3.bias, None, self.norm3.eps, img)
+        ops.gemm_tc(img, ops.weight_image(self.linear1.weight), self.linear1.bias, T, ops.OUT_AIMG, relu=True, out=img_ffn)
+        ops.gemm_tc(img_ffn, ops.weight_image(self.linear2.weight), self.linear2.bias, T, ops.OUT_F32, residual=x, out=x)
+        return x
+
     def forward(self, src, tgt, src_key_padding_mask=None, tgt_key_padding_mask=None, src_pos=None, tgt_pos=None):
         sm, tm = src_key_padding_mask, tgt_key_padding_mask
         if self.normalize_before:  # transformers.py:184-245
@@ -142,6 +181,7 @@ class TransformerCrossEncoder(nn.Module):
         self.layers = nn.ModuleList([copy.deepcopy(cross_encoder_layer) for _ in range(num_layers)])
         self.num_layers = num_layers
         self.norm = norm
+        self.fused = True  # dense layers on the tcgen05 GEMM (False: cuBLAS fp32 through torch)
 
     def forward(self, src, tgt, src_key_padding_mask=None, tgt_key_padding_mask=None, src_pos=None, tgt_pos=None):
         for layer in self.layers:
@@ -150,6 +190,34 @@ class TransformerCrossEncoder(nn.Module):
         if self.norm is not None:
             src, tgt = self.norm(src), self.norm(tgt)
         return src.unsqueeze(0), tgt.unsqueeze(0)
+
+    def supports_packed(self) -> bool:
+        l0 = self.layers[0]
+        return bool(l0.normalize_before and l0.sa_val_has_pos_emb and l0.ca_val_has_pos_emb
+                    and l0.self_attn.embed_dim // l0.self_attn.num_heads == 32)
+
+    def forward_packed(self, x, pos, lens):
+        """x, pos: [total_tokens, d], clouds stacked [src..., tgt...]; lens: token count of every cloud (2B entries).
+        Returns the conditioned features in the same packed layout."""
+        B = len(lens) // 2
+        offs = [0]
+        for n in lens:
+            offs.append(offs[-1] + n)
+        partner = list(range(B, 2 * B)) + list(range(0, B))
+        sa_tiles = ops.attention_tiles(offs[:-1], lens, offs[:-1], lens, x.device)
+        ca_tiles = ops.attention_tiles(offs[:-1], lens, [offs[p] for p in partner], [lens[p] for p in partner], x.device)
+        if self.fused and x.shape[1] == 256:
+            x = x.clone()  # updated in place layer by layer
+            img = ops.gemm_a_image(x.shape[0], 256, x.device)
+            img_ffn = ops.gemm_a_image(x.shape[0], self.layers[0].linear1.out_features, x.device)
+            for layer in self.layers:
+                x = layer.forward_fused(x, pos, sa_tiles, ca_tiles, img, img_ffn)
+            if self.norm is None:
+                return x
+            return ops.layernorm256_prepare(x, self.norm.weight, self.norm.bias, None, self.norm.eps, None, out_f32=True)
+        for layer in self.layers:
+            x = layer.forward_packed(x, pos, sa_tiles, ca_tiles)
+        return self.norm(x) if self.norm is not None else x
 
 
 # ------------------------------------------------------------------------------------------------
@@ -182,6 +250,7 @@ class RegTR(nn.Module):
         self.overlap_predictor = nn.Linear(cfg.d_embed, 1)
         self.dual_normalization = True  # hard-coded in the reference (:120)
         self.return_attn = True          # outputs['attn'] (:295); set False to skip materialising N x M matrices
+        self.packed_transformer = True   # packed tokens + our attention kernel; False = padded PyTorch modules
 
     def load_reference_state_dict(self, state_dict):
         """Load a reference checkpoint; training-only keys (loss modules) are ignored."""
@@ -206,28 +275,38 @@ class RegTR(nn.Module):
 
         feats_un, _ = self.kpf_encoder(feats0, meta)
         both = self.feat_proj(feats_un)
-        src_feats_un, tgt_feats_un = split_src_tgt(both, slens_c)
         src_xyz_c, tgt_xyz_c = split_src_tgt(pts_c, slens_c)
-        src_pe, tgt_pe = split_src_tgt(self.pos_embed(pts_c), slens_c)
-        src_pe_pad, _, _ = pad_sequence(src_pe)
-        tgt_pe_pad, _, _ = pad_sequence(tgt_pe)
-        src_pad, src_mask, _ = pad_sequence(src_feats_un, require_padding_mask=True)
-        tgt_pad, tgt_mask, _ = pad_sequence(tgt_feats_un, require_padding_mask=True)
         use_pe = cfg.transformer_encoder_has_pos_emb
-        src_cond, tgt_cond = self.transformer_encoder(
-            src_pad, tgt_pad, src_key_padding_mask=src_mask, tgt_key_padding_mask=tgt_mask,
-            src_pos=src_pe_pad if use_pe else None, tgt_pos=tgt_pe_pad if use_pe else None)
-
-        src_overlap = torch.sigmoid(self.overlap_predictor(src_cond))
-        tgt_overlap = torch.sigmoid(self.overlap_predictor(tgt_cond))
-        src_overlap_list = unpad_sequences(src_overlap, src_slens_c)
-        tgt_overlap_list = unpad_sequences(tgt_overlap, tgt_slens_c)
-        src_cond_list = unpad_sequences(src_cond, src_slens_c)
-        tgt_cond_list = unpad_sequences(tgt_cond, tgt_slens_c)
-
-        # packed (sum N, D) features in pair order for the batched matching kernels
-        src_packed = src_cond[0].transpose(0, 1)[~src_mask]
-        tgt_packed = tgt_cond[0].transpose(0, 1)[~tgt_mask]
+        pe = self.pos_embed(pts_c)
+        if self.packed_transformer and self.transformer_encoder.supports_packed():
+            # tokens stay packed [src_0..src_B-1, tgt_0..tgt_B-1]: no padding, no masks, one launch per operator
+            cond = self.transformer_encoder.forward_packed(both, pe if use_pe else None, slens_c)
+            overlap = torch.sigmoid(self.overlap_predictor(cond))
+            total_src_c = sum(src_slens_c)
+            src_packed, tgt_packed = cond[:total_src_c], cond[total_src_c:]
+            src_cond_list = [c.unsqueeze(0) for c in torch.split(src_packed, src_slens_c)]
+            tgt_cond_list = [c.unsqueeze(0) for c in torch.split(tgt_packed, tgt_slens_c)]
+            src_overlap_list = [c.unsqueeze(0) for c in torch.split(overlap[:total_src_c], src_slens_c)]
+            tgt_overlap_list = [c.unsqueeze(0) for c in torch.split(overlap[total_src_c:], tgt_slens_c)]
+        else:
+            src_feats_un, tgt_feats_un = split_src_tgt(both, slens_c)
+            src_pe, tgt_pe = split_src_tgt(pe, slens_c)
+            src_pe_pad, _, _ = pad_sequence(src_pe)
+            tgt_pe_pad, _, _ = pad_sequence(tgt_pe)
+            src_pad, src_mask, _ = pad_sequence(src_feats_un, require_padding_mask=True)
+            tgt_pad, tgt_mask, _ = pad_sequence(tgt_feats_un, require_padding_mask=True)
+            src_cond, tgt_cond = self.transformer_encoder(
+                src_pad, tgt_pad, src_key_padding_mask=src_mask, tgt_key_padding_mask=tgt_mask,
+                src_pos=src_pe_pad if use_pe else None, tgt_pos=tgt_pe_pad if use_pe else None)
+            src_overlap = torch.sigmoid(self.overlap_predictor(src_cond))
+            tgt_overlap = torch.sigmoid(self.overlap_predictor(tgt_cond))
+            src_overlap_list = unpad_sequences(src_overlap, src_slens_c)
+            tgt_overlap_list = unpad_sequences(tgt_overlap, tgt_slens_c)
+            src_cond_list = unpad_sequences(src_cond, src_slens_c)
+            tgt_cond_list = unpad_sequences(tgt_cond, tgt_slens_c)
+            # packed (sum N, D) features in pair order for the batched matching kernels
+            src_packed = src_cond[0].transpose(0, 1)[~src_mask]
+            tgt_packed = tgt_cond[0].transpose(0, 1)[~tgt_mask]
         pose, attn_list, val_list, ind_list, src_pts_list, tgt_pts_list = self._match_and_solve(
             src_packed, tgt_packed, pts_c, src_slens_c, tgt_slens_c)
 

@@ -276,3 +276,146 @@ def gather_rows3(src, ind, row_base) -> torch.Tensor:
     rc = L.spr_gather_rows3(s.data_ptr(), ii.data_ptr(), rb.data_ptr(), ii.shape[0], out.data_ptr(), _stream())
     _lib.check(rc, "spr_gather_rows3")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# cross-encoder building blocks (packed tokens)
+# ------------------------------------------------------------------------------------------------
+
+def split_f16(x: torch.Tensor, n_scaled: int = 0, scale: float = 1.0):
+    """fp32 [rows, cols] -> fp16 (hi, lo) planes with x = hi + lo to ~22 bits; columns < n_scaled are pre-multiplied
+    by `scale`."""
+    L = _lib.lib()
+    xx = _f32c(x, "x")
+    rows, cols = xx.shape
+    hi = torch.empty((rows, cols), dtype=torch.float16, device=xx.device)
+    lo = torch.empty_like(hi)
+    rc = L.spr_split_f16(xx.data_ptr(), rows, cols, cols, hi.data_ptr(), lo.data_ptr(), cols, int(n_scaled), float(scale),
+                         _stream())
+    _lib.check(rc, "spr_split_f16")
+    return hi, lo
+
+
+def attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q: int = 64) -> torch.Tensor:
+    """Tile list of spr_attention_varlen: one row {first query row, rows, first key row, key rows} per 64 queries."""
+    rows = []
+    for qo, qn, ko, kn in zip(q_offsets, q_lens, kv_offsets, kv_lens):
+        if qn <= 0:
+            continue
+        if kn <= 0:
+            raise RuntimeError("attention over an empty key segment")
+        for q0 in range(0, qn, block_q):
+            rows.append((qo + q0, min(block_q, qn - q0), ko, kn))
+    return torch.tensor(rows, dtype=torch.int32).to(device, non_blocking=True)
+
+
+def attention_varlen(hi: torch.Tensor, lo: torch.Tensor, tiles: torch.Tensor, n_heads: int, q_col: int, k_col: int,
+                     v_col: int, d_model: int, out_image: Optional[torch.Tensor] = None, image_scale: float = 1.0):
+    """Multi-head attention over packed tokens; hi/lo are the fp16 planes of the (pre-scaled) QKV projection.
+    With out_image the result is written as the A image of the output projection (gemm_tc) instead of fp32 rows."""
+    L = _lib.lib()
+    _need_cuda(hi, "hi")
+    if hi.dtype != torch.float16 or lo.dtype != torch.float16 or hi.shape != lo.shape or not hi.is_contiguous() \
+            or not lo.is_contiguous():
+        raise RuntimeError("attention_varlen: hi/lo must be contiguous fp16 tensors of the same shape")
+    rows, ld = hi.shape
+    head_dim = d_model // n_heads
+    out = None if out_image is not None else torch.empty((rows, d_model), dtype=torch.float32, device=hi.device)
+    rc = L.spr_attention_varlen(hi.data_ptr(), lo.data_ptr(), ld, q_col, k_col, v_col, n_heads, head_dim,
+                                tiles.data_ptr(), tiles.shape[0], _ptr(out), d_model, _ptr(out_image),
+                                float(image_scale), _stream())
+    _lib.check(rc, "spr_attention_varlen")
+    return out_image if out is None else out
+
+
+# ---- tensor-core dense layers (gemm_tc.cu) ---------------------------------------------------------
+A_SCALE = 16.0          # power-of-two scale of activations inside the fp16 operand images
+OUT_F32, OUT_PLANES, OUT_AIMG = 0, 1, 2
+
+
+def gemm_a_image(T: int, K: int, device) -> torch.Tensor:
+    return torch.empty(_lib.lib().spr_gemm_a_image_bytes(int(T), int(K)), dtype=torch.uint8, device=device)
+
+
+class WeightImage:
+    """fp16 (hi | lo) shared-memory image of an nn.Linear weight [N, K], built once per weight version."""
+
+    def __init__(self, weight: torch.Tensor):
+        L = _lib.lib()
+        w = _f32c(weight.detach(), "weight")
+        self.N, self.K = w.shape
+        amax = float(w.abs().max())
+        import math as _m
+        self.w_scale = 2.0 ** _m.floor(_m.log2(512.0 / amax)) if amax > 0 and _m.isfinite(amax) else 1.0
+        self.img = torch.empty(L.spr_gemm_w_image_bytes(self.N, self.K), dtype=torch.uint8, device=w.device)
+        rc = L.spr_gemm_prepare_weight(w.data_ptr(), self.N, self.K, self.w_scale, self.img.data_ptr(), _stream())
+        _lib.check(rc, "spr_gemm_prepare_weight")
+        self.key = (weight.data_ptr(), weight._version)
+
+
+_WEIGHT_IMAGES = {}
+
+
+def weight_image(weight: torch.Tensor) -> WeightImage:
+    key = (weight.data_ptr(), weight._version)
+    wi = _WEIGHT_IMAGES.get(id(weight))
+    if wi is None or wi.key != key:
+        wi = WeightImage(weight)
+        _WEIGHT_IMAGES[id(weight)] = wi
+    return wi
+
+
+def gemm_prepare_input(x: torch.Tensor, img: Optional[torch.Tensor] = None) -> torch.Tensor:
+    L = _lib.lib()
+    xx = _f32c(x, "x")
+    T, K = xx.shape
+    if img is None:
+        img = gemm_a_image(T, K, xx.device)
+    rc = L.spr_gemm_prepare_input(xx.data_ptr(), T, K, K, A_SCALE, img.data_ptr(), _stream())
+    _lib.check(rc, "spr_gemm_prepare_input")
+    return img
+
+
+def layernorm256_prepare(x, gamma, beta, pos, eps: float, img: Optional[torch.Tensor], out_f32: bool = False):
+    """LayerNorm over 256 channels (+ pos) -> A image and/or fp32 rows."""
+    L = _lib.lib()
+    xx = _f32c(x, "x")
+    T, d = xx.shape
+    if d != 256:
+        raise RuntimeError("layernorm256_prepare: d_model must be 256")
+    out = torch.empty_like(xx) if out_f32 else None
+    rc = L.spr_layernorm256_prepare(xx.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(pos), T, float(eps), A_SCALE,
+                                    _ptr(img), _ptr(out), _stream())
+    _lib.check(rc, "spr_layernorm256_prepare")
+    return out
+
+
+def gemm_tc(a_img: torch.Tensor, wi: WeightImage, bias, T: int, mode: int = OUT_F32, residual=None, relu: bool = False,
+            out=None, out_lo=None, n_scaled: int = 0, col_scale: float = 1.0):
+    """Y = act(X W^T + b) (+ residual) on the tcgen05 tensor cores from operand images; see include/spr_b200.h."""
+    L = _lib.lib()
+    N, K = wi.N, wi.K
+    dev = a_img.device
+    ld_out = N
+    if mode == OUT_F32:
+        if out is None:
+            out = torch.empty((T, N), dtype=torch.float32, device=dev)
+    elif mode == OUT_PLANES:
+        if out is None:
+            out = torch.empty((T, N), dtype=torch.float16, device=dev)
+            out_lo = torch.empty_like(out)
+    else:
+        if out is None:
+            out = gemm_a_image(T, N, dev)
+    rc = L.spr_gemm_tc(a_img.data_ptr(), wi.img.data_ptr(), _ptr(bias), _ptr(residual),
+                       residual.shape[1] if residual is not None else 0, int(T), N, K, 1.0 / (A_SCALE * wi.w_scale),
+                       1 if relu else 0, int(mode), out.data_ptr(), _ptr(out_lo), ld_out, int(n_scaled),
+                       float(col_scale), A_SCALE, _stream())
+    _lib.check(rc, "spr_gemm_tc")
+    return (out, out_lo) if mode == OUT_PLANES else out
+
+
+def linear_tc(x: torch.Tensor, weight: torch.Tensor, bias=None, relu: bool = False, residual=None) -> torch.Tensor:
+    """Drop-in for F.linear on fp32 rows: builds the operand image, then one tensor-core GEMM."""
+    img = gemm_prepare_input(x)
+    return gemm_tc(img, weight_image(weight), bias, x.shape[0], OUT_F32, residual=residual, relu=relu)

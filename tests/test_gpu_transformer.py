@@ -1,0 +1,152 @@
+"""Packed cross-encoder path (our attention kernel) against PyTorch fp32/fp64 references."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from superpoints_registration_b200 import config as cfgs
+from superpoints_registration_b200 import ops
+from superpoints_registration_b200.model import RegTR
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ref_attention(qkv, tiles_spec, n_heads, d):
+    """fp64 soft-max attention per segment: tiles_spec = [(q_off, q_len, kv_off, kv_len)]."""
+    out = torch.zeros((qkv.shape[0], d), dtype=torch.float64)
+    hd = d // n_heads
+    x = qkv.double().cpu()
+    for qo, qn, ko, kn in tiles_spec:
+        q = x[qo:qo + qn, :d].view(qn, n_heads, hd).transpose(0, 1)
+        k = x[ko:ko + kn, d:2 * d].view(kn, n_heads, hd).transpose(0, 1)
+        v = x[ko:ko + kn, 2 * d:].view(kn, n_heads, hd).transpose(0, 1)
+        p = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(hd), dim=-1)
+        out[qo:qo + qn] = (p @ v).transpose(0, 1).reshape(qn, d)
+    return out
+
+
+@pytest.mark.parametrize("lens", [[5, 64, 65, 130], [1, 1], [700, 333, 128, 257, 64, 63]])
+def test_attention_varlen_against_fp64(lens):
+    torch.manual_seed(len(lens))
+    d, nh = 256, 8
+    T = sum(lens)
+    qkv = (torch.randn(T, 3 * d) * 2.0).to(DEV)
+    offs = np.concatenate([[0], np.cumsum(lens)]).tolist()
+    B = len(lens) // 2
+    partner = list(range(B, 2 * B)) + list(range(B))
+    for kind in ("self", "cross"):
+        ko = offs[:-1] if kind == "self" else [offs[p] for p in partner]
+        kn = lens if kind == "self" else [lens[p] for p in partner]
+        tiles = ops.attention_tiles(offs[:-1], lens, ko, kn, DEV)
+        hi, lo = ops.split_f16(qkv, n_scaled=d, scale=math.log2(math.e) / math.sqrt(d // nh))
+        out = ops.attention_varlen(hi, lo, tiles, nh, 0, d, 2 * d, d).cpu().double()
+        ref = _ref_attention(qkv, list(zip(offs[:-1], lens, ko, kn)), nh, d)
+        err = (out - ref).abs().max().item()
+        # logits reach +-16 here: 22-bit operand products leave ~|S| * 2^-22 relative error on P, the same order as fp32
+        assert err <= 6e-6 * ref.abs().max().item(), (kind, err, ref.abs().max().item())
+
+
+def test_split_f16_reconstructs_fp32():
+    x = (torch.randn(300, 768, device=DEV) * 3)
+    hi, lo = ops.split_f16(x, n_scaled=256, scale=0.25)
+    want = x.clone()
+    want[:, :256] *= 0.25
+    err = (hi.float() + lo.float() - want).abs().max().item()
+    assert err <= 4e-7 * want.abs().max().item()
+
+
+def test_packed_encoder_matches_padded_pytorch_modules():
+    torch.manual_seed(0)
+    cfg = cfgs.threedmatch_config()
+    model = RegTR(cfg).to(DEV).eval()
+    enc = model.transformer_encoder
+    lens = [150, 97, 64, 201]     # 2 pairs
+    T = sum(lens)
+    x = torch.randn(T, cfg.d_embed, device=DEV)
+    pos = torch.randn(T, cfg.d_embed, device=DEV) * 0.5
+    with torch.no_grad():
+        got = enc.forward_packed(x, pos, lens)
+        # padded reference through the nn.MultiheadAttention modules
+        parts, pparts = torch.split(x, lens), torch.split(pos, lens)
+        pad = lambda seqs: torch.nn.utils.rnn.pad_sequence(list(seqs))
+        mask = lambda ls: (torch.arange(max(ls), device=DEV)[None, :] >= torch.tensor(ls, device=DEV)[:, None])
+        s, t = enc(pad(parts[:2]), pad(parts[2:]), src_key_padding_mask=mask(lens[:2]), tgt_key_padding_mask=mask(lens[2:]),
+                   src_pos=pad(pparts[:2]), tgt_pos=pad(pparts[2:]))
+    ref = torch.cat([s[0, :lens[0], 0], s[0, :lens[1], 1], t[0, :lens[2], 0], t[0, :lens[3], 1]])
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-5 * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("T,N,K", [(64, 128, 64), (200, 256, 256), (1000, 768, 256), (333, 256, 1024), (70, 32, 96)])
+def test_gemm_tc_against_fp64(T, N, K):
+    torch.manual_seed(T + N + K)
+    x = torch.randn(T, K, device=DEV) * 1.5
+    w = torch.randn(N, K, device=DEV) / math.sqrt(K)
+    b = torch.randn(N, device=DEV)
+    res = torch.randn(T, N, device=DEV)
+    ref = (x.double() @ w.double().t() + b.double())
+    y = ops.linear_tc(x, w, b)
+    assert (y.double() - ref).abs().max().item() <= 3e-6 * ref.abs().max().item()
+    y2 = ops.linear_tc(x, w, b, residual=res)
+    assert (y2.double() - (ref + res.double())).abs().max().item() <= 3e-6 * ref.abs().max().item()
+    y3 = ops.linear_tc(x, w, None, relu=True)
+    assert (y3.double() - (x.double() @ w.double().t()).clamp(min=0)).abs().max().item() <= 3e-6 * ref.abs().max().item()
+
+
+def test_gemm_tc_plane_and_image_outputs_chain():
+    """QKV-style plane output and FFN-style image chaining (GEMM -> ReLU -> image -> GEMM)."""
+    torch.manual_seed(5)
+    T, d, dff = 300, 256, 1024
+    x = torch.randn(T, d, device=DEV)
+    w1 = torch.randn(dff, d, device=DEV) / math.sqrt(d)
+    b1 = torch.randn(dff, device=DEV) * 0.1
+    w2 = torch.randn(d, dff, device=DEV) / math.sqrt(dff)
+    b2 = torch.randn(d, device=DEV) * 0.1
+    img = ops.gemm_prepare_input(x)
+    hi, lo = ops.gemm_tc(img, ops.weight_image(w1), b1, T, ops.OUT_PLANES, n_scaled=256, col_scale=0.5)
+    want = x.double() @ w1.double().t() + b1.double()
+    want[:, :256] *= 0.5
+    got = hi.double() + lo.double()
+    assert (got - want).abs().max().item() <= 3e-6 * want.abs().max().item()
+    h_img = ops.gemm_tc(img, ops.weight_image(w1), b1, T, ops.OUT_AIMG, relu=True)
+    y = ops.gemm_tc(h_img, ops.weight_image(w2), b2, T, ops.OUT_F32, residual=x)
+    ref = (x.double() @ w1.double().t() + b1.double()).clamp(min=0) @ w2.double().t() + b2.double() + x.double()
+    assert (y.double() - ref).abs().max().item() <= 3e-6 * ref.abs().max().item()
+
+
+def test_layernorm_prepare_matches_torch():
+    torch.manual_seed(6)
+    T = 130
+    x = torch.randn(T, 256, device=DEV) * 2 + 0.3
+    g, b = torch.randn(256, device=DEV), torch.randn(256, device=DEV)
+    pos = torch.randn(T, 256, device=DEV)
+    out = ops.layernorm256_prepare(x, g, b, pos, 1e-5, None, out_f32=True)
+    ref = F.layer_norm(x, (256,), g, b, 1e-5) + pos
+    assert (out - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
+    # the image feeds a GEMM that reproduces LN(x) @ I
+    img = ops.gemm_a_image(T, 256, DEV)
+    ops.layernorm256_prepare(x, g, b, pos, 1e-5, img)
+    eye = torch.eye(256, device=DEV)
+    y = ops.gemm_tc(img, ops.weight_image(eye), None, T, ops.OUT_F32)
+    assert (y - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
+
+
+def test_fused_encoder_matches_packed_torch_linears():
+    torch.manual_seed(1)
+    cfg = cfgs.threedmatch_config()
+    model = RegTR(cfg).to(DEV).eval()
+    enc = model.transformer_encoder
+    lens = [150, 97, 64, 201, 130, 33]
+    T = sum(lens)
+    x = torch.randn(T, cfg.d_embed, device=DEV)
+    pos = torch.randn(T, cfg.d_embed, device=DEV) * 0.5
+    with torch.no_grad():
+        enc.fused = True
+        got = enc.forward_packed(x, pos, lens)
+        enc.fused = False
+        ref = enc.forward_packed(x, pos, lens)
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-5 * ref.abs().max().item(), (err, ref.abs().max().item())

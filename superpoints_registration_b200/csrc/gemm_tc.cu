@@ -9,7 +9,7 @@
 // K-major SWIZZLE_128B tiles, see tc05.cuh), so the producer is a bare bulk async copy per tile:
 //   A image : [m_tile = token / 64][k_atom = k / 64] x (128 rows x 128 B)         written by the previous kernel
 //   W image : [n_tile = n / 128][k_atom][sub = hi | lo] x (128 rows x 128 B)      built once per weight
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-5 = epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-9 = epilogue.
 // Two accumulator buffers (2 x 256 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 // The epilogue can emit fp32 rows, fp16 hi/lo planes (for the attention kernel), or the A image of the next GEMM.
 #include "spr_common.cuh"
@@ -25,7 +25,8 @@ constexpr int BN = 128;                    // output columns per tile (256 B row
 constexpr int A_STAGE = 128 * 128;         // 16 KB
 constexpr int B_STAGE = 2 * 128 * 128;     // 32 KB
 constexpr int NSTAGES = 4;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;               // 2 per TMEM lane quadrant, each owning 64 of the 128 tile columns
+constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;
 constexpr size_t GEMM_SMEM = 1024 + (size_t)NSTAGES * (A_STAGE + B_STAGE) + 256;
 
 enum { OUT_F32 = 0, OUT_PLANES = 1, OUT_AIMG = 2 };
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_accf[i], 1);
-      mbar_init(&bar_acce[i], 4);
+      mbar_init(&bar_acce[i], EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -135,7 +136,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
     __syncwarp();
   } else {
     // ------------------------------------ epilogue ------------------------------------
+    // Software-pipelined over 8-column groups: the TMEM loads of group i+1 and the bias / residual loads of group
+    // i are in flight while group i is reduced, so the per-tile latency chain is one TMEM round trip, not sixteen.
     const int qd = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int chalf = (warp - 2) >> 2;             // which 64 columns of the tile
     const int row = qd * 32 + lane;                // stacked row: token 2r = hi, 2r+1 = lo
     const int tok_l = row >> 1;
     const int half_sel = lane & 1;                 // even lane stores columns c0..c0+3, odd lane c0+4..c0+7
@@ -147,48 +151,46 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
       const bool tok_ok = token < g.T;
       mbar_wait_sleep(&bar_accf[buf], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16) + buf * 256;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 8) {
-        float v1[8], v2[8];
-        tmem_ld8(trow + c0, v1);
-        tmem_ld8(trow + 128 + c0, v2);
-        tmem_ld_wait();
+      const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16) + buf * 256 + chalf * 64;
+      float v1[2][8], v2[2][8];
+      tmem_ld8(trow, v1[0]);
+      tmem_ld8(trow + 128, v2[0]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int cur = i & 1;
+        const int c0 = chalf * 64 + i * 8;
+        const int n = nt * BN + c0 + half_sel * 4;
+        const bool ok = tok_ok && n < g.N;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), rv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && g.bias) bv = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+        if (ok && mode == OUT_F32 && g.residual)
+          rv = *reinterpret_cast<const float4*>(g.residual + (size_t)token * g.ld_res + n);
+        tmem_ld_wait(v1[cur], v2[cur]);  // group i has landed
+        if (i + 1 < 8) {
+          tmem_ld8(trow + (i + 1) * 8, v1[cur ^ 1]);
+          tmem_ld8(trow + 128 + (i + 1) * 8, v2[cur ^ 1]);
+        }
         float sum[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          sum[i] = v1[i] + v2[i];
-          sum[i] += __shfl_xor_sync(kFull, sum[i], 1);
+        for (int e = 0; e < 8; ++e) {
+          sum[e] = v1[cur][e] + v2[cur][e];
+          sum[e] += __shfl_xor_sync(kFull, sum[e], 1);
         }
-        const int n = nt * BN + c0 + half_sel * 4;
-        if (tok_ok && n < g.N) {
+        if (ok) {
           float y[4];
+          const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+          const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            y[i] = sum[half_sel * 4 + i] * g.out_scale;
-            if (g.bias) y[i] += __ldg(g.bias + n + i);
+          for (int e = 0; e < 4; ++e) {
+            y[e] = (half_sel ? sum[4 + e] : sum[e]) * g.out_scale + bb[e] + rr[e];
+            if (g.relu) y[e] = fmaxf(y[e], 0.f);
           }
           if (mode == OUT_F32) {
-            if (g.residual) {
-              const float4 r = *reinterpret_cast<const float4*>(g.residual + (size_t)token * g.ld_res + n);
-              y[0] += r.x;
-              y[1] += r.y;
-              y[2] += r.z;
-              y[3] += r.w;
-            }
-            if (g.relu) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) y[i] = fmaxf(y[i], 0.f);
-            }
             *reinterpret_cast<float4*>(g.out_f32 + (size_t)token * g.ld_out + n) = make_float4(y[0], y[1], y[2], y[3]);
           } else {
-            if (g.relu) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) y[i] = fmaxf(y[i], 0.f);
-            }
             const float sc = mode == OUT_AIMG ? g.next_scale : (n < g.n_scaled ? g.col_scale : 1.f);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) y[i] *= sc;
+            for (int e = 0; e < 4; ++e) y[e] *= sc;
             const __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
             const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
             const __half2 l0 = __floats2half2_rn(y[0] - f0.x, y[1] - f0.y), l1 = __floats2half2_rn(y[2] - f1.x, y[3] - f1.y);

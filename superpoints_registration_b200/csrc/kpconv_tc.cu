@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
           float v1[8], v2[8];
           tmem_ld8(trow + c0, v1);
           tmem_ld8(trow + C + c0, v2);
-          tmem_ld_wait();
+          tmem_ld_wait(v1, v2);
           float sum[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {

@@ -83,6 +83,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// same, and ties the loaded registers to the wait so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(float (&a)[8], float (&b)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]),
+                 "+f"(b[0]), "+f"(b[1]), "+f"(b[2]), "+f"(b[3]), "+f"(b[4]), "+f"(b[5]), "+f"(b[6]), "+f"(b[7])
+               :
+               : "memory");
+}
 
 // ---- UMMA descriptors ------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: LBO = 1 (unused), SBO = 1024 B between 8-row groups,

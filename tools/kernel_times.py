@@ -1,0 +1,41 @@
+"""Per-kernel device time of one forward pass (torch.profiler / CUPTI), aggregated by kernel name.
+Development aid: python tools/kernel_times.py [--pairs 8]"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+import superpoints_registration_b200 as spr
+from superpoints_registration_b200 import synthetic
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--pairs", type=int, default=8)
+ap.add_argument("--points", type=int, default=20000)
+ap.add_argument("--top", type=int, default=32)
+args = ap.parse_args()
+dev = "cuda:0"
+cfg = spr.threedmatch_config()
+torch.manual_seed(0); np.random.seed(0)
+model = spr.RegTR(cfg).to(dev).eval()
+model.return_attn = False
+data = synthetic.make_batch("3dmatch", args.pairs, seed=2, n_points=args.points)
+batch = {"src_xyz": [torch.from_numpy(c).to(dev) for c in data["src_xyz"]],
+         "tgt_xyz": [torch.from_numpy(c).to(dev) for c in data["tgt_xyz"]]}
+for _ in range(3):
+    model(dict(batch))
+torch.cuda.synchronize()
+N = 3
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(N):
+        model(dict(batch))
+    torch.cuda.synchronize()
+rows = [(e.key, e.device_time_total / N, e.count / N) for e in prof.key_averages() if e.device_time_total > 0 and e.device_type.name == "CUDA"]
+rows.sort(key=lambda r: -r[1])
+tot = sum(r[1] for r in rows)
+print(f"total device time per forward: {tot / 1e3:.3f} ms over {sum(r[2] for r in rows):.0f} kernels")
+for k, t, c in rows[:args.top]:
+    print(f"{t / 1e3:8.3f} ms {100 * t / tot:5.1f}%  n={c:5.0f}  {k[:100]}")

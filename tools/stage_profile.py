@@ -49,18 +49,14 @@ def staged(rec):
         t, e = begin()
         both = model.feat_proj(feats)
         pts_c = meta["points"][-1]
-        sf, tf = M.split_src_tgt(both, slens_c)
-        spe, tpe = M.split_src_tgt(model.pos_embed(pts_c), slens_c)
-        spp, _, _ = M.pad_sequence(spe); tpp, _, _ = M.pad_sequence(tpe)
-        sp, sm, _ = M.pad_sequence(sf, require_padding_mask=True)
-        tp, tm, _ = M.pad_sequence(tf, require_padding_mask=True)
-        mark("proj+pad", t, e)
+        pe = model.pos_embed(pts_c)
+        mark("proj+pe", t, e)
         t, e = begin()
-        sc, tc = model.transformer_encoder(sp, tp, src_key_padding_mask=sm, tgt_key_padding_mask=tm, src_pos=spp, tgt_pos=tpp)
+        cond = model.transformer_encoder.forward_packed(both, pe, slens_c)
         mark("transformer", t, e)
         t, e = begin()
-        s_packed = sc[0].transpose(0, 1)[~sm]; t_packed = tc[0].transpose(0, 1)[~tm]
-        out = model._match_and_solve(s_packed, t_packed, pts_c, slens_c[:B], slens_c[B:])
+        ts = sum(slens_c[:B])
+        out = model._match_and_solve(cond[:ts], cond[ts:], pts_c, slens_c[:B], slens_c[B:])
         mark("match+pose", t, e)
     return meta
 
@@ -84,5 +80,16 @@ print(f"{'total':12s} host {tot_h:8.2f} ms   device {tot_d:8.2f} ms   -> {B / to
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(args.iters):
     model(dict(batch))
+t_host = (time.perf_counter() - t0) / args.iters
 torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / args.iters
-print(f"unstaged forward: {1e3 * dt:.2f} ms -> {B / dt:.1f} pairs/s")
+print(f"unstaged forward: {1e3 * dt:.2f} ms -> {B / dt:.1f} pairs/s   (host returns after {1e3 * t_host:.2f} ms per forward)")
+# host-side cost alone: profile the Python of one forward
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable()
+for _ in range(3):
+    model(dict(batch))
+torch.cuda.synchronize(); pr.disable()
+st = pstats.Stats(pr); st.sort_stats("cumulative")
+import io
+buf = io.StringIO(); st.stream = buf; st.print_stats(22)
+print("\n".join(buf.getvalue().splitlines()[:45]))

@@ -64,60 +64,107 @@ __device__ __forceinline__ float influence_fast(float cx, float cy, float cz, fl
                                                 float inv_extent) {
   const float dx = cx - kx, dy = cy - ky, dz = cz - kz;
   const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-  const float d = d2 * rsqrtf(fmaxf(d2, 1e-30f));
+  float d;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(d2));  // MUFU.SQRT, rel. error ~2^-23, sqrt(0) = 0
   return fmaxf(fmaf(-d, inv_extent, 1.f), 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Cin == 1 (first encoder block, features = ones): one warp per query, lanes = neighbours.
+// Cin == 1 (first encoder block, features = ones): one warp per query.
+// Lane (g = lane / 4, t = lane % 4) owns kernel points g and g + 8 and, in every block of 8 neighbours, slots 2t and
+// 2t + 1: the 16 x 8 influence evaluations of a block are spread over the warp without redundancy, a lane
+// accumulates its two kernel points directly, and the sum over neighbours is two shuffles at the end (instead of
+// one butterfly per kernel point).  wf[15] is then broadcast and contracted with W[15, Cout] held in registers
+// (Cout <= 64) or shared memory.
 // ---------------------------------------------------------------------------------------------
-template <typename IdxT>
+template <typename IdxT, int NO>  // NO = Cout / 32 outputs per lane
 __global__ void __launch_bounds__(256)
     k_kpconv_cin1(const float* __restrict__ q, const float* __restrict__ s, const IdxT* __restrict__ idx,
-                  int row_stride, int H, const float* __restrict__ x, const float* __restrict__ w, int cout,
+                  int row_stride, int H, const float* __restrict__ x, const float* __restrict__ w,
                   const float* __restrict__ kp, float extent, float* __restrict__ out, int nq, int ns) {
+  constexpr int COUT = NO * 32;
   extern __shared__ float sm[];
-  float* s_w = sm;                  // [KP][cout]
-  float* s_kp = sm + KP * cout;     // [KP*3]
-  for (int i = threadIdx.x; i < KP * cout; i += blockDim.x) s_w[i] = w[i];
-  for (int i = threadIdx.x; i < KP * 3; i += blockDim.x) s_kp[i] = kp[i];
-  __syncthreads();
+  float* s_w = sm;  // [KP][COUT], only used when NO > 2
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  if (NO > 2) {
+    for (int i = threadIdx.x; i < KP * COUT; i += blockDim.x) s_w[i] = w[i];
+    __syncthreads();
+  }
+  float wreg[NO <= 2 ? KP : 1][NO <= 2 ? NO : 1];
+  if (NO <= 2) {
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+#pragma unroll
+      for (int o = 0; o < NO; ++o) wreg[k][o] = __ldg(w + k * COUT + lane + 32 * o);
+  }
+  const float inv_extent = 1.f / extent;
+  const float k0x = __ldg(kp + 3 * g), k0y = __ldg(kp + 3 * g + 1), k0z = __ldg(kp + 3 * g + 2);
+  const int g1 = g < 7 ? g + 8 : 0;
+  const float k1x = __ldg(kp + 3 * g1), k1y = __ldg(kp + 3 * g1 + 1), k1z = __ldg(kp + 3 * g1 + 2);
+  const float k1_on = g < 7 ? 1.f : 0.f;
+  const int nblk = (H + 7) >> 3;
   for (int n = blockIdx.x * warps + (threadIdx.x >> 5); n < nq; n += gridDim.x * warps) {
     const float qx = __ldg(q + 3 * (size_t)n), qy = __ldg(q + 3 * (size_t)n + 1), qz = __ldg(q + 3 * (size_t)n + 2);
-    float wf[KP];
+    // neighbour row, lanes = slots (coalesced)
+    int jr[3];
 #pragma unroll
-    for (int k = 0; k < KP; ++k) wf[k] = 0.f;
-    int nn = 0;
-    for (int h0 = 0; h0 < H; h0 += 32) {
-      const int h = h0 + lane;
-      int j = ns;
-      if (h < H) j = load_idx(idx + (size_t)n * row_stride + h);
-      const bool valid = j >= 0 && j < ns;
-      float xv = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
-      if (valid) {
-        xv = __ldg(x + j);
-        cx = __ldg(s + 3 * (size_t)j) - qx;
-        cy = __ldg(s + 3 * (size_t)j + 1) - qy;
-        cz = __ldg(s + 3 * (size_t)j + 2) - qz;
+    for (int i = 0; i < 3; ++i) {
+      const int h = 32 * i + lane;
+      int j = -1;
+      if (h < H) {
+        j = load_idx(idx + (size_t)n * row_stride + h);
+        if (j < 0 || j >= ns) j = -1;
       }
-      nn += __popc(__ballot_sync(kFull, valid && xv > 0.f));
-      if (valid) {
+      jr[i] = j;
+    }
+    float acc0 = 0.f, acc1 = 0.f, cnt = 0.f;
+    for (int b = 0; b < nblk; ++b) {
+      const int src = (b & 3) * 8 + 2 * t;
+      const int jsel = (b >> 2) == 0 ? jr[0] : ((b >> 2) == 1 ? jr[1] : jr[2]);
+      const int ja = __shfl_sync(kFull, jsel, src);
+      const int jb = __shfl_sync(kFull, jsel, src + 1);
+      if (!__any_sync(kFull, ja >= 0 || jb >= 0)) continue;  // padding block
+      float xa = 0.f, xb = 0.f, ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+      if (ja >= 0) {
+        xa = __ldg(x + ja);
+        ax = __ldg(s + 3 * (size_t)ja) - qx;
+        ay = __ldg(s + 3 * (size_t)ja + 1) - qy;
+        az = __ldg(s + 3 * (size_t)ja + 2) - qz;
+      }
+      if (jb >= 0) {
+        xb = __ldg(x + jb);
+        bx = __ldg(s + 3 * (size_t)jb) - qx;
+        by = __ldg(s + 3 * (size_t)jb + 1) - qy;
+        bz = __ldg(s + 3 * (size_t)jb + 2) - qz;
+      }
+      // an absent neighbour has x = 0 and therefore contributes nothing
+      acc0 = fmaf(influence_fast(ax, ay, az, k0x, k0y, k0z, inv_extent), xa, acc0);
+      acc0 = fmaf(influence_fast(bx, by, bz, k0x, k0y, k0z, inv_extent), xb, acc0);
+      acc1 = fmaf(influence_fast(ax, ay, az, k1x, k1y, k1z, inv_extent), xa, acc1);
+      acc1 = fmaf(influence_fast(bx, by, bz, k1x, k1y, k1z, inv_extent), xb, acc1);
+      cnt += (xa > 0.f ? 1.f : 0.f) + (xb > 0.f ? 1.f : 0.f);  // neighbour_num: rowsum(x) = x for Cin = 1
+    }
+    acc0 += __shfl_xor_sync(kFull, acc0, 1);
+    acc0 += __shfl_xor_sync(kFull, acc0, 2);
+    acc1 += __shfl_xor_sync(kFull, acc1, 1);
+    acc1 += __shfl_xor_sync(kFull, acc1, 2);
+    acc1 *= k1_on;
+    cnt += __shfl_xor_sync(kFull, cnt, 1);
+    cnt += __shfl_xor_sync(kFull, cnt, 2);   // every g group now holds the full count
+    const float inv = 1.f / fmaxf(cnt, 1.f);
+    float o[NO];
 #pragma unroll
-        for (int k = 0; k < KP; ++k)
-          wf[k] = fmaf(influence(cx, cy, cz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], extent), xv, wf[k]);
-      }
+    for (int i = 0; i < NO; ++i) o[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const float wf = __shfl_sync(kFull, k < 8 ? acc0 : acc1, 4 * (k & 7));
+#pragma unroll
+      for (int i = 0; i < NO; ++i) o[i] = fmaf(wf, NO <= 2 ? wreg[k][i] : s_w[k * COUT + lane + 32 * i], o[i]);
     }
 #pragma unroll
-    for (int k = 0; k < KP; ++k) wf[k] = warp_sum(wf[k]);
-    const float inv = 1.f / (float)max(nn, 1);
-    for (int o = lane; o < cout; o += 32) {
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < KP; ++k) acc = fmaf(wf[k], s_w[k * cout + o], acc);
-      out[(size_t)n * cout + o] = acc * inv;
-    }
+    for (int i = 0; i < NO; ++i) out[(size_t)n * COUT + lane + 32 * i] = o[i] * inv;
   }
 }
 
@@ -476,18 +523,30 @@ extern "C" int spr_kpconv_forward(const float* d_q, const float* d_s, const void
     return SPR_EUNSUPPORTED;
   }
   if (cin == 1) {
-    const size_t smem = (size_t)(KP * cout + KP * 3) * 4;
-    SPR_CHECK_ARG(smem <= 48 * 1024, "kpconv_forward: cout %d too large for the Cin=1 kernel", cout);
+    SPR_CHECK_ARG(cout == 32 || cout == 64 || cout == 128 || cout == 256,
+                  "kpconv_forward: the Cin=1 kernel supports Cout in {32,64,128,256} (got %d)", cout);
+    SPR_CHECK_ARG(H <= 96, "kpconv_forward: at most 96 neighbour columns are supported (got %d)", H);
     const int warps = 8;
     int grid = (nq + warps - 1) / warps;
     if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-    if (idx_is_64)
-      k_kpconv_cin1<long long><<<grid, warps * 32, smem, stream>>>(d_q, d_s, static_cast<const long long*>(d_idx),
-                                                                   row_stride, H, d_x, d_w, cout, d_kp, extent, d_out,
-                                                                   nq, ns);
-    else
-      k_kpconv_cin1<int><<<grid, warps * 32, smem, stream>>>(d_q, d_s, static_cast<const int*>(d_idx), row_stride, H,
-                                                             d_x, d_w, cout, d_kp, extent, d_out, nq, ns);
+    const size_t smem = cout > 64 ? (size_t)KP * cout * 4 : 0;
+#define SPR_CIN1(NO)                                                                                              \
+  do {                                                                                                            \
+    if (idx_is_64)                                                                                                \
+      k_kpconv_cin1<long long, NO><<<grid, warps * 32, smem, stream>>>(d_q, d_s, static_cast<const long long*>(d_idx), \
+                                                                        row_stride, H, d_x, d_w, d_kp, extent, d_out, \
+                                                                        nq, ns);                                   \
+    else                                                                                                          \
+      k_kpconv_cin1<int, NO><<<grid, warps * 32, smem, stream>>>(d_q, d_s, static_cast<const int*>(d_idx), row_stride, \
+                                                                  H, d_x, d_w, d_kp, extent, d_out, nq, ns);       \
+  } while (0)
+    switch (cout) {
+      case 32: SPR_CIN1(1); break;
+      case 64: SPR_CIN1(2); break;
+      case 128: SPR_CIN1(4); break;
+      default: SPR_CIN1(8); break;
+    }
+#undef SPR_CIN1
     SPR_LAUNCH_CHECK("k_kpconv_cin1");
     return SPR_OK;
   }

@@ -119,7 +119,9 @@ class UnaryBlock(nn.Module):
     def forward(self, x, stack_lengths=None, residual=None, slope=None):
         if slope is None:
             slope = 1.0 if self.no_relu else LRELU_SLOPE
-        return self.batch_norm(self.mlp(x), stack_lengths, slope=slope, residual=residual)
+        # the Linear runs on the tcgen05 split-precision GEMM (fp32-level accuracy); CPU tensors raise, as everywhere
+        y = ops.linear_tc(x, self.mlp.weight, self.mlp.bias)
+        return self.batch_norm(y, stack_lengths, slope=slope, residual=residual)
 
     def __repr__(self):
         return (f'UnaryBlock(in_feat: {self.in_dim:d}, out_feat: {self.out_dim:d}, BN: {self.use_bn}, '

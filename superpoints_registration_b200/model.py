@@ -6,9 +6,12 @@ loads key for key (`kpf_encoder.*`, `feat_proj.*`, `transformer_encoder.*`, `ove
 `alpha`, `beta`).  Training-only members (losses, metrics, optimiser plumbing) are out of scope.
 
 What runs where:
-  preprocessor, kpf_encoder, superpoint matching, Sinkhorn, pose solve  -> our sm_100a kernels (libspr_b200.so)
-  unary Linear layers, feat_proj, the 6-layer cross-attention transformer  -> PyTorch fp32 (cuBLAS / SDPA);
-  the transformer is on the path but outside north_star's change list.
+  preprocessor, kpf_encoder (KPConv, unary Linear layers, InstanceNorm), feat_proj, the 6-layer cross-attention
+  transformer (packed tokens: LayerNorm, projections and FFN on the tcgen05 GEMM, varlen flash-attention),
+  superpoint matching, Sinkhorn, pose solve  -> our sm_100a kernels (libspr_b200.so);
+  PyTorch supplies memory, streams and a few element-wise glue ops (sine position embedding, sigmoid).
+  Configurations outside the shipped ones (post-norm, values without positional embedding) keep the padded
+  nn.MultiheadAttention modules on the GPU.
 The per-pair Python loop of the reference (:445) is gone: all pairs of the batch go through the same launches.
 """
 from __future__ import annotations
@@ -274,7 +277,7 @@ class RegTR(nn.Module):
         feats0 = torch.ones_like(meta['points'][0][:, 0:1])
 
         feats_un, _ = self.kpf_encoder(feats0, meta)
-        both = self.feat_proj(feats_un)
+        both = ops.linear_tc(feats_un, self.feat_proj.weight, self.feat_proj.bias)
         src_xyz_c, tgt_xyz_c = split_src_tgt(pts_c, slens_c)
         use_pe = cfg.transformer_encoder_has_pos_emb
         pe = self.pos_embed(pts_c)

@@ -108,6 +108,17 @@ SPR_API int spr_kpconv_forward(const float* d_q, const float* d_s, const void* d
                        float extent, float* d_out, int nq, int ns, int mode, void* d_workspace, size_t workspace_bytes,
                        void* stream);
 
+/* KPConv (tensor-core path) with operands prepared by the producing kernels instead of the built-in pre-pass:
+ *   spr_kpconv_prepare_weights: [W_hi | W_lo] stage images + max|W| (one word), once per weight
+ *   spr_kpconv_forward_prepared: d_pts4 [ns] float4, d_x16 [ns, c] (hi | lo<<16), d_amax_x (one word) as written
+ *   by spr_instance_norm_lrelu_ex.  Cin = Cout = c in {32, 64, 128, 256}. */
+SPR_API size_t spr_kpconv_weight_image_bytes(int c);
+SPR_API int spr_kpconv_prepare_weights(const float* d_w, int c, void* d_img, void* d_amax_w, void* stream);
+SPR_API int spr_kpconv_forward_prepared(const float* d_q, const void* d_idx, int idx_is_64, int row_stride, int H,
+                                const void* d_pts4, const void* d_x16, const void* d_amax_x, int c, const void* d_wimg,
+                                const void* d_amax_w, const float* d_kp, float extent, float* d_out, int nq, int ns,
+                                void* stream);
+
 /* Per-cloud instance normalisation + LeakyReLU (+ optional residual add before the activation).
  * Replaces BatchNormBlock.forward with nn.InstanceNorm1d (kpconv_blocks.py:474-530: per cloud, per
  * channel, biased variance, eps, no affine, no running stats) followed by nn.LeakyReLU
@@ -118,6 +129,15 @@ SPR_API size_t spr_instance_norm_workspace_bytes(int n_rows, int n_clouds, int c
 SPR_API int spr_instance_norm_lrelu(const float* d_x, const int32_t* d_lengths, int n, int n_clouds, int c, float eps,
                             float slope, const float* d_residual, float* d_out, void* d_workspace,
                             size_t workspace_bytes, void* stream);
+
+/* Same operator with format-aware outputs, so that the consumer of the normalised rows needs no conversion pass.
+ * Any of: d_out_f32 (plain rows), d_out_img (operand image of the next spr_gemm_tc with K = c, see below),
+ * d_out_x16 + d_out_pts4 + d_amax (pre-split feature rows, packed support points (x, y, z, +-2^-e) built from
+ * d_points [n,3], and max|y|: the inputs of spr_kpconv_forward_prepared).  c must be a multiple of 32. */
+SPR_API int spr_instance_norm_lrelu_ex(const float* d_x, const int32_t* d_lengths, int n, int n_clouds, int c, float eps,
+                               float slope, const float* d_residual, float* d_out_f32, void* d_out_img, float a_scale,
+                               void* d_out_x16, void* d_out_pts4, const float* d_points, void* d_amax,
+                               void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* max_pool(x, inds)  kpconv_blocks.py:127-143: out[n,c] = max_h xpad[idx[n,h],c] where xpad has a zero
  * row appended for the shadow index. */

@@ -33,6 +33,12 @@ _SIGNATURES = {
     "spr_instance_norm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "spr_instance_norm_lrelu": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_float, c_float, c_fp, c_fp, c_fp, c_size_t,
                                         c_void_p]),
+    "spr_instance_norm_lrelu_ex": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_float, c_float, c_fp, c_fp, c_fp, c_float,
+                                           c_fp, c_fp, c_fp, c_fp, c_fp, c_size_t, c_void_p]),
+    "spr_kpconv_weight_image_bytes": (c_size_t, [c_int]),
+    "spr_kpconv_prepare_weights": (c_int, [c_fp, c_int, c_fp, c_fp, c_void_p]),
+    "spr_kpconv_forward_prepared": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp,
+                                            c_float, c_fp, c_int, c_int, c_void_p]),
     "spr_max_pool": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp, c_void_p]),
     "spr_match_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "spr_dual_softmax_match": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int,

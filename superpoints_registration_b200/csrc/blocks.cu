@@ -9,6 +9,8 @@
 // partial sums, a second kernel folds them in chunk order, a third normalises.
 #include "spr_common.cuh"
 
+#include <cuda_fp16.h>
+
 namespace spr {
 namespace {
 
@@ -127,6 +129,122 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// byte offset of 16-byte chunk j of row r inside a (rows x 128 B) SWIZZLE_128B operand tile (tc05.cuh)
+__device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t j) {
+  return (r >> 3) * 1024u + (r & 7u) * 128u + ((j ^ (r & 7u)) << 4);
+}
+
+// Normalise + residual + LeakyReLU with format-aware outputs, so that the consumer needs no conversion pass:
+//   out_f32   plain rows (block outputs, residual inputs)
+//   out_img   operand image of the next tensor-core GEMM (gemm_tc.cu A image, K = c, scaled by a_scale)
+//   out_x16 / out_pts4 / amax_bits   pre-split feature rows, packed support points and max|y| of the next KPConv
+//             (kpconv_tc.cu pre-pass outputs)
+// A group of G = min(c/8, 32) lanes owns one row, a lane 8 consecutive channels per step of 8*G.
+__global__ void __launch_bounds__(256)
+    k_in_apply_ex(const float* __restrict__ x, const int* __restrict__ offs, int B, int n, int c,
+                  const float2* __restrict__ stats, float slope, const float* __restrict__ residual,
+                  float* __restrict__ out_f32, unsigned char* __restrict__ out_img, float a_scale,
+                  uint32_t* __restrict__ out_x16, float4* __restrict__ out_pts4, const float* __restrict__ s_pts,
+                  unsigned int* __restrict__ amax_bits) {
+  const int lane = threadIdx.x & 31;
+  const int G = c / 8 < 32 ? c / 8 : 32;
+  const int rpw = 32 / G;
+  const int steps = c / (8 * G);
+  const int gl = lane % G;
+  const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw + lane / G;
+  const bool live = row < n;
+  const int b = live ? find_cloud(offs, B, row) : 0;
+  const int KA = (c + 63) / 64;
+  float rmax = 0.f, rsum = 0.f;
+  float y[4][8];  // up to c = 1024
+#pragma unroll
+  for (int st = 0; st < 4; ++st) {
+    if (st >= steps) break;
+    const int ch = (st * G + gl) * 8;
+    if (live) {
+      const float4 v0 = *reinterpret_cast<const float4*>(x + (size_t)row * c + ch);
+      const float4 v1 = *reinterpret_cast<const float4*>(x + (size_t)row * c + ch + 4);
+      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      const float4* st4 = reinterpret_cast<const float4*>(stats + (size_t)b * c + ch);
+      float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (residual) {
+        const float4 r0 = *reinterpret_cast<const float4*>(residual + (size_t)row * c + ch);
+        const float4 r1 = *reinterpret_cast<const float4*>(residual + (size_t)row * c + ch + 4);
+        r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 s2 = __ldg(st4 + i);  // (mean, rstd) of channels 2i, 2i+1
+        float a = (v[2 * i] - s2.x) * s2.y + r[2 * i], bb = (v[2 * i + 1] - s2.z) * s2.w + r[2 * i + 1];
+        a = a >= 0.f ? a : a * slope;
+        bb = bb >= 0.f ? bb : bb * slope;
+        y[st][2 * i] = a;
+        y[st][2 * i + 1] = bb;
+        rsum += a + bb;
+        rmax = fmaxf(rmax, fmaxf(fabsf(a), fabsf(bb)));
+      }
+      if (out_f32) {
+        *reinterpret_cast<float4*>(out_f32 + (size_t)row * c + ch) = make_float4(y[st][0], y[st][1], y[st][2], y[st][3]);
+        *reinterpret_cast<float4*>(out_f32 + (size_t)row * c + ch + 4) = make_float4(y[st][4], y[st][5], y[st][6], y[st][7]);
+      }
+      if (out_img) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float y0 = y[st][2 * i] * a_scale, y1 = y[st][2 * i + 1] * a_scale;
+          const __half2 hh = __floats2half2_rn(y0, y1);
+          const float2 hf = __half22float2(hh);
+          const __half2 ll = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+          hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
+          lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        const int chunk = ch >> 3;
+        unsigned char* blk = out_img + ((size_t)(row >> 6) * KA + (chunk >> 3)) * 16384;
+        const uint32_t r2 = 2 * (row & 63);
+        *reinterpret_cast<uint4*>(blk + sw128_off(r2, chunk & 7)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(blk + sw128_off(r2 + 1, chunk & 7)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if (c < 64 && gl + c / 8 < 8) {  // K is padded to one 64-wide atom: the padding chunks must be finite
+          *reinterpret_cast<uint4*>(blk + sw128_off(r2, gl + c / 8)) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(blk + sw128_off(r2 + 1, gl + c / 8)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    }
+  }
+  if (out_x16) {
+    for (int o = G >> 1; o > 0; o >>= 1) {
+      rsum += __shfl_xor_sync(kFull, rsum, o);
+      rmax = fmaxf(rmax, __shfl_xor_sync(kFull, rmax, o));
+    }
+    const int e = scale_exp(rmax, 14);
+    const float rs = pow2i(e);
+    if (live) {
+#pragma unroll
+      for (int st = 0; st < 4; ++st) {
+        if (st >= steps) break;
+        const int ch = (st * G + gl) * 8;
+        uint32_t o8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v = y[st][i] * rs;
+          const __half hi = __float2half_rn(v);
+          const __half lo = __float2half_rn(v - __half2float(hi));
+          o8[i] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+        }
+        *reinterpret_cast<uint4*>(out_x16 + (size_t)row * c + ch) = make_uint4(o8[0], o8[1], o8[2], o8[3]);
+        *reinterpret_cast<uint4*>(out_x16 + (size_t)row * c + ch + 4) = make_uint4(o8[4], o8[5], o8[6], o8[7]);
+      }
+      if (gl == 0) {
+        const float inv = pow2i(-e);
+        out_pts4[row] = make_float4(s_pts[3 * (size_t)row], s_pts[3 * (size_t)row + 1], s_pts[3 * (size_t)row + 2],
+                                    rsum > 0.f ? inv : -inv);
+      }
+    }
+    rmax = warp_maxf(live ? rmax : 0.f);
+    if (lane == 0 && __float_as_uint(rmax) > *reinterpret_cast<volatile unsigned int*>(amax_bits))
+      atomicMax(amax_bits, __float_as_uint(rmax));
+  }
+}
+
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
     k_max_pool(const float* __restrict__ x, const IdxT* __restrict__ idx, int row_stride, int H, int nq, int ns, int c,
@@ -195,6 +313,43 @@ extern "C" int spr_instance_norm_lrelu(const float* d_x, const int32_t* d_length
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   k_in_apply<<<blocks, 256, 0, stream>>>(d_x, offs, n_clouds, n, c, stats, slope, d_residual, d_out);
   SPR_LAUNCH_CHECK("k_in_apply");
+  return SPR_OK;
+}
+
+extern "C" int spr_instance_norm_lrelu_ex(const float* d_x, const int32_t* d_lengths, int n, int n_clouds, int c,
+                                          float eps, float slope, const float* d_residual, float* d_out_f32,
+                                          void* d_out_img, float a_scale, void* d_out_x16, void* d_out_pts4,
+                                          const float* d_points, void* d_amax, void* d_workspace, size_t workspace_bytes,
+                                          void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPR_CHECK_ARG(n > 0 && n_clouds > 0 && c > 0, "instance_norm_ex: empty input (n=%d, clouds=%d, c=%d)", n, n_clouds, c);
+  SPR_CHECK_ARG(c % 32 == 0 && c <= 1024, "instance_norm_ex: channel count %d must be a multiple of 32, at most 1024", c);
+  SPR_CHECK_ARG(d_x && d_lengths && d_workspace, "instance_norm_ex: null pointer");
+  SPR_CHECK_ARG(d_out_f32 || d_out_img || d_out_x16, "instance_norm_ex: no output requested");
+  SPR_CHECK_ARG(!d_out_x16 || (d_out_pts4 && d_points && d_amax), "instance_norm_ex: KPConv outputs need pts4, points, amax");
+  if (workspace_bytes < spr_instance_norm_workspace_bytes(n, n_clouds, c)) {
+    set_error("instance_norm_ex: workspace too small");
+    return SPR_ENOSPACE;
+  }
+  Carver ws(d_workspace, workspace_bytes);
+  const size_t chunks = in_chunks_upper(n, n_clouds);
+  double2* part = ws.take<double2>(chunks * (size_t)c);
+  float2* stats = ws.take<float2>((size_t)n_clouds * c);
+  int* offs = ws.take<int>((size_t)n_clouds + 1);
+  int rc = cloud_offsets(d_lengths, n_clouds, offs, stream);
+  if (rc) return rc;
+  k_in_partial<<<(unsigned)chunks, 256, 0, stream>>>(d_x, d_lengths, n_clouds, c, part);
+  SPR_LAUNCH_CHECK("k_in_partial");
+  dim3 gs((c + 255) / 256, n_clouds);
+  k_in_stats<<<gs, 256, 0, stream>>>(part, d_lengths, n_clouds, c, eps, stats);
+  SPR_LAUNCH_CHECK("k_in_stats");
+  if (d_amax) SPR_CUDA(cudaMemsetAsync(d_amax, 0, sizeof(unsigned int), stream));
+  const int G = c / 8 < 32 ? c / 8 : 32;
+  const int rows_per_block = 8 * (32 / G);
+  k_in_apply_ex<<<(n + rows_per_block - 1) / rows_per_block, 256, 0, stream>>>(
+      d_x, offs, n_clouds, n, c, stats, slope, d_residual, d_out_f32, static_cast<unsigned char*>(d_out_img), a_scale,
+      static_cast<uint32_t*>(d_out_x16), static_cast<float4*>(d_out_pts4), d_points, static_cast<unsigned int*>(d_amax));
+  SPR_LAUNCH_CHECK("k_in_apply_ex");
   return SPR_OK;
 }
 

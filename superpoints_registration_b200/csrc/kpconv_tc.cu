@@ -41,15 +41,6 @@ struct TcScales {
   unsigned int amax_w_bits;
 };
 
-// power-of-two exponent e such that v * 2^e <= 2^target (v > 0 finite); 0 otherwise
-__device__ __forceinline__ int scale_exp(float v, int target) {
-  const int ef = (int)((__float_as_uint(v) >> 23) & 0xffu);
-  if (!(v > 0.f) || ef == 0 || ef == 255) return 0;  // zero, denormal, inf, nan
-  const int e = target - (ef - 126);                  // v = m * 2^(ef-126), m in [0.5, 1)
-  return e < -60 ? -60 : (e > 60 ? 60 : e);
-}
-__device__ __forceinline__ float pow2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }  // |e| <= 126
-
 // ---------------------------------------------------------------------------------------------
 // pre-pass 1 (one warp per support row): the feature row pre-split into fp16 (hi, lo) pairs of x * 2^e with a
 // per-row power-of-two scale; the packed support point (x, y, z, +-2^-e) whose sign carries rowsum(x) > 0 (the
@@ -128,7 +119,8 @@ __global__ void __launch_bounds__(256) k_flags_absmax(const float* __restrict__ 
 // 2*atom + kk/32 (kernel point 15 is zero padding), input channel pass*32 + kk%32.  One thread per 16-byte chunk.
 // ---------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(256) k_weight_image(const float* __restrict__ w, const TcScales* __restrict__ sc,
+__global__ void __launch_bounds__(256) k_weight_image(const float* __restrict__ w,
+                                                       const unsigned int* __restrict__ amax_w_bits,
                                                        unsigned char* __restrict__ img) {
   constexpr int NCOL = 2 * C, NS = NCOL < 128 ? NCOL : 128, NSUB = NCOL / NS;
   constexpr int CHUNKS = (C / 32) * 8 * NSUB * NS * 8;
@@ -144,7 +136,7 @@ __global__ void __launch_bounds__(256) k_weight_image(const float* __restrict__ 
   const bool lo_part = ncol >= C;
   const int o = lo_part ? ncol - C : ncol;
   const int k = atom * 2 + (j >> 2);  // kernel point of this chunk (15 = zero padding)
-  const float tscale = pow2i(scale_exp(__uint_as_float(sc->amax_w_bits), 14));
+  const float tscale = pow2i(scale_exp(__uint_as_float(*amax_w_bits), 14));
   __align__(16) __half h[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -225,7 +217,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
     k_kpconv_tc(const float* __restrict__ q, const float* __restrict__ s, const IdxT* __restrict__ idx, int row_stride,
                 int H, const uint32_t* __restrict__ x16, const unsigned char* __restrict__ wimg,
                 const float* __restrict__ kp, const float4* __restrict__ pts4,
-                const TcScales* __restrict__ sc, float extent, float* __restrict__ out, int nq, int ns, int tq,
+                const unsigned int* __restrict__ amax_x_bits, const unsigned int* __restrict__ amax_w_bits, float extent, float* __restrict__ out, int nq, int ns, int tq,
                 int n_tiles) {
   using K = TcCfg<C>;
   extern __shared__ unsigned char smem_raw[];
@@ -261,8 +253,8 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  const int es = scale_exp((float)H * __uint_as_float(sc->amax_x_bits), 15);
-  const int et = scale_exp(__uint_as_float(sc->amax_w_bits), 14);
+  const int es = scale_exp((float)H * __uint_as_float(*amax_x_bits), 15);
+  const int et = scale_exp(__uint_as_float(*amax_w_bits), 14);
 
   if (warp < K::WORKERS) {
     // =========================================== producers ===========================================
@@ -591,27 +583,33 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
   if (warp == K::WORKERS) tmem_dealloc(tmem, K::TMEM_COLS);
 }
 
+// max|W| -> *amax_w_bits (atomicMax on float bits; the word must be zero before the launch)
+__global__ void __launch_bounds__(256) k_absmax(const float* __restrict__ w, int n, unsigned int* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
+  m = warp_maxf(m);
+  if ((threadIdx.x & 31) == 0 && __float_as_uint(m) > *reinterpret_cast<volatile unsigned int*>(amax_bits))
+    atomicMax(amax_bits, __float_as_uint(m));
+}
+
+template <int C>
+int prepare_weights(const float* w, unsigned char* img, unsigned int* amax_w_bits, cudaStream_t stream) {
+  using K = TcCfg<C>;
+  SPR_CUDA(cudaMemsetAsync(amax_w_bits, 0, sizeof(unsigned int), stream));
+  k_absmax<<<(KP * C * C + 1023) / 1024, 256, 0, stream>>>(w, KP * C * C, amax_w_bits);
+  SPR_LAUNCH_CHECK("k_absmax");
+  constexpr int chunks = (int)(K::IMG_BYTES / 16);
+  k_weight_image<C><<<(chunks + 255) / 256, 256, 0, stream>>>(w, amax_w_bits, img);
+  SPR_LAUNCH_CHECK("k_weight_image");
+  return SPR_OK;
+}
+
 template <int C, typename IdxT>
-int launch_tc(const float* q, const float* s, const void* idx, int row_stride, int H, const float* x, const float* w,
-              const float* kp, float extent, float* out, int nq, int ns, void* workspace, cudaStream_t stream) {
+int launch_main(const float* q, const void* idx, int row_stride, int H, const uint32_t* x16, const unsigned char* img,
+                const float* kp, const float4* pts4, const unsigned int* amax_x_bits, const unsigned int* amax_w_bits,
+                float extent, float* out, int nq, int ns, cudaStream_t stream) {
   using K = TcCfg<C>;
   SPR_CHECK_ARG(H <= 96, "kpconv_forward(mode 1): at most 96 neighbour columns are supported (got %d)", H);
-  Carver cv(workspace, (size_t)-1);
-  TcScales* sc = cv.take<TcScales>(1);
-  float4* pts4 = cv.take<float4>((size_t)ns);
-  uint32_t* x16 = cv.take<uint32_t>((size_t)ns * C);
-  unsigned char* img = cv.take<unsigned char>(K::IMG_BYTES);
-
-  SPR_CUDA(cudaMemsetAsync(sc, 0, sizeof(TcScales), stream));
-  constexpr int rows_per_block = 8 * (C / 4 < 32 ? 32 / (C / 4) : 1);
-  const int n_xblocks = (ns + rows_per_block - 1) / rows_per_block;
-  const int n_wblocks = (KP * C * C + 1023) / 1024;
-  k_flags_absmax<C><<<n_xblocks + n_wblocks, 256, 0, stream>>>(x, s, ns, pts4, x16, w, KP * C * C, n_xblocks, sc);
-  SPR_LAUNCH_CHECK("k_flags_absmax");
-  constexpr int chunks = (int)(K::IMG_BYTES / 16);
-  k_weight_image<C><<<(chunks + 255) / 256, 256, 0, stream>>>(w, sc, img);
-  SPR_LAUNCH_CHECK("k_weight_image");
-
   // Tile size: the largest tq <= 64 that deals every SM the same number of tiles (a tile is the M extent of
   // one MMA; short tiles only leave MMA rows unused, which costs nothing on the critical path).
   int tq = K::TQ;
@@ -630,17 +628,44 @@ int launch_tc(const float* q, const float* s, const void* idx, int row_stride, i
   }
   const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
   const IdxT* idx_t = static_cast<const IdxT*>(idx);
+  const float* s_unused = nullptr;
   if (H <= 32)
-    k_kpconv_tc<C, IdxT, 1><<<grid, K::THREADS, K::SMEM, stream>>>(q, s, idx_t, row_stride, H, x16, img, kp, pts4, sc,
-                                                                   extent, out, nq, ns, tq, n_tiles);
+    k_kpconv_tc<C, IdxT, 1><<<grid, K::THREADS, K::SMEM, stream>>>(q, s_unused, idx_t, row_stride, H, x16, img, kp, pts4,
+                                                                   amax_x_bits, amax_w_bits, extent, out, nq, ns, tq,
+                                                                   n_tiles);
   else if (H <= 64)
-    k_kpconv_tc<C, IdxT, 2><<<grid, K::THREADS, K::SMEM, stream>>>(q, s, idx_t, row_stride, H, x16, img, kp, pts4, sc,
-                                                                   extent, out, nq, ns, tq, n_tiles);
+    k_kpconv_tc<C, IdxT, 2><<<grid, K::THREADS, K::SMEM, stream>>>(q, s_unused, idx_t, row_stride, H, x16, img, kp, pts4,
+                                                                   amax_x_bits, amax_w_bits, extent, out, nq, ns, tq,
+                                                                   n_tiles);
   else
-    k_kpconv_tc<C, IdxT, 3><<<grid, K::THREADS, K::SMEM, stream>>>(q, s, idx_t, row_stride, H, x16, img, kp, pts4, sc,
-                                                                   extent, out, nq, ns, tq, n_tiles);
+    k_kpconv_tc<C, IdxT, 3><<<grid, K::THREADS, K::SMEM, stream>>>(q, s_unused, idx_t, row_stride, H, x16, img, kp, pts4,
+                                                                   amax_x_bits, amax_w_bits, extent, out, nq, ns, tq,
+                                                                   n_tiles);
   SPR_LAUNCH_CHECK("k_kpconv_tc");
   return SPR_OK;
+}
+
+template <int C, typename IdxT>
+int launch_tc(const float* q, const float* s, const void* idx, int row_stride, int H, const float* x, const float* w,
+              const float* kp, float extent, float* out, int nq, int ns, void* workspace, cudaStream_t stream) {
+  using K = TcCfg<C>;
+  Carver cv(workspace, (size_t)-1);
+  TcScales* sc = cv.take<TcScales>(1);
+  float4* pts4 = cv.take<float4>((size_t)ns);
+  uint32_t* x16 = cv.take<uint32_t>((size_t)ns * C);
+  unsigned char* img = cv.take<unsigned char>(K::IMG_BYTES);
+
+  SPR_CUDA(cudaMemsetAsync(sc, 0, sizeof(TcScales), stream));
+  constexpr int rows_per_block = 8 * (C / 4 < 32 ? 32 / (C / 4) : 1);
+  const int n_xblocks = (ns + rows_per_block - 1) / rows_per_block;
+  const int n_wblocks = (KP * C * C + 1023) / 1024;
+  k_flags_absmax<C><<<n_xblocks + n_wblocks, 256, 0, stream>>>(x, s, ns, pts4, x16, w, KP * C * C, n_xblocks, sc);
+  SPR_LAUNCH_CHECK("k_flags_absmax");
+  constexpr int chunks = (int)(K::IMG_BYTES / 16);
+  k_weight_image<C><<<(chunks + 255) / 256, 256, 0, stream>>>(w, &sc->amax_w_bits, img);
+  SPR_LAUNCH_CHECK("k_weight_image");
+  return launch_main<C, IdxT>(q, idx, row_stride, H, x16, img, kp, pts4, &sc->amax_x_bits, &sc->amax_w_bits, extent, out,
+                              nq, ns, stream);
 }
 
 template <int C>
@@ -680,3 +705,61 @@ int kpconv_tc_forward(const float* q, const float* s, const void* idx, int idx_i
 }
 
 }  // namespace spr
+
+using namespace spr;
+
+extern "C" size_t spr_kpconv_weight_image_bytes(int c) {
+  switch (c) {
+    case 32: return TcCfg<32>::IMG_BYTES;
+    case 64: return TcCfg<64>::IMG_BYTES;
+    case 128: return TcCfg<128>::IMG_BYTES;
+    case 256: return TcCfg<256>::IMG_BYTES;
+  }
+  return 0;
+}
+
+extern "C" int spr_kpconv_prepare_weights(const float* d_w, int c, void* d_img, void* d_amax_w, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPR_CHECK_ARG(d_w && d_img && d_amax_w, "kpconv_prepare_weights: null pointer");
+  unsigned char* img = static_cast<unsigned char*>(d_img);
+  unsigned int* am = static_cast<unsigned int*>(d_amax_w);
+  switch (c) {
+    case 32: return prepare_weights<32>(d_w, img, am, stream);
+    case 64: return prepare_weights<64>(d_w, img, am, stream);
+    case 128: return prepare_weights<128>(d_w, img, am, stream);
+    case 256: return prepare_weights<256>(d_w, img, am, stream);
+  }
+  set_error("kpconv_prepare_weights: unsupported channel count %d", c);
+  return SPR_EUNSUPPORTED;
+}
+
+extern "C" int spr_kpconv_forward_prepared(const float* d_q, const void* d_idx, int idx_is_64, int row_stride, int H,
+                                           const void* d_pts4, const void* d_x16, const void* d_amax_x, int c,
+                                           const void* d_wimg, const void* d_amax_w, const float* d_kp, float extent,
+                                           float* d_out, int nq, int ns, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPR_CHECK_ARG(nq > 0 && ns > 0 && H > 0 && row_stride >= H, "kpconv_forward_prepared: bad shape");
+  SPR_CHECK_ARG(extent > 0.f, "kpconv_forward_prepared: extent must be > 0");
+  SPR_CHECK_ARG(d_q && d_idx && d_pts4 && d_x16 && d_amax_x && d_wimg && d_amax_w && d_kp && d_out,
+                "kpconv_forward_prepared: null pointer");
+  const float4* pts4 = static_cast<const float4*>(d_pts4);
+  const uint32_t* x16 = static_cast<const uint32_t*>(d_x16);
+  const unsigned char* img = static_cast<const unsigned char*>(d_wimg);
+  const unsigned int* ax = static_cast<const unsigned int*>(d_amax_x);
+  const unsigned int* aw = static_cast<const unsigned int*>(d_amax_w);
+#define SPR_TCP(CC)                                                                                                  \
+  case CC:                                                                                                           \
+    return idx_is_64 ? launch_main<CC, long long>(d_q, d_idx, row_stride, H, x16, img, d_kp, pts4, ax, aw, extent, d_out, \
+                                                  nq, ns, stream)                                                    \
+                     : launch_main<CC, int>(d_q, d_idx, row_stride, H, x16, img, d_kp, pts4, ax, aw, extent, d_out, nq, \
+                                            ns, stream);
+  switch (c) {
+    SPR_TCP(32)
+    SPR_TCP(64)
+    SPR_TCP(128)
+    SPR_TCP(256)
+  }
+#undef SPR_TCP
+  set_error("kpconv_forward_prepared: unsupported channel count %d", c);
+  return SPR_EUNSUPPORTED;
+}

@@ -118,6 +118,15 @@ __device__ __forceinline__ float warp_maxf(float v) {
   return v;
 }
 
+// power-of-two exponent e such that v * 2^e <= 2^target (v > 0, finite, normal); 0 otherwise.  |e| <= 60.
+__device__ __forceinline__ int scale_exp(float v, int target) {
+  const int ef = (int)((__float_as_uint(v) >> 23) & 0xffu);
+  if (!(v > 0.f) || ef == 0 || ef == 255) return 0;  // zero, denormal, inf, nan
+  const int e = target - (ef - 126);                  // v = m * 2^(ef-126), m in [0.5, 1)
+  return e < -60 ? -60 : (e > 60 ? 60 : e);
+}
+__device__ __forceinline__ float pow2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }  // |e| <= 126
+
 #endif  // __CUDACC__
 
 // Exclusive scan of int32 (device), n up to 2^31; out may alias in.  d_total (optional) gets the sum.

@@ -99,6 +99,15 @@ class BatchNormBlock(nn.Module):
             y = y + residual
         return y if slope == 1.0 else torch.nn.functional.leaky_relu(y, slope)
 
+    def forward_ex(self, x, stack_lengths, slope: float = 1.0, residual=None, want_f32=True, want_image=False,
+                   kpconv_points=None):
+        """Format-aware variant (ops.instance_norm_lrelu_ex): the consumer's operand formats come out of the
+        normalisation kernel itself.  Only with instance norm (every shipped config)."""
+        if not self.use_bn:
+            raise NotImplementedError("format-aware outputs need use_batch_norm=True")
+        return ops.instance_norm_lrelu_ex(x, stack_lengths, IN_EPS, slope, residual, want_f32=want_f32,
+                                          want_image=want_image, kpconv_points=kpconv_points)
+
     def __repr__(self):
         return f'BatchNormBlock(in_feat: {self.in_dim:d}, momentum: {self.bn_momentum:.3f}, only_bias: {not self.use_bn})'
 
@@ -122,6 +131,13 @@ class UnaryBlock(nn.Module):
         # the Linear runs on the tcgen05 split-precision GEMM (fp32-level accuracy); CPU tensors raise, as everywhere
         y = ops.linear_tc(x, self.mlp.weight, self.mlp.bias)
         return self.batch_norm(y, stack_lengths, slope=slope, residual=residual)
+
+    def forward_ex(self, x_image, n_rows, stack_lengths, residual=None, slope=None, **wants):
+        """Same operator from an operand image of x; `wants` selects the output formats (BatchNormBlock.forward_ex)."""
+        if slope is None:
+            slope = 1.0 if self.no_relu else LRELU_SLOPE
+        y = ops.gemm_tc(x_image, ops.weight_image(self.mlp.weight), self.mlp.bias, n_rows, ops.OUT_F32)
+        return self.batch_norm.forward_ex(y, stack_lengths, slope=slope, residual=residual, **wants)
 
     def __repr__(self):
         return (f'UnaryBlock(in_feat: {self.in_dim:d}, out_feat: {self.out_dim:d}, BN: {self.use_bn}, '
@@ -157,6 +173,10 @@ class SimpleBlock(nn.Module):
     def forward(self, x, batch):
         q_pts, s_pts, inds, lengths = _level_io(batch, self.layer_ind, 'strided' in self.block_name)
         x = self.KPConv(q_pts, s_pts, inds, x)
+        if self.use_bn and x.shape[1] % 32 == 0:
+            o = self.batch_norm.forward_ex(x, lengths, slope=LRELU_SLOPE, want_f32=True, want_image=True)
+            batch['_operand_image'] = (o['f32'].data_ptr(), o['image'])   # for the next block's unary GEMMs
+            return o['f32']
         return self.batch_norm(x, lengths, slope=LRELU_SLOPE)
 
 
@@ -183,7 +203,44 @@ class ResnetBottleneckBlock(nn.Module):
         self.unary_shortcut = (UnaryBlock(in_dim, out_dim, self.use_bn, self.bn_momentum, no_relu=True)
                                if in_dim != out_dim else nn.Identity())
 
+    def _fusable(self, features):
+        mid = self.out_dim // 4
+        return (self.use_bn and isinstance(self.unary1, UnaryBlock) and features.is_cuda and self.KPConv.mode is None
+                and mid in ops._TC_CHANNELS and self.in_dim % 32 == 0 and self.out_dim % 32 == 0
+                and self.out_dim <= 1024)
+
+    def _forward_fused(self, features, batch):
+        """Same arithmetic as forward(); every intermediate is written once, directly in the format its consumer
+        reads: unary1's normalised output as pre-split KPConv rows, the KPConv norm as the operand image of unary2,
+        the block output as rows + operand image of the next block's unary GEMMs."""
+        strided = 'strided' in self.block_name
+        pre_lengths = batch['stack_lengths'][self.layer_ind]
+        q_pts, s_pts, inds, post_lengths = _level_io(batch, self.layer_ind, strided)
+        n_in = features.shape[0]
+        stash = batch.get('_operand_image')
+        f_img = stash[1] if stash is not None and stash[0] == features.data_ptr() else ops.gemm_prepare_input(features)
+
+        x = self.unary1.forward_ex(f_img, n_in, pre_lengths, want_f32=False, kpconv_points=s_pts)['kpconv']
+        x = ops.kpconv_forward_prepared(q_pts, inds, x, self.KPConv.weights, self.KPConv.kernel_points,
+                                        self.KPConv.KP_extent)
+        x_img = self.batch_norm_conv.forward_ex(x, post_lengths, slope=LRELU_SLOPE, want_f32=False,
+                                                want_image=True)['image']
+        n_out = q_pts.shape[0]
+        if strided:
+            shortcut = max_pool(features, inds)
+            s_img = ops.gemm_prepare_input(shortcut) if isinstance(self.unary_shortcut, UnaryBlock) else None
+        else:
+            shortcut, s_img = features, f_img
+        if isinstance(self.unary_shortcut, UnaryBlock):
+            shortcut = self.unary_shortcut.forward_ex(s_img, n_out, post_lengths, want_f32=True)['f32']
+        o = self.unary2.forward_ex(x_img, n_out, post_lengths, residual=shortcut, slope=LRELU_SLOPE, want_f32=True,
+                                   want_image=True)
+        batch['_operand_image'] = (o['f32'].data_ptr(), o['image'])
+        return o['f32']
+
     def forward(self, features, batch):
+        if self._fusable(features):
+            return self._forward_fused(features, batch)
         strided = 'strided' in self.block_name
         pre_lengths = batch['stack_lengths'][self.layer_ind]
         q_pts, s_pts, inds, post_lengths = _level_io(batch, self.layer_ind, strided)

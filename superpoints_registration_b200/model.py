@@ -277,7 +277,11 @@ class RegTR(nn.Module):
         feats0 = torch.ones_like(meta['points'][0][:, 0:1])
 
         feats_un, _ = self.kpf_encoder(feats0, meta)
-        both = ops.linear_tc(feats_un, self.feat_proj.weight, self.feat_proj.bias)
+        stash = meta.get('_operand_image')  # the last encoder block wrote its output as a GEMM operand image too
+        if stash is not None and stash[0] == feats_un.data_ptr():
+            both = ops.gemm_tc(stash[1], ops.weight_image(self.feat_proj.weight), self.feat_proj.bias, feats_un.shape[0])
+        else:
+            both = ops.linear_tc(feats_un, self.feat_proj.weight, self.feat_proj.bias)
         src_xyz_c, tgt_xyz_c = split_src_tgt(pts_c, slens_c)
         use_pe = cfg.transformer_encoder_has_pos_emb
         pe = self.pos_embed(pts_c)

@@ -179,6 +179,88 @@ def instance_norm_lrelu(x, lengths, eps: float = 1e-5, slope: float = 1.0, resid
     return out
 
 
+def instance_norm_lrelu_ex(x, lengths, eps: float = 1e-5, slope: float = 1.0, residual=None, want_f32: bool = True,
+                           want_image: bool = False, kpconv_points=None):
+    """InstanceNorm (+ residual) + LeakyReLU with format-aware outputs.  Returns a dict with any of
+    'f32' (rows), 'image' (operand image of the next tensor-core GEMM, K = c), 'kpconv' (PreparedFeatures for
+    kpconv_forward_prepared; needs kpconv_points = the [n,3] points the rows belong to)."""
+    L = _lib.lib()
+    xx = _f32c(x, "x")
+    lens = _i32c(lengths, "stack_lengths")
+    n, c = xx.shape
+    res = None if residual is None else _f32c(residual, "residual")
+    out = {}
+    f32 = torch.empty_like(xx) if want_f32 else None
+    img = gemm_a_image(n, c, xx.device) if want_image else None
+    x16 = pts4 = amax = pts = None
+    if kpconv_points is not None:
+        pts = _f32c(kpconv_points, "kpconv_points")
+        x16 = torch.empty((n, c), dtype=torch.int32, device=xx.device)
+        pts4 = torch.empty((n, 4), dtype=torch.float32, device=xx.device)
+        amax = torch.empty(1, dtype=torch.int32, device=xx.device)
+    ws = _ws(L.spr_instance_norm_workspace_bytes(n, lens.shape[0], c), xx.device)
+    rc = L.spr_instance_norm_lrelu_ex(xx.data_ptr(), lens.data_ptr(), n, lens.shape[0], c, float(eps), float(slope),
+                                      _ptr(res), _ptr(f32), _ptr(img), A_SCALE, _ptr(x16), _ptr(pts4), _ptr(pts),
+                                      _ptr(amax), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "spr_instance_norm_lrelu_ex")
+    if f32 is not None:
+        out["f32"] = f32
+    if img is not None:
+        out["image"] = img
+    if x16 is not None:
+        out["kpconv"] = PreparedFeatures(x16, pts4, amax, c)
+    return out
+
+
+class PreparedFeatures:
+    """Inputs of the tensor-core KPConv already in kernel format (pre-split rows, packed points, max|x|)."""
+
+    def __init__(self, x16, pts4, amax, c):
+        self.x16, self.pts4, self.amax, self.c = x16, pts4, amax, c
+
+
+class KPConvWeightImage:
+    def __init__(self, weights: torch.Tensor):
+        L = _lib.lib()
+        w = _f32c(weights.detach(), "weights")
+        self.c = w.shape[1]
+        self.img = torch.empty(L.spr_kpconv_weight_image_bytes(self.c), dtype=torch.uint8, device=w.device)
+        self.amax = torch.empty(1, dtype=torch.int32, device=w.device)
+        rc = L.spr_kpconv_prepare_weights(w.data_ptr(), self.c, self.img.data_ptr(), self.amax.data_ptr(), _stream())
+        _lib.check(rc, "spr_kpconv_prepare_weights")
+        self.key = (weights.data_ptr(), weights._version)
+
+
+_KPCONV_WEIGHT_IMAGES = {}
+
+
+def kpconv_weight_image(weights: torch.Tensor) -> KPConvWeightImage:
+    key = (weights.data_ptr(), weights._version)
+    wi = _KPCONV_WEIGHT_IMAGES.get(id(weights))
+    if wi is None or wi.key != key:
+        wi = KPConvWeightImage(weights)
+        _KPCONV_WEIGHT_IMAGES[id(weights)] = wi
+    return wi
+
+
+def kpconv_forward_prepared(q_pts, neighb_inds, feats: PreparedFeatures, weights, kernel_points, extent: float):
+    """KPConv on the tensor-core path from inputs prepared by instance_norm_lrelu_ex (no pre-pass kernels)."""
+    L = _lib.lib()
+    q = _f32c(q_pts, "q_pts")
+    kp = _f32c(kernel_points, "kernel_points")
+    idx, is64, stride, H = _idx_arg(neighb_inds)
+    nq, ns = q.shape[0], feats.x16.shape[0]
+    wi = kpconv_weight_image(weights)
+    if wi.c != feats.c:
+        raise RuntimeError("kpconv_forward_prepared: channel mismatch between features and weights")
+    out = torch.empty((nq, feats.c), dtype=torch.float32, device=q.device)
+    rc = L.spr_kpconv_forward_prepared(q.data_ptr(), idx.data_ptr(), is64, stride, H, feats.pts4.data_ptr(),
+                                       feats.x16.data_ptr(), feats.amax.data_ptr(), feats.c, wi.img.data_ptr(),
+                                       wi.amax.data_ptr(), kp.data_ptr(), float(extent), out.data_ptr(), nq, ns, _stream())
+    _lib.check(rc, "spr_kpconv_forward_prepared")
+    return out
+
+
 def max_pool(x, inds):
     L = _lib.lib()
     xx = _f32c(x, "x")

@@ -188,3 +188,36 @@ def test_encoder_against_golden(golden_dir):
     ref = g["encoder_out"]
     err = np.abs(out.cpu().numpy() - ref).max()
     assert err <= 1e-4 * np.abs(ref).max(), (err, np.abs(ref).max())   # 8 stacked blocks of fp32 rounding
+
+
+def test_format_aware_instance_norm_outputs_feed_gemm_and_kpconv():
+    """instance_norm_lrelu_ex writes the operand image / pre-split rows its consumers read: results must equal the
+    plain fp32 route (norm -> linear_tc, norm -> kpconv_forward)."""
+    rng = np.random.default_rng(21)
+    lens = np.array([300, 157, 43], dtype=np.int32)
+    n, c = int(lens.sum()), 64
+    x = rng.normal(size=(n, c)).astype(np.float32) * 2 + 0.3
+    res = rng.normal(size=(n, c)).astype(np.float32)
+    pts = rng.uniform(0, 1, size=(n, 3)).astype(np.float32)
+    plain = ops.instance_norm_lrelu(_t(x), _t(lens), slope=0.1, residual=_t(res))
+    o = ops.instance_norm_lrelu_ex(_t(x), _t(lens), slope=0.1, residual=_t(res), want_f32=True, want_image=True,
+                                   kpconv_points=_t(pts))
+    assert (o["f32"] - plain).abs().max().item() <= 1e-6 * plain.abs().max().item()   # FMA contraction may differ
+    plain = o["f32"]
+    w = torch.randn(96, c, device=DEV) / 8
+    y_img = ops.gemm_tc(o["image"], ops.weight_image(w), None, n)
+    y_ref = ops.linear_tc(plain, w)
+    assert (y_img - y_ref).abs().max().item() <= 2e-6 * y_ref.abs().max().item()
+    H = 20
+    idx = rng.integers(0, n + 1, size=(n, H))
+    wk = (rng.normal(size=(15, c, c)) / np.sqrt(15 * c)).astype(np.float32)
+    kp = (rng.normal(size=(15, 3)) * 0.15).astype(np.float32)
+    a = ops.kpconv_forward_prepared(_t(pts), _t(idx), o["kpconv"], _t(wk), _t(kp), 0.3)
+    b = ops.kpconv_forward(_t(pts), _t(pts), _t(idx), plain, _t(wk), _t(kp), 0.3, mode=1)
+    assert (a - b).abs().max().item() <= 2e-6 * b.abs().max().item()
+    # c = 32: the image's K is padded to one 64-wide atom
+    x32 = rng.normal(size=(n, 32)).astype(np.float32)
+    o32 = ops.instance_norm_lrelu_ex(_t(x32), _t(lens), slope=0.1, want_f32=True, want_image=True)
+    w32 = torch.randn(128, 32, device=DEV) / 6
+    assert (ops.gemm_tc(o32["image"], ops.weight_image(w32), None, n) - ops.linear_tc(o32["f32"], w32)).abs().max().item() \
+        <= 1e-6 * 10

@@ -58,8 +58,16 @@ __global__ void __launch_bounds__(256) k_in_partial(const float* __restrict__ x,
     const int ch = c0 + tc;
     double s1 = 0.0, s2 = 0.0;
     if (ch < c && tr < rl) {
-      for (int r = tr; r < rows; r += rl) {
-        const double v = (double)x[(size_t)(row0 + r) * c + ch];
+      const float* col = x + (size_t)row0 * c + ch;
+      int r = tr;
+      for (; r + 3 * rl < rows; r += 4 * rl) {  // four independent loads in flight per thread
+        const float v0 = col[(size_t)r * c], v1 = col[(size_t)(r + rl) * c], v2 = col[(size_t)(r + 2 * rl) * c],
+                    v3 = col[(size_t)(r + 3 * rl) * c];
+        s1 += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+        s2 += ((double)v0 * v0 + (double)v1 * v1) + ((double)v2 * v2 + (double)v3 * v3);
+      }
+      for (; r < rows; r += rl) {
+        const double v = (double)col[(size_t)r * c];
         s1 += v;
         s2 += v * v;
       }
@@ -153,17 +161,23 @@ __global__ void __launch_bounds__(256)
   const int gl = lane % G;
   const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw + lane / G;
   const bool live = row < n;
-  const int b = live ? find_cloud(offs, B, row) : 0;
   const int KA = (c + 63) / 64;
   float rmax = 0.f, rsum = 0.f;
   float y[4][8];  // up to c = 1024
+  // the first step's rows are requested before the (dependent-load) cloud search
+  float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+  if (live) {
+    p0 = *reinterpret_cast<const float4*>(x + (size_t)row * c + gl * 8);
+    p1 = *reinterpret_cast<const float4*>(x + (size_t)row * c + gl * 8 + 4);
+  }
+  const int b = live ? find_cloud(offs, B, row) : 0;
 #pragma unroll
   for (int st = 0; st < 4; ++st) {
     if (st >= steps) break;
     const int ch = (st * G + gl) * 8;
     if (live) {
-      const float4 v0 = *reinterpret_cast<const float4*>(x + (size_t)row * c + ch);
-      const float4 v1 = *reinterpret_cast<const float4*>(x + (size_t)row * c + ch + 4);
+      const float4 v0 = st == 0 ? p0 : *reinterpret_cast<const float4*>(x + (size_t)row * c + ch);
+      const float4 v1 = st == 0 ? p1 : *reinterpret_cast<const float4*>(x + (size_t)row * c + ch + 4);
       const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
       const float4* st4 = reinterpret_cast<const float4*>(stats + (size_t)b * c + ch);
       float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};

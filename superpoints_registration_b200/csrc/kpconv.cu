@@ -77,11 +77,18 @@ __device__ __forceinline__ float influence_fast(float cx, float cy, float cz, fl
 // one butterfly per kernel point).  wf[15] is then broadcast and contracted with W[15, Cout] held in registers
 // (Cout <= 64) or shared memory.
 // ---------------------------------------------------------------------------------------------
+// support point and its scalar feature in one 16-byte record: one load per neighbour instead of four
+__global__ void __launch_bounds__(256) k_pack_points(const float* __restrict__ s, const float* __restrict__ x, int ns,
+                                                      float4* __restrict__ packed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ns) packed[i] = make_float4(s[3 * (size_t)i], s[3 * (size_t)i + 1], s[3 * (size_t)i + 2], x[i]);
+}
+
 template <typename IdxT, int NO>  // NO = Cout / 32 outputs per lane
 __global__ void __launch_bounds__(256)
-    k_kpconv_cin1(const float* __restrict__ q, const float* __restrict__ s, const IdxT* __restrict__ idx,
-                  int row_stride, int H, const float* __restrict__ x, const float* __restrict__ w,
-                  const float* __restrict__ kp, float extent, float* __restrict__ out, int nq, int ns) {
+    k_kpconv_cin1(const float* __restrict__ q, const float4* __restrict__ packed, const IdxT* __restrict__ idx,
+                  int row_stride, int H, const float* __restrict__ w, const float* __restrict__ kp, float extent,
+                  float* __restrict__ out, int nq, int ns) {
   constexpr int COUT = NO * 32;
   extern __shared__ float sm[];
   float* s_w = sm;  // [KP][COUT], only used when NO > 2
@@ -104,47 +111,72 @@ __global__ void __launch_bounds__(256)
   const int g1 = g < 7 ? g + 8 : 0;
   const float k1x = __ldg(kp + 3 * g1), k1y = __ldg(kp + 3 * g1 + 1), k1z = __ldg(kp + 3 * g1 + 2);
   const float k1_on = g < 7 ? 1.f : 0.f;
-  const int nblk = (H + 7) >> 3;
-  for (int n = blockIdx.x * warps + (threadIdx.x >> 5); n < nq; n += gridDim.x * warps) {
-    const float qx = __ldg(q + 3 * (size_t)n), qy = __ldg(q + 3 * (size_t)n + 1), qz = __ldg(q + 3 * (size_t)n + 2);
-    // neighbour row, lanes = slots (coalesced)
-    int jr[3];
+  const int stride_q = gridDim.x * warps;
+  int n = blockIdx.x * warps + (threadIdx.x >> 5);
+  if (n >= nq) return;
+
+  // neighbour row of the NEXT query is requested while the current one is processed; the two packed points of
+  // block b+1 are in flight while block b is evaluated
+  int jr[3], jn[3];
+  auto load_row = [&](int nn_, int (&dst)[3]) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int h = 32 * i + lane;
-      int j = -1;
-      if (h < H) {
-        j = load_idx(idx + (size_t)n * row_stride + h);
-        if (j < 0 || j >= ns) j = -1;
+      dst[i] = -1;
+      if (32 * i < H && h < H && nn_ < nq) dst[i] = load_idx(idx + (size_t)nn_ * row_stride + h);
+    }
+  };
+  load_row(n, jn);
+  float qnx = __ldg(q + 3 * (size_t)n), qny = __ldg(q + 3 * (size_t)n + 1), qnz = __ldg(q + 3 * (size_t)n + 2);
+  for (; n < nq; n += stride_q) {
+    const float qx = qnx, qy = qny, qz = qnz;
+    unsigned bm = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const bool valid = jn[i] >= 0 && jn[i] < ns;
+      jr[i] = valid ? jn[i] : -1;
+      if (32 * i < H) {
+        const unsigned m = __ballot_sync(kFull, valid);
+        bm |= (((m & 0xffu) ? 1u : 0u) | ((m & 0xff00u) ? 2u : 0u) | ((m & 0xff0000u) ? 4u : 0u) |
+               ((m & 0xff000000u) ? 8u : 0u)) << (4 * i);
       }
-      jr[i] = j;
+    }
+    const int n_next = n + stride_q;
+    load_row(n_next, jn);
+    if (n_next < nq) {
+      qnx = __ldg(q + 3 * (size_t)n_next);
+      qny = __ldg(q + 3 * (size_t)n_next + 1);
+      qnz = __ldg(q + 3 * (size_t)n_next + 2);
     }
     float acc0 = 0.f, acc1 = 0.f, cnt = 0.f;
-    for (int b = 0; b < nblk; ++b) {
+    auto fetch = [&](float4& pa, float4& pb) {
+      const int b = __ffs(bm) - 1;
+      bm &= bm - 1;
       const int src = (b & 3) * 8 + 2 * t;
       const int jsel = (b >> 2) == 0 ? jr[0] : ((b >> 2) == 1 ? jr[1] : jr[2]);
       const int ja = __shfl_sync(kFull, jsel, src);
       const int jb = __shfl_sync(kFull, jsel, src + 1);
-      if (!__any_sync(kFull, ja >= 0 || jb >= 0)) continue;  // padding block
-      float xa = 0.f, xb = 0.f, ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
-      if (ja >= 0) {
-        xa = __ldg(x + ja);
-        ax = __ldg(s + 3 * (size_t)ja) - qx;
-        ay = __ldg(s + 3 * (size_t)ja + 1) - qy;
-        az = __ldg(s + 3 * (size_t)ja + 2) - qz;
-      }
-      if (jb >= 0) {
-        xb = __ldg(x + jb);
-        bx = __ldg(s + 3 * (size_t)jb) - qx;
-        by = __ldg(s + 3 * (size_t)jb + 1) - qy;
-        bz = __ldg(s + 3 * (size_t)jb + 2) - qz;
-      }
-      // an absent neighbour has x = 0 and therefore contributes nothing
-      acc0 = fmaf(influence_fast(ax, ay, az, k0x, k0y, k0z, inv_extent), xa, acc0);
-      acc0 = fmaf(influence_fast(bx, by, bz, k0x, k0y, k0z, inv_extent), xb, acc0);
-      acc1 = fmaf(influence_fast(ax, ay, az, k1x, k1y, k1z, inv_extent), xa, acc1);
-      acc1 = fmaf(influence_fast(bx, by, bz, k1x, k1y, k1z, inv_extent), xb, acc1);
-      cnt += (xa > 0.f ? 1.f : 0.f) + (xb > 0.f ? 1.f : 0.f);  // neighbour_num: rowsum(x) = x for Cin = 1
+      pa = make_float4(0.f, 0.f, 0.f, 0.f);
+      pb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ja >= 0) pa = __ldg(packed + ja);
+      if (jb >= 0) pb = __ldg(packed + jb);
+    };
+    float4 ca, cb, na, nb;
+    bool have = bm != 0;  // warp-uniform: the row has at least one neighbour
+    if (have) fetch(na, nb);
+    while (have) {
+      ca = na;
+      cb = nb;
+      have = bm != 0;
+      if (have) fetch(na, nb);
+      // an absent neighbour has w = x = 0 and contributes nothing
+      const float ax = ca.x - qx, ay = ca.y - qy, az = ca.z - qz;
+      const float bx = cb.x - qx, by = cb.y - qy, bz = cb.z - qz;
+      acc0 = fmaf(influence_fast(ax, ay, az, k0x, k0y, k0z, inv_extent), ca.w, acc0);
+      acc0 = fmaf(influence_fast(bx, by, bz, k0x, k0y, k0z, inv_extent), cb.w, acc0);
+      acc1 = fmaf(influence_fast(ax, ay, az, k1x, k1y, k1z, inv_extent), ca.w, acc1);
+      acc1 = fmaf(influence_fast(bx, by, bz, k1x, k1y, k1z, inv_extent), cb.w, acc1);
+      cnt += (ca.w > 0.f ? 1.f : 0.f) + (cb.w > 0.f ? 1.f : 0.f);  // neighbour_num: rowsum(x) = x for Cin = 1
     }
     acc0 += __shfl_xor_sync(kFull, acc0, 1);
     acc0 += __shfl_xor_sync(kFull, acc0, 2);
@@ -499,7 +531,8 @@ using namespace spr;
 extern "C" size_t spr_kpconv_workspace_bytes(int nq, int ns, int cin, int cout, int n_kernel_points) {
   (void)nq;
   (void)n_kernel_points;
-  const size_t simt = align_up((size_t)(ns > 0 ? ns : 0) + 1, 256) + 256;
+  const size_t simt = cin == 1 ? align_up((size_t)(ns > 0 ? ns : 0) * 16, 256) + 256
+                               : align_up((size_t)(ns > 0 ? ns : 0) + 1, 256) + 256;
   const size_t tc = cin == cout ? kpconv_tc_workspace_bytes(ns > 0 ? ns : 0, cin) : 0;
   return simt > tc ? simt : tc;
 }
@@ -526,19 +559,26 @@ extern "C" int spr_kpconv_forward(const float* d_q, const float* d_s, const void
     SPR_CHECK_ARG(cout == 32 || cout == 64 || cout == 128 || cout == 256,
                   "kpconv_forward: the Cin=1 kernel supports Cout in {32,64,128,256} (got %d)", cout);
     SPR_CHECK_ARG(H <= 96, "kpconv_forward: at most 96 neighbour columns are supported (got %d)", H);
+    if (!d_workspace || workspace_bytes < spr_kpconv_workspace_bytes(nq, ns, cin, cout, n_kernel_points)) {
+      set_error("kpconv_forward: workspace too small");
+      return SPR_ENOSPACE;
+    }
+    float4* packed = static_cast<float4*>(d_workspace);
+    k_pack_points<<<(ns + 255) / 256, 256, 0, stream>>>(d_s, d_x, ns, packed);
+    SPR_LAUNCH_CHECK("k_pack_points");
     const int warps = 8;
     int grid = (nq + warps - 1) / warps;
-    if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+    if (grid > kNumSMs * 6) grid = kNumSMs * 6;
     const size_t smem = cout > 64 ? (size_t)KP * cout * 4 : 0;
 #define SPR_CIN1(NO)                                                                                              \
   do {                                                                                                            \
     if (idx_is_64)                                                                                                \
-      k_kpconv_cin1<long long, NO><<<grid, warps * 32, smem, stream>>>(d_q, d_s, static_cast<const long long*>(d_idx), \
-                                                                        row_stride, H, d_x, d_w, d_kp, extent, d_out, \
-                                                                        nq, ns);                                   \
+      k_kpconv_cin1<long long, NO><<<grid, warps * 32, smem, stream>>>(d_q, packed, static_cast<const long long*>(d_idx), \
+                                                                        row_stride, H, d_w, d_kp, extent, d_out, nq, \
+                                                                        ns);                                       \
     else                                                                                                          \
-      k_kpconv_cin1<int, NO><<<grid, warps * 32, smem, stream>>>(d_q, d_s, static_cast<const int*>(d_idx), row_stride, \
-                                                                  H, d_x, d_w, d_kp, extent, d_out, nq, ns);       \
+      k_kpconv_cin1<int, NO><<<grid, warps * 32, smem, stream>>>(d_q, packed, static_cast<const int*>(d_idx), row_stride, \
+                                                                  H, d_w, d_kp, extent, d_out, nq, ns);            \
   } while (0)
     switch (cout) {
       case 32: SPR_CIN1(1); break;

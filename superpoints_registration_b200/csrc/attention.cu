@@ -72,7 +72,7 @@ struct AttnTile {
 };
 
 // planes: hi and lo fp16 matrices with `ld` halves per row; q_col / k_col / v_col = first column of head 0
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128)
     k_attention(const __half* __restrict__ hi, const __half* __restrict__ lo, int ld, int q_col, int k_col, int v_col,
                 const AttnTile* __restrict__ tiles, float* __restrict__ out, int out_ld,
                 unsigned char* __restrict__ out_img, int img_katoms, float img_scale) {
@@ -141,22 +141,35 @@ __global__ void __launch_bounds__(128, 4)
     const uint32_t vh_s = kh_s + 2 * PLANE_BYTES, vl_s = kh_s + 3 * PLANE_BYTES;
 
     // ---- S = Q K^T : 8 key tiles of 8, 2 k-steps of 16 ----
+    // Issue order is product-major over groups of 4 key tiles: consecutive MMAs write different accumulators, so
+    // the tensor pipe is not stalled on its own result latency (6 chained MMAs per tile otherwise).
     float s[8][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) s[j][e] = 0.f;
-      // matrices: (rows 8j.., d chunk 0), (chunk 1), (chunk 2), (chunk 3)  ->  b0,b1 of k-step 0 ; b0,b1 of k-step 1
-      const uint32_t off = tile_off(8 * j + (lane & 7), lane >> 3);
-      uint32_t bh[4], bl[4];
-      ldsm_x4(kh_s + off, bh);
-      ldsm_x4(kl_s + off, bl);
-      mma16816(s[j], ql[0], bh[0], bh[1]);
-      mma16816(s[j], qh[0], bl[0], bl[1]);
-      mma16816(s[j], qh[0], bh[0], bh[1]);
-      mma16816(s[j], ql[1], bh[2], bh[3]);
-      mma16816(s[j], qh[1], bl[2], bl[3]);
-      mma16816(s[j], qh[1], bh[2], bh[3]);
+#pragma unroll
+    for (int j0 = 0; j0 < 8; j0 += 4) {
+      uint32_t bh[4][4], bl[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // matrices: (rows 8j.., d chunk 0), (chunk 1), (chunk 2), (chunk 3) -> b0,b1 of k-step 0 ; b0,b1 of k-step 1
+        const uint32_t off = tile_off(8 * (j0 + j) + (lane & 7), lane >> 3);
+        ldsm_x4(kh_s + off, bh[j]);
+        ldsm_x4(kl_s + off, bl[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma16816(s[j0 + j], ql[0], bh[j][0], bh[j][1]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma16816(s[j0 + j], qh[0], bl[j][0], bl[j][1]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma16816(s[j0 + j], ql[1], bh[j][2], bh[j][3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma16816(s[j0 + j], qh[1], bl[j][2], bl[j][3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma16816(s[j0 + j], qh[0], bh[j][0], bh[j][1]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma16816(s[j0 + j], qh[1], bh[j][2], bh[j][3]);
     }
     // mask the tail of the segment
     if ((kt + 1) * BK > tl.kv_len) {
@@ -213,21 +226,22 @@ __global__ void __launch_bounds__(128, 4)
         ph[e] = h2u(hh);
         pl[e] = h2u(__floats2half2_rn(v0 - hf.x, v1 - hf.y));
       }
+      uint32_t bh[2][4], bl[2][4];
 #pragma unroll
       for (int dp = 0; dp < 2; ++dp) {
         // matrices: (keys 16kk.., d chunk 2dp), (keys 16kk+8.., chunk 2dp), (keys 16kk.., chunk 2dp+1), (+8, 2dp+1)
         const int r = 16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8;
         const uint32_t off = tile_off(r, 2 * dp + (lane >> 4));
-        uint32_t bh[4], bl[4];
-        ldsm_x4_trans(vh_s + off, bh);
-        ldsm_x4_trans(vl_s + off, bl);
-        mma16816(o[2 * dp], pl, bh[0], bh[1]);
-        mma16816(o[2 * dp], ph, bl[0], bl[1]);
-        mma16816(o[2 * dp], ph, bh[0], bh[1]);
-        mma16816(o[2 * dp + 1], pl, bh[2], bh[3]);
-        mma16816(o[2 * dp + 1], ph, bl[2], bl[3]);
-        mma16816(o[2 * dp + 1], ph, bh[2], bh[3]);
+        ldsm_x4_trans(vh_s + off, bh[dp]);
+        ldsm_x4_trans(vl_s + off, bl[dp]);
       }
+      // product-major: the four d tiles are independent accumulators
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mma16816(o[i], pl, bh[i >> 1][2 * (i & 1)], bh[i >> 1][2 * (i & 1) + 1]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mma16816(o[i], ph, bl[i >> 1][2 * (i & 1)], bl[i >> 1][2 * (i & 1) + 1]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mma16816(o[i], ph, bh[i >> 1][2 * (i & 1)], bh[i >> 1][2 * (i & 1) + 1]);
     }
     __syncthreads();  // the buffer is re-filled two iterations later
   }

@@ -9,6 +9,9 @@
 // K-major SWIZZLE_128B tiles, see tc05.cuh), so the producer is a bare bulk async copy per tile:
 //   A image : [m_tile = token / 64][k_atom = k / 64] x (128 rows x 128 B)         written by the previous kernel
 //   W image : [n_tile = n / 128][k_atom][sub = hi | lo] x (128 rows x 128 B)      built once per weight
+// K <= 256 (every projection of the cross-encoder except FFN2): the CTA is pinned to ONE n tile, loads that tile's
+// whole W image (<= 128 KB) into shared memory once and streams only A tiles afterwards -- the kernel is bound by
+// L2 -> SM operand traffic, and this cuts it 3x.  Larger K streams W through the ring with A.
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-9 = epilogue.
 // Two accumulator buffers (2 x 256 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 // The epilogue can emit fp32 rows, fp16 hi/lo planes (for the attention kernel), or the A image of the next GEMM.
@@ -27,7 +30,10 @@ constexpr int B_STAGE = 2 * 128 * 128;     // 32 KB
 constexpr int NSTAGES = 4;
 constexpr int EPI_WARPS = 8;               // 2 per TMEM lane quadrant, each owning 64 of the 128 tile columns
 constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;
-constexpr size_t GEMM_SMEM = 1024 + (size_t)NSTAGES * (A_STAGE + B_STAGE) + 256;
+constexpr int RES_STAGES = 6;               // A ring depth when W is resident (bytes in flight bound the A stream)
+constexpr int RES_KA = 4;                   // W atoms kept resident (K <= 256)
+constexpr size_t GEMM_SMEM = 1024 + (size_t)RES_STAGES * A_STAGE + (size_t)RES_KA * B_STAGE + 256;
+static_assert((size_t)NSTAGES * (A_STAGE + B_STAGE) <= (size_t)RES_STAGES * A_STAGE + (size_t)RES_KA * B_STAGE, "smem");
 
 enum { OUT_F32 = 0, OUT_PLANES = 1, OUT_AIMG = 2 };
 
@@ -52,21 +58,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem =
       reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* sA = smem;
-  unsigned char* sB = smem + NSTAGES * A_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGES * (A_STAGE + B_STAGE));
-  uint64_t* bar_full = bars;            // [NSTAGES]
-  uint64_t* bar_empty = bars + 4;       // [NSTAGES]
-  uint64_t* bar_accf = bars + 8;        // [2] accumulator full
-  uint64_t* bar_acce = bars + 10;       // [2] accumulator empty
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 12);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int KA = g.K / 64;
+  const bool resident = KA <= RES_KA;
+  const int nstages = resident ? RES_STAGES : NSTAGES;
+  unsigned char* sA = smem;                       // [nstages] A tiles
+  unsigned char* sB = smem + nstages * A_STAGE;   // streaming: [NSTAGES] W stages ; resident: [KA <= 4] W atoms
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RES_STAGES * A_STAGE + RES_KA * B_STAGE);
+  uint64_t* bar_full = bars;            // [<= 8]
+  uint64_t* bar_empty = bars + 8;       // [<= 8]
+  uint64_t* bar_accf = bars + 16;       // [2] accumulator full
+  uint64_t* bar_acce = bars + 18;       // [2] accumulator empty
+  uint64_t* bar_w = bars + 20;          // resident W image has landed
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 22);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m_tiles = (g.T + BM_TOK - 1) / BM_TOK, n_tiles = (g.N + BN - 1) / BN;
-  const int total = m_tiles * n_tiles;
+  // tile walk: resident mode pins the CTA to n tile (blockIdx % n_tiles) and strides over m tiles; streaming mode
+  // walks the (m, n) grid with n fastest.  Both are expressed as  tile_i = first + i * step,  i < count.
+  const int nt_fixed = resident ? (int)blockIdx.x % n_tiles : 0;
+  const int first = resident ? (int)blockIdx.x / n_tiles : (int)blockIdx.x;
+  const int step = resident ? (int)gridDim.x / n_tiles : (int)gridDim.x;
+  const int limit = resident ? m_tiles : m_tiles * n_tiles;
 
   if (tid == 0) {
-    for (int i = 0; i < NSTAGES; ++i) {
+    for (int i = 0; i < 8; ++i) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
     }
@@ -74,6 +88,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
       mbar_init(&bar_accf[i], 1);
       mbar_init(&bar_acce[i], EPI_WARPS);
     }
+    mbar_init(bar_w, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
@@ -86,14 +101,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int mt = tile / n_tiles, nt = tile % n_tiles;
+      if (resident && first < limit) {
+        mbar_arrive_expect_tx(bar_w, (uint32_t)KA * B_STAGE);
+        for (int a = 0; a < KA; ++a)
+          bulk_g2s(sB + a * B_STAGE, g.w_img + ((size_t)nt_fixed * KA + a) * B_STAGE, B_STAGE, bar_w);
+      }
+      for (int tile = first; tile < limit; tile += step) {
+        const int mt = resident ? tile : tile / n_tiles, nt = resident ? nt_fixed : tile % n_tiles;
         for (int a = 0; a < KA; ++a) {
-          mbar_wait_sleep(&bar_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&bar_full[stage], A_STAGE + B_STAGE);
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bar_full[stage], resident ? A_STAGE : A_STAGE + B_STAGE);
           bulk_g2s(sA + stage * A_STAGE, g.a_img + ((size_t)mt * KA + a) * A_STAGE, A_STAGE, &bar_full[stage]);
-          bulk_g2s(sB + stage * B_STAGE, g.w_img + ((size_t)nt * KA + a) * B_STAGE, B_STAGE, &bar_full[stage]);
-          if (++stage == NSTAGES) {
+          if (!resident)
+            bulk_g2s(sB + stage * B_STAGE, g.w_img + ((size_t)nt * KA + a) * B_STAGE, B_STAGE, &bar_full[stage]);
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -109,23 +130,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      if (resident && first < limit) mbar_wait(bar_w, 0);
+      for (int tile = first; tile < limit; tile += step, ++it) {
         const int buf = it & 1;
-        mbar_wait_sleep(&bar_acce[buf], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        mbar_wait(&bar_acce[buf], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         for (int a = 0; a < KA; ++a) {
-          mbar_wait_sleep(&bar_full[stage], phase);
+          mbar_wait(&bar_full[stage], phase);
           tc_fence_after();
+          const int bslot = resident ? a : stage;
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub)
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t ad = adesc0 + (uint64_t)((stage * A_STAGE + kk * 32) >> 4);
-              const uint64_t bd = bdesc0 + (uint64_t)((stage * B_STAGE + sub * A_STAGE + kk * 32) >> 4);
+              const uint64_t bd = bdesc0 + (uint64_t)((bslot * B_STAGE + sub * A_STAGE + kk * 32) >> 4);
               umma_f16(tmem + buf * 256 + sub * 128, ad, bd, idesc, (a | kk) != 0);
             }
           umma_commit(&bar_empty[stage]);
-          if (++stage == NSTAGES) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -144,20 +167,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
     const int tok_l = row >> 1;
     const int half_sel = lane & 1;                 // even lane stores columns c0..c0+3, odd lane c0+4..c0+7
     int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    for (int tile = first; tile < limit; tile += step, ++it) {
       const int buf = it & 1;
-      const int mt = tile / n_tiles, nt = tile % n_tiles;
+      const int mt = resident ? tile : tile / n_tiles, nt = resident ? nt_fixed : tile % n_tiles;
       const int token = mt * BM_TOK + tok_l;
       const bool tok_ok = token < g.T;
-      mbar_wait_sleep(&bar_accf[buf], (it >> 1) & 1);
+      mbar_wait(&bar_accf[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16) + buf * 256 + chalf * 64;
-      float v1[2][8], v2[2][8];
-      tmem_ld8(trow, v1[0]);
-      tmem_ld8(trow + 128, v2[0]);
+      // all 16 TMEM loads of this warp's 64 columns are issued back to back, then ONE wait
+      float v1[8][8], v2[8][8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int cur = i & 1;
+        tmem_ld8(trow + i * 8, v1[i]);
+        tmem_ld8(trow + 128 + i * 8, v2[i]);
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tmem_ld_fence(v1[i], v2[i]);
+      // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before the stores
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_acce[buf]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int cur = i;
         const int c0 = chalf * 64 + i * 8;
         const int n = nt * BN + c0 + half_sel * 4;
         const bool ok = tok_ok && n < g.N;
@@ -165,11 +199,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
         if (ok && g.bias) bv = __ldg(reinterpret_cast<const float4*>(g.bias + n));
         if (ok && mode == OUT_F32 && g.residual)
           rv = *reinterpret_cast<const float4*>(g.residual + (size_t)token * g.ld_res + n);
-        tmem_ld_wait(v1[cur], v2[cur]);  // group i has landed
-        if (i + 1 < 8) {
-          tmem_ld8(trow + (i + 1) * 8, v1[cur ^ 1]);
-          tmem_ld8(trow + 128 + (i + 1) * 8, v2[cur ^ 1]);
-        }
         float sum[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -210,9 +239,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_acce[buf]);
     }
   }
   tc_fence_before();
@@ -410,8 +436,17 @@ extern "C" int spr_gemm_tc(const void* d_a_img, const void* d_w_img, const float
     SPR_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     attr_set = true;
   }
-  const int total = ((T + BM_TOK - 1) / BM_TOK) * ((N + BN - 1) / BN);
-  const int grid = total < kNumSMs ? total : kNumSMs;
+  const int m_tiles = (T + BM_TOK - 1) / BM_TOK, n_tiles = (N + BN - 1) / BN;
+  int grid;
+  if (g.K / 64 <= RES_KA) {  // W-resident walk: a multiple of n_tiles CTAs, each pinned to one n tile
+    int per = kNumSMs / n_tiles;
+    if (per < 1) per = 1;
+    if (per > m_tiles) per = m_tiles;
+    grid = per * n_tiles;
+  } else {
+    const int total = m_tiles * n_tiles;
+    grid = total < kNumSMs ? total : kNumSMs;
+  }
   k_gemm_tc<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(g, out_mode);
   SPR_LAUNCH_CHECK("k_gemm_tc");
   return SPR_OK;

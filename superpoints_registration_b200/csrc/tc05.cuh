@@ -92,6 +92,16 @@ __device__ __forceinline__ void tmem_ld_wait(float (&a)[8], float (&b)[8]) {
                : "memory");
 }
 
+// compiler-only fence: ties registers written by an earlier tcgen05.ld (already waited for) to this point, so that
+// no use of them is scheduled above the wait
+__device__ __forceinline__ void tmem_ld_fence(float (&a)[8], float (&b)[8]) {
+  asm volatile(""
+               : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]),
+                 "+f"(b[0]), "+f"(b[1]), "+f"(b[2]), "+f"(b[3]), "+f"(b[4]), "+f"(b[5]), "+f"(b[6]), "+f"(b[7])
+               :
+               : "memory");
+}
+
 // ---- UMMA descriptors ------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: LBO = 1 (unused), SBO = 1024 B between 8-row groups,
 // descriptor version 1 (sm_100), layout type 2

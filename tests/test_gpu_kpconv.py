@@ -221,3 +221,36 @@ def test_format_aware_instance_norm_outputs_feed_gemm_and_kpconv():
     w32 = torch.randn(128, 32, device=DEV) / 6
     assert (ops.gemm_tc(o32["image"], ops.weight_image(w32), None, n) - ops.linear_tc(o32["f32"], w32)).abs().max().item() \
         <= 1e-6 * 10
+
+
+@pytest.mark.parametrize("cout", [32, 64, 128, 256])
+def test_kpconv_stem_cin1_against_oracle(cout):
+    """First encoder block (Cin = 1): every supported output width, more than 64 neighbour columns, shadow entries."""
+    rng = np.random.default_rng(cout)
+    ns, nq, H = 600, 257, 70
+    s = rng.uniform(0, 1, size=(ns, 3)).astype(np.float32)
+    q = s[:nq] + rng.normal(0, 0.01, size=(nq, 3)).astype(np.float32)
+    idx = rng.integers(0, ns + 1, size=(nq, H))
+    idx[3] = ns
+    x = np.where(rng.uniform(size=(ns, 1)) < 0.7, 1.0, -0.25).astype(np.float32)
+    w = (rng.normal(size=(15, 1, cout)) / 4).astype(np.float32)
+    kp = (rng.normal(size=(15, 3)) * 0.15).astype(np.float32)
+    out = ops.kpconv_forward(_t(q), _t(s), _t(idx), _t(x), _t(w), _t(kp), 0.3).cpu().numpy()
+    exact = oracle.kpconv_forward(q, s, idx, x, w, kp, 0.3)
+    assert np.abs(out - exact).max() <= FEAT_RTOL * np.abs(exact).max()
+    assert np.all(out[3] == 0)
+
+
+def test_kpconv_tensor_core_wide_rows():
+    """More than 64 neighbour columns (KITTI limits 68 / 74): three 32-slot rounds per row."""
+    rng = np.random.default_rng(33)
+    ns, nq, H, c = 900, 400, 74, 128
+    s = rng.uniform(0, 1, size=(ns, 3)).astype(np.float32)
+    q = s[:nq]
+    idx = np.sort(rng.integers(0, ns + 1, size=(nq, H)), axis=1)   # shadows at the end, like the real pyramids
+    x = rng.normal(size=(ns, c)).astype(np.float32)
+    w = (rng.normal(size=(15, c, c)) / np.sqrt(15 * c)).astype(np.float32)
+    kp = (rng.normal(size=(15, 3)) * 0.15).astype(np.float32)
+    out = ops.kpconv_forward(_t(q), _t(s), _t(idx), _t(x), _t(w), _t(kp), 0.3, mode=1).cpu().numpy()
+    exact = oracle.kpconv_forward(q, s, idx, x, w, kp, 0.3)
+    assert np.abs(out - exact).max() <= FEAT_RTOL * np.abs(exact).max()

@@ -187,37 +187,33 @@ __global__ void __launch_bounds__(kThreads)
   sorted[pos] = make_float4(s[3 * (size_t)i], s[3 * (size_t)i + 1], s[3 * (size_t)i + 2], __int_as_float(i));
 }
 
-// (d2, idx) lexicographic "a before b"
-__device__ __forceinline__ bool before(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+// A hit is one 64-bit key: fp32 bits of d2 (non-negative, so the bit pattern orders like the value) in the high
+// word, support index in the low word.  key_a < key_b  <=>  (d2, idx) of a comes before b: the reference's order
+// by distance (neighbors.cpp:296-310 via nanoflann's sorted result set) with ties by lower index.
+__device__ __forceinline__ unsigned long long make_key(float d2, int id) {
+  return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)id;
+}
 
-// Keep the `limit` best staged hits (by (d2, idx)), packed at the front in rank order.
-__device__ __forceinline__ int compact_stage(float* __restrict__ sd, int* __restrict__ si, int cnt, int limit,
-                                             int lane) {
-  // ranks are computed against the un-modified stage, then written to a register-held list
-  float kd[(kStage + 31) / 32];
-  int ki[(kStage + 31) / 32], kr[(kStage + 31) / 32];
+// Keep the `limit` best staged hits, packed at the front in rank order (rare path: more than kStage hits).
+__device__ __forceinline__ int compact_stage(unsigned long long* __restrict__ sk, int cnt, int limit, int lane) {
+  unsigned long long kk[(kStage + 31) / 32];
+  int kr[(kStage + 31) / 32];
 #pragma unroll
   for (int t = 0; t < (kStage + 31) / 32; ++t) {
     const int e = t * 32 + lane;
     kr[t] = 0x7fffffff;
     if (e < cnt) {
-      const float d = sd[e];
-      const int id = si[e];
+      const unsigned long long k = sk[e];
       int r = 0;
-      for (int f = 0; f < cnt; ++f) r += before(sd[f], si[f], d, id) ? 1 : 0;
-      kd[t] = d;
-      ki[t] = id;
+      for (int f = 0; f < cnt; ++f) r += sk[f] < k ? 1 : 0;
+      kk[t] = k;
       kr[t] = r;
     }
   }
   __syncwarp();
 #pragma unroll
-  for (int t = 0; t < (kStage + 31) / 32; ++t) {
-    if (kr[t] < limit) {
-      sd[kr[t]] = kd[t];
-      si[kr[t]] = ki[t];
-    }
-  }
+  for (int t = 0; t < (kStage + 31) / 32; ++t)
+    if (kr[t] < limit) sk[kr[t]] = kk[t];
   __syncwarp();
   return min(cnt, limit);
 }
@@ -228,13 +224,11 @@ __global__ void __launch_bounds__(kThreads)
                    const CellGrid* __restrict__ grids, const int* __restrict__ cell_start,
                    const float4* __restrict__ sorted, int ns_total, float r2, int limit, IdxT* __restrict__ out,
                    int row_stride, int* __restrict__ max_count) {
-  __shared__ float s_d[kWarpsPerBlock][kStage];
-  __shared__ int s_i[kWarpsPerBlock][kStage];
+  __shared__ unsigned long long s_k[kWarpsPerBlock][kStage];
   __shared__ int s_beg[kWarpsPerBlock][9];
   __shared__ int s_pre[kWarpsPerBlock][10];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* sd = s_d[warp];
-  int* si = s_i[warp];
+  unsigned long long* sk = s_k[warp];
   int block_max = 0;
 
   for (int qi = blockIdx.x * kWarpsPerBlock + warp; qi < nq; qi += gridDim.x * kWarpsPerBlock) {
@@ -272,50 +266,35 @@ __global__ void __launch_bounds__(kThreads)
 
     int cnt = 0;         // staged hits
     int in_radius = 0;   // all hits (for max_count)
-    bool have_thr = false;
-    float thr_d = 0.f;
-    int thr_i = 0;
+    unsigned long long thr = ~0ull;  // admission threshold: the limit-th best key once the stage was compacted
     for (int t0 = 0; t0 < total; t0 += 32) {
       const int t = t0 + lane;
       bool hit = false;
-      float d2 = 0.f;
-      int id = 0;
+      unsigned long long key = ~0ull;
       if (t < total) {
         int r = 0;
 #pragma unroll
         for (int k = 1; k < 9; ++k) r += (t >= s_pre[warp][k]) ? 1 : 0;
         const float4 c = __ldg(sorted + s_beg[warp][r] + (t - s_pre[warp][r]));
-        d2 = sqdist_exact(px, py, pz, c.x, c.y, c.z);
-        id = __float_as_int(c.w);
+        const float d2 = sqdist_exact(px, py, pz, c.x, c.y, c.z);
         hit = d2 < r2;
+        key = make_key(d2, __float_as_int(c.w));
       }
       const unsigned hm = __ballot_sync(kFull, hit);
       in_radius += __popc(hm);
-      const bool admit = hit && (!have_thr || before(d2, id, thr_d, thr_i));
+      const bool admit = hit && key < thr;
       const unsigned am = __ballot_sync(kFull, admit);
       if (am) {
         if (cnt + __popc(am) > kStage) {  // warp-uniform
-          cnt = compact_stage(sd, si, cnt, limit, lane);
-          have_thr = cnt == limit;
-          if (have_thr) {
-            thr_d = sd[limit - 1];
-            thr_i = si[limit - 1];
-          }
+          cnt = compact_stage(sk, cnt, limit, lane);
+          if (cnt == limit) thr = sk[limit - 1];
           // re-test this batch against the new threshold
-          const bool admit2 = admit && (!have_thr || before(d2, id, thr_d, thr_i));
+          const bool admit2 = admit && key < thr;
           const unsigned am2 = __ballot_sync(kFull, admit2);
-          if (admit2) {
-            const int pos = cnt + __popc(am2 & ((1u << lane) - 1u));
-            sd[pos] = d2;
-            si[pos] = id;
-          }
+          if (admit2) sk[cnt + __popc(am2 & ((1u << lane) - 1u))] = key;
           cnt += __popc(am2);
         } else {
-          if (admit) {
-            const int pos = cnt + __popc(am & ((1u << lane) - 1u));
-            sd[pos] = d2;
-            si[pos] = id;
-          }
+          if (admit) sk[cnt + __popc(am & ((1u << lane) - 1u))] = key;
           cnt += __popc(am);
         }
         __syncwarp();
@@ -325,12 +304,24 @@ __global__ void __launch_bounds__(kThreads)
 
     // rank the staged hits and emit the row
     IdxT* __restrict__ row = out + (size_t)qi * row_stride;
-    for (int e = lane; e < cnt; e += 32) {
-      const float d = sd[e];
-      const int id = si[e];
-      int r = 0;
-      for (int f = 0; f < cnt; ++f) r += before(sd[f], si[f], d, id) ? 1 : 0;
-      if (r < limit) row[r] = (IdxT)id;
+    if (cnt <= 64) {
+      // common case: a lane owns staged hits `lane` and `lane + 32`; ONE pass over the stage ranks both
+      const unsigned long long k0 = lane < cnt ? sk[lane] : ~0ull, k1 = lane + 32 < cnt ? sk[lane + 32] : ~0ull;
+      int r0 = 0, r1 = 0;
+      for (int f = 0; f < cnt; ++f) {
+        const unsigned long long kf = sk[f];
+        r0 += kf < k0 ? 1 : 0;
+        r1 += kf < k1 ? 1 : 0;
+      }
+      if (lane < cnt && r0 < limit) row[r0] = (IdxT)(unsigned int)k0;
+      if (lane + 32 < cnt && r1 < limit) row[r1] = (IdxT)(unsigned int)k1;
+    } else {
+      for (int e = lane; e < cnt; e += 32) {
+        const unsigned long long k = sk[e];
+        int r = 0;
+        for (int f = 0; f < cnt; ++f) r += sk[f] < k ? 1 : 0;
+        if (r < limit) row[r] = (IdxT)(unsigned int)k;
+      }
     }
     for (int j = min(cnt, limit) + lane; j < limit; j += 32) row[j] = (IdxT)ns_total;
     __syncwarp();

@@ -18,6 +18,8 @@
 #include "spr_common.cuh"
 #include "tc05.cuh"
 
+#include <cstdlib>
+
 namespace spr {
 namespace {
 
@@ -54,7 +56,9 @@ struct GemmArgs {
   float next_scale;        // OUT_AIMG: activation scale of the next GEMM's A operand
 };
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, int mode) {
+__device__ long long g_gemm_dbg[4096];
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, int mode, int dbg) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem =
       reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -124,29 +128,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_f16_f32(128, 128);
+      // ONE N = 256 MMA per K step covers [W_hi | W_lo] (the two 128-row halves of a stage are contiguous row
+      // groups of the same K-major tile): the A tile is read from shared memory once instead of twice, and SS-mode
+      // MMAs are shared-memory-bandwidth bound (measured 104 cycles per N=128 MMA vs 128 per N=256)
+      constexpr uint32_t idesc = idesc_f16_f32(128, 256);
       const uint64_t adesc0 = desc_sw128_kmajor(smem_u32(sA));
       const uint64_t bdesc0 = desc_sw128_kmajor(smem_u32(sB));
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const bool rec = dbg && blockIdx.x == 0;
+      if (rec) g_gemm_dbg[0] = clock64();
       if (resident && first < limit) mbar_wait(bar_w, 0);
+      if (rec) g_gemm_dbg[1] = clock64();
       for (int tile = first; tile < limit; tile += step, ++it) {
         const int buf = it & 1;
+        if (rec && it < 60) g_gemm_dbg[8 + it * 8 + 0] = clock64();
         mbar_wait(&bar_acce[buf], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
+        if (rec && it < 60) g_gemm_dbg[8 + it * 8 + 1] = clock64();
         for (int a = 0; a < KA; ++a) {
           mbar_wait(&bar_full[stage], phase);
           tc_fence_after();
+          if (rec && it < 60 && a < 4) g_gemm_dbg[8 + it * 8 + 2 + a] = clock64();
           const int bslot = resident ? a : stage;
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t ad = adesc0 + (uint64_t)((stage * A_STAGE + kk * 32) >> 4);
-              const uint64_t bd = bdesc0 + (uint64_t)((bslot * B_STAGE + sub * A_STAGE + kk * 32) >> 4);
-              umma_f16(tmem + buf * 256 + sub * 128, ad, bd, idesc, (a | kk) != 0);
-            }
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t ad = adesc0 + (uint64_t)((stage * A_STAGE + kk * 32) >> 4);
+            const uint64_t bd = bdesc0 + (uint64_t)((bslot * B_STAGE + kk * 32) >> 4);
+            umma_f16(tmem + buf * 256, ad, bd, idesc, (a | kk) != 0);
+          }
           umma_commit(&bar_empty[stage]);
           if (++stage == nstages) {
             stage = 0;
@@ -154,7 +165,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
           }
         }
         umma_commit(&bar_accf[buf]);
+        if (rec && it < 60) g_gemm_dbg[8 + it * 8 + 6] = clock64();
       }
+      if (rec) g_gemm_dbg[2] = clock64();
     }
     __syncwarp();
   } else {
@@ -447,7 +460,22 @@ extern "C" int spr_gemm_tc(const void* d_a_img, const void* d_w_img, const float
     const int total = m_tiles * n_tiles;
     grid = total < kNumSMs ? total : kNumSMs;
   }
-  k_gemm_tc<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(g, out_mode);
+  static int dbg = -1;
+  if (dbg < 0) dbg = getenv("SPR_GEMM_DEBUG") ? 1 : 0;
+  k_gemm_tc<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(g, out_mode, dbg);
   SPR_LAUNCH_CHECK("k_gemm_tc");
+  if (dbg) {
+    long long h[4096];
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(h, g_gemm_dbg, sizeof(h));
+    fprintf(stderr, "[gemm dbg] T=%d N=%d K=%d grid=%d: start->W %lld, total %lld cycles\n", T, N, K, grid, h[1] - h[0],
+            h[2] - h[0]);
+    const int tiles = (g.K / 64 <= RES_KA) ? (m_tiles - 0 + grid / n_tiles - 1) / (grid / n_tiles) : (m_tiles * n_tiles + grid - 1) / grid;
+    for (int i = 0; i < tiles && i < 8; ++i) {
+      long long* r = h + 8 + i * 8;
+      fprintf(stderr, "  tile %d: +%lld wait_acce %lld | full0 +%lld full1 +%lld full2 +%lld full3 +%lld | issued +%lld\n", i,
+              r[0] - h[0], r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5]);
+    }
+  }
   return SPR_OK;
 }

@@ -175,7 +175,7 @@ class SimpleBlock(nn.Module):
         x = self.KPConv(q_pts, s_pts, inds, x)
         if self.use_bn and x.shape[1] % 32 == 0:
             o = self.batch_norm.forward_ex(x, lengths, slope=LRELU_SLOPE, want_f32=True, want_image=True)
-            batch['_operand_image'] = (o['f32'].data_ptr(), o['image'])   # for the next block's unary GEMMs
+            batch['_operand_image'] = (o['f32'], o['image'])   # for the next block's unary GEMMs (matched by identity)
             return o['f32']
         return self.batch_norm(x, lengths, slope=LRELU_SLOPE)
 
@@ -218,7 +218,9 @@ class ResnetBottleneckBlock(nn.Module):
         q_pts, s_pts, inds, post_lengths = _level_io(batch, self.layer_ind, strided)
         n_in = features.shape[0]
         stash = batch.get('_operand_image')
-        f_img = stash[1] if stash is not None and stash[0] == features.data_ptr() else ops.gemm_prepare_input(features)
+        # the stash holds the tensor itself: identity, not address, decides (a freed block output's address can be
+        # handed to a later tensor)
+        f_img = stash[1] if stash is not None and stash[0] is features else ops.gemm_prepare_input(features)
 
         x = self.unary1.forward_ex(f_img, n_in, pre_lengths, want_f32=False, kpconv_points=s_pts)['kpconv']
         x = ops.kpconv_forward_prepared(q_pts, inds, x, self.KPConv.weights, self.KPConv.kernel_points,
@@ -235,12 +237,13 @@ class ResnetBottleneckBlock(nn.Module):
             shortcut = self.unary_shortcut.forward_ex(s_img, n_out, post_lengths, want_f32=True)['f32']
         o = self.unary2.forward_ex(x_img, n_out, post_lengths, residual=shortcut, slope=LRELU_SLOPE, want_f32=True,
                                    want_image=True)
-        batch['_operand_image'] = (o['f32'].data_ptr(), o['image'])
+        batch['_operand_image'] = (o['f32'], o['image'])
         return o['f32']
 
     def forward(self, features, batch):
         if self._fusable(features):
             return self._forward_fused(features, batch)
+        batch['_operand_image'] = None  # this route writes plain rows only
         strided = 'strided' in self.block_name
         pre_lengths = batch['stack_lengths'][self.layer_ind]
         q_pts, s_pts, inds, post_lengths = _level_io(batch, self.layer_ind, strided)

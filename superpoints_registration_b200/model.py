@@ -278,7 +278,7 @@ class RegTR(nn.Module):
 
         feats_un, _ = self.kpf_encoder(feats0, meta)
         stash = meta.get('_operand_image')  # the last encoder block wrote its output as a GEMM operand image too
-        if stash is not None and stash[0] == feats_un.data_ptr():
+        if stash is not None and stash[0] is feats_un:
             both = ops.gemm_tc(stash[1], ops.weight_image(self.feat_proj.weight), self.feat_proj.bias, feats_un.shape[0])
         else:
             both = ops.linear_tc(feats_un, self.feat_proj.weight, self.feat_proj.bias)

@@ -231,15 +231,12 @@ class KPConvWeightImage:
         self.key = (weights.data_ptr(), weights._version)
 
 
-_KPCONV_WEIGHT_IMAGES = {}
-
-
 def kpconv_weight_image(weights: torch.Tensor) -> KPConvWeightImage:
     key = (weights.data_ptr(), weights._version)
-    wi = _KPCONV_WEIGHT_IMAGES.get(id(weights))
+    wi = getattr(weights, "_spr_kpconv_image", None)   # cached on the tensor, see weight_image
     if wi is None or wi.key != key:
         wi = KPConvWeightImage(weights)
-        _KPCONV_WEIGHT_IMAGES[id(weights)] = wi
+        weights._spr_kpconv_image = wi
     return wi
 
 
@@ -435,15 +432,15 @@ class WeightImage:
         self.key = (weight.data_ptr(), weight._version)
 
 
-_WEIGHT_IMAGES = {}
-
-
 def weight_image(weight: torch.Tensor) -> WeightImage:
+    """Operand image of a weight, cached ON the tensor object (so it dies with it: an id()-keyed dict would hand a
+    stale image to a new parameter that happens to reuse the id, address and version of a freed one) and rebuilt when
+    the storage or the version counter changes (load_state_dict, .to(), optimiser steps)."""
     key = (weight.data_ptr(), weight._version)
-    wi = _WEIGHT_IMAGES.get(id(weight))
+    wi = getattr(weight, "_spr_weight_image", None)
     if wi is None or wi.key != key:
         wi = WeightImage(weight)
-        _WEIGHT_IMAGES[id(weight)] = wi
+        weight._spr_weight_image = wi
     return wi
 
 

@@ -175,9 +175,33 @@ def test_forward_fused_paths_agree_with_plain_paths(kind):
             if m.__class__.__name__ == "KPConv":
                 m.mode = 0
         plain = model(dict(batch))
+        # third route for diagnosis: packed tokens, our attention, torch linears, fp32 SIMT KPConv
+        model.packed_transformer = True
+        model.transformer_encoder.fused = False
+        third = model(dict(batch))
+    for a, b, c in zip(fused["src_feat"] + fused["tgt_feat"], plain["src_feat"] + plain["tgt_feat"],
+                       third["src_feat"] + third["tgt_feat"]):
+        print(f"[{kind}] fused-plain {(a - b).abs().max().item():.2e} fused-third {(a - c).abs().max().item():.2e} "
+              f"plain-third {(b - c).abs().max().item():.2e}")
     for a, b in zip(fused["src_feat"] + fused["tgt_feat"], plain["src_feat"] + plain["tgt_feat"]):
         assert torch.isfinite(a).all()
         err = (a - b).abs().max().item()
         assert err <= 3e-4 * b.abs().max().item(), (kind, err, b.abs().max().item())
     R = fused["pose"][:, :, :3].double()
     assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3, device=DEV, dtype=torch.float64).expand_as(R), atol=1e-5)
+
+
+def test_weight_image_cache_follows_the_tensor():
+    """The operand image of a weight is rebuilt when the weight changes in place and never leaks to another tensor."""
+    x = torch.randn(70, 64, device=DEV)
+    w = torch.nn.Parameter(torch.randn(32, 64, device=DEV))
+    y1 = ops.linear_tc(x, w)
+    with torch.no_grad():
+        w.mul_(2.0)
+    y2 = ops.linear_tc(x, w)
+    assert (y2 - 2 * y1).abs().max().item() <= 1e-5 * y2.abs().max().item()
+    for _ in range(20):   # fresh parameters may reuse the freed one's id / address / version
+        w2 = torch.nn.Parameter(torch.randn(32, 64, device=DEV))
+        ref = x.double() @ w2.double().t()
+        assert (ops.linear_tc(x, w2).double() - ref).abs().max().item() <= 3e-6 * ref.abs().max().item()
+        del w2

@@ -32,9 +32,11 @@ constexpr int B_STAGE = 2 * 128 * 128;     // 32 KB
 constexpr int NSTAGES = 4;
 constexpr int EPI_WARPS = 8;               // 2 per TMEM lane quadrant, each owning 64 of the 128 tile columns
 constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;
-constexpr int RES_STAGES = 6;               // A ring depth when W is resident (bytes in flight bound the A stream)
+constexpr int RES_STAGES = 4;               // A ring depth when W is resident
 constexpr int RES_KA = 4;                   // W atoms kept resident (K <= 256)
-constexpr size_t GEMM_SMEM = 1024 + (size_t)RES_STAGES * A_STAGE + (size_t)RES_KA * B_STAGE + 256;
+constexpr int EPI_ROW = 36;                 // floats per staged row (32 + 4 padding: conflict-free 16-byte accesses)
+constexpr int EPI_STAGE_BYTES = 16 * EPI_ROW * 4;   // per epilogue warp: 16 tokens x 32 columns
+constexpr size_t GEMM_SMEM = 1024 + (size_t)RES_STAGES * A_STAGE + (size_t)RES_KA * B_STAGE + 256 + EPI_WARPS * EPI_STAGE_BYTES;
 static_assert((size_t)NSTAGES * (A_STAGE + B_STAGE) <= (size_t)RES_STAGES * A_STAGE + (size_t)RES_KA * B_STAGE, "smem");
 
 enum { OUT_F32 = 0, OUT_PLANES = 1, OUT_AIMG = 2 };
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
   uint64_t* bar_acce = bars + 18;       // [2] accumulator empty
   uint64_t* bar_w = bars + 20;          // resident W image has landed
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 22);
+  float* s_epi = reinterpret_cast<float*>(smem + RES_STAGES * A_STAGE + RES_KA * B_STAGE + 256);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m_tiles = (g.T + BM_TOK - 1) / BM_TOK, n_tiles = (g.N + BN - 1) / BN;
   // tile walk: resident mode pins the CTA to n tile (blockIdx % n_tiles) and strides over m tiles; streaming mode
@@ -185,8 +188,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
       const int mt = resident ? tile : tile / n_tiles, nt = resident ? nt_fixed : tile % n_tiles;
       const int token = mt * BM_TOK + tok_l;
       const bool tok_ok = token < g.T;
+      const bool erec = dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 60;
+      if (erec) g_gemm_dbg[1024 + it * 4 + 0] = clock64();
       mbar_wait(&bar_accf[buf], (it >> 1) & 1);
       tc_fence_after();
+      if (erec) g_gemm_dbg[1024 + it * 4 + 1] = clock64();
       const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16) + buf * 256 + chalf * 64;
       // all 16 TMEM loads of this warp's 64 columns are issued back to back, then ONE wait
       float v1[8][8], v2[8][8];
@@ -202,35 +208,61 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acce[buf]);
+      if (erec) g_gemm_dbg[1024 + it * 4 + 2] = clock64();
+      // The accumulator rows are per-lane (lane = stacked token row): writing them directly costs one memory
+      // transaction per token per instruction.  Each group of 32 columns is transposed through a small per-warp
+      // shared-memory stage so that global accesses (bias, residual, output) are row-contiguous: a warp
+      // instruction covers 4 tokens x 128 bytes.
+      float* stg = s_epi + (warp - 2) * (EPI_STAGE_BYTES / 4);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int cur = i;
-        const int c0 = chalf * 64 + i * 8;
-        const int n = nt * BN + c0 + half_sel * 4;
-        const bool ok = tok_ok && n < g.N;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), rv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok && g.bias) bv = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-        if (ok && mode == OUT_F32 && g.residual)
-          rv = *reinterpret_cast<const float4*>(g.residual + (size_t)token * g.ld_res + n);
-        float sum[8];
+      for (int grp = 0; grp < 2; ++grp) {
+        // bias and residual of this group's coalesced phase are requested first: their latency overlaps the transpose
+        const int pcol = nt * BN + chalf * 64 + grp * 32 + (lane & 7) * 4;
+        float4 pbias = make_float4(0.f, 0.f, 0.f, 0.f), pres[4];
+        if (g.bias && pcol < g.N && dbg < 2) pbias = __ldg(reinterpret_cast<const float4*>(g.bias + pcol));
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          sum[e] = v1[cur][e] + v2[cur][e];
-          sum[e] += __shfl_xor_sync(kFull, sum[e], 1);
+        for (int k = 0; k < 4; ++k) {
+          pres[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int ptok = mt * BM_TOK + qd * 16 + k * 4 + (lane >> 3);
+          if (mode == OUT_F32 && g.residual && ptok < g.T && pcol < g.N && dbg < 2)
+            pres[k] = *reinterpret_cast<const float4*>(g.residual + (size_t)ptok * g.ld_res + pcol);
         }
-        if (ok) {
-          float y[4];
-          const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
-          const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            y[e] = (half_sel ? sum[4 + e] : sum[e]) * g.out_scale + bb[e] + rr[e];
-            if (g.relu) y[e] = fmaxf(y[e], 0.f);
+        for (int ii = 0; ii < 4; ++ii) {
+          const int i = grp * 4 + ii;
+          float sum[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            sum[e] = v1[i][e] + v2[i][e];
+            sum[e] += __shfl_xor_sync(kFull, sum[e], 1);
           }
+          const float4 y = half_sel ? make_float4(sum[4], sum[5], sum[6], sum[7]) : make_float4(sum[0], sum[1], sum[2], sum[3]);
+          *reinterpret_cast<float4*>(stg + (lane >> 1) * EPI_ROW + ii * 8 + half_sel * 4) = y;
+        }
+        __syncwarp();
+        const int ncol0 = nt * BN + chalf * 64 + grp * 32 + (lane & 7) * 4;  // first of this lane's 4 columns
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int tl = k * 4 + (lane >> 3);                    // token within the warp's 16
+          const int token = mt * BM_TOK + qd * 16 + tl;
+          const bool ok = token < g.T && ncol0 < g.N && dbg < 2;
+          if (!ok) continue;
+          const float4 a = *reinterpret_cast<const float4*>(stg + tl * EPI_ROW + (lane & 7) * 4);
+          float y[4] = {a.x * g.out_scale, a.y * g.out_scale, a.z * g.out_scale, a.w * g.out_scale};
+          y[0] += pbias.x; y[1] += pbias.y; y[2] += pbias.z; y[3] += pbias.w;
           if (mode == OUT_F32) {
-            *reinterpret_cast<float4*>(g.out_f32 + (size_t)token * g.ld_out + n) = make_float4(y[0], y[1], y[2], y[3]);
+            y[0] += pres[k].x; y[1] += pres[k].y; y[2] += pres[k].z; y[3] += pres[k].w;
+            if (g.relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], 0.f);
+            }
+            *reinterpret_cast<float4*>(g.out_f32 + (size_t)token * g.ld_out + ncol0) = make_float4(y[0], y[1], y[2], y[3]);
           } else {
-            const float sc = mode == OUT_AIMG ? g.next_scale : (n < g.n_scaled ? g.col_scale : 1.f);
+            if (g.relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], 0.f);
+            }
+            const float sc = mode == OUT_AIMG ? g.next_scale : (ncol0 < g.n_scaled ? g.col_scale : 1.f);
 #pragma unroll
             for (int e = 0; e < 4; ++e) y[e] *= sc;
             const __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
@@ -239,19 +271,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
             const uint2 hv = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
             const uint2 lv = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
             if (mode == OUT_PLANES) {
-              *reinterpret_cast<uint2*>(g.out_hi + (size_t)token * g.ld_out + n) = hv;
-              *reinterpret_cast<uint2*>(g.out_lo + (size_t)token * g.ld_out + n) = lv;
+              *reinterpret_cast<uint2*>(g.out_hi + (size_t)token * g.ld_out + ncol0) = hv;
+              *reinterpret_cast<uint2*>(g.out_lo + (size_t)token * g.ld_out + ncol0) = lv;
             } else {  // A image of the next GEMM, whose K is this N
               const int KA2 = (g.N + 63) / 64;
               unsigned char* blk = reinterpret_cast<unsigned char*>(g.out_hi) +
-                                   ((size_t)(token >> 6) * KA2 + (n >> 6)) * A_STAGE;
-              const uint32_t r2 = 2 * (token & 63), chunk = (n & 63) >> 3, inb = (n & 7) * 2;
+                                   ((size_t)(token >> 6) * KA2 + (ncol0 >> 6)) * A_STAGE;
+              const uint32_t r2 = 2 * (token & 63), chunk = (ncol0 & 63) >> 3, inb = (ncol0 & 7) * 2;
               *reinterpret_cast<uint2*>(blk + sw128_offset(r2, chunk) + inb) = hv;
               *reinterpret_cast<uint2*>(blk + sw128_offset(r2 + 1, chunk) + inb) = lv;
             }
           }
         }
+        __syncwarp();
       }
+      if (erec) g_gemm_dbg[1024 + it * 4 + 3] = clock64();
     }
   }
   tc_fence_before();
@@ -461,7 +495,7 @@ extern "C" int spr_gemm_tc(const void* d_a_img, const void* d_w_img, const float
     grid = total < kNumSMs ? total : kNumSMs;
   }
   static int dbg = -1;
-  if (dbg < 0) dbg = getenv("SPR_GEMM_DEBUG") ? 1 : 0;
+  if (dbg < 0) dbg = getenv("SPR_GEMM_DEBUG") ? atoi(getenv("SPR_GEMM_DEBUG")) : 0;
   k_gemm_tc<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(g, out_mode, dbg);
   SPR_LAUNCH_CHECK("k_gemm_tc");
   if (dbg) {
@@ -473,8 +507,11 @@ extern "C" int spr_gemm_tc(const void* d_a_img, const void* d_w_img, const float
     const int tiles = (g.K / 64 <= RES_KA) ? (m_tiles - 0 + grid / n_tiles - 1) / (grid / n_tiles) : (m_tiles * n_tiles + grid - 1) / grid;
     for (int i = 0; i < tiles && i < 8; ++i) {
       long long* r = h + 8 + i * 8;
-      fprintf(stderr, "  tile %d: +%lld wait_acce %lld | full0 +%lld full1 +%lld full2 +%lld full3 +%lld | issued +%lld\n", i,
-              r[0] - h[0], r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5]);
+      long long* e = h + 1024 + i * 4;
+      fprintf(stderr, "  tile %d: +%lld wait_acce %lld | full0 +%lld full1 +%lld full2 +%lld full3 +%lld | issued +%lld"
+                      " || epi: wait_accf %lld, tmem loads %lld, math+stores %lld\n", i,
+              r[0] - h[0], r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], e[1] - e[0],
+              e[2] - e[1], e[3] - e[2]);
     }
   }
   return SPR_OK;

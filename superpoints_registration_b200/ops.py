@@ -14,7 +14,14 @@ import torch
 from . import _lib
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream.  The raw accessor is ~20x cheaper than building a Stream object; a
+    forward makes ~350 calls."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

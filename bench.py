@@ -35,9 +35,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=8, help="pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=32, help="pairs per GPU per step")
     ap.add_argument("--points", type=int, default=20000, help="nominal points per fragment")
-    ap.add_argument("--arch", default="3stage", choices=["3stage", "4stage"])
+    ap.add_argument("--arch", default="4stage", choices=["3stage", "4stage"],
+                    help="4stage = the configuration BASELINE.json names; 3stage = the shipped yaml")
+    ap.add_argument("--no-alt", action="store_true", help="skip the short run of the other architecture")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-pairs", type=int, default=1, help="pairs in the bounded CPU sample")
@@ -50,7 +52,8 @@ def make_cfg(arch):
 
 
 def workload_name(args):
-    stages = "3-stage (shipped conf/qk_regtr_full_3dmatch.yaml)" if args.arch == "3stage" else "4-stage variant"
+    stages = ("3-stage (shipped conf/qk_regtr_full_3dmatch.yaml:56-63)" if args.arch == "3stage"
+              else "4-stage (BASELINE.json configs[2]; conf/qk_regtr_full_3dmatch.yaml:64-74)")
     return (f"3DMatch-shape fragments (~{args.points // 1000}k pts, voxel 0.025 m, {stages} KPConv), "
             f"full forward + pose, Sinkhorn x3")
 
@@ -367,6 +370,29 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if world == 1 and not args.no_alt:
+            # the other architecture of the same yaml, short run, same timing rules (reported beside, not the headline)
+            other = "3stage" if args.arch == "4stage" else "4stage"
+            torch.manual_seed(0)
+            alt_model = spr.RegTR(make_cfg(other)).to(dev).eval()
+            alt_model.return_attn = False
+            for _ in range(3):
+                alt_model(dict(dev_batch))
+            torch.cuda.synchronize()
+            alt_ms = 0.0
+            alt_steps = max(3, args.steps // 2)
+            for _ in range(alt_steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                alt_model(dict(dev_batch))
+                e1.record()
+                torch.cuda.synchronize()
+                alt_ms += e0.elapsed_time(e1)
+            line["alt"] = {"workload": workload_name(argparse.Namespace(**{**vars(args), "arch": other})),
+                           "value": B * alt_steps / (alt_ms * 1e-3), "unit": UNIT, "ms_per_step": alt_ms / alt_steps,
+                           "steps": alt_steps}
+            del alt_model
         if world == 1 and not args.no_cpu_baseline:
             v, dt, cores, kind, sample = cpu_forward_timing(args, max(1, args.cpu_pairs), repeats=2)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}

@@ -36,11 +36,13 @@ __device__ __forceinline__ bool locate_chunk(const int* __restrict__ lens, int B
   return false;
 }
 
-// part[chunk][c] = (sum, sumsq) over the chunk's rows, fp64.
+// part[chunk][c] = (sum, sumsq) over the chunk's rows, fp64.  A thread owns 4 consecutive channels (16-byte loads),
+// c/4 threads cover a row, 256/(c/4) rows are read per step with the whole chunk's loads issued up front; the rows
+// of a thread are folded in a fixed order, then the row lanes are folded in a fixed order through shared memory.
 __global__ void __launch_bounds__(256) k_in_partial(const float* __restrict__ x, const int* __restrict__ lens, int B,
                                                     int c, double2* __restrict__ part) {
   __shared__ int s_loc[3];
-  __shared__ double2 s_red[256];
+  __shared__ double s_red[256 * 8];
   if (threadIdx.x == 0) {
     int cloud, row0, rows;
     if (!locate_chunk(lens, B, blockIdx.x, cloud, row0, rows)) rows = 0;
@@ -51,36 +53,48 @@ __global__ void __launch_bounds__(256) k_in_partial(const float* __restrict__ x,
   __syncthreads();
   const int row0 = s_loc[1], rows = s_loc[2];
   if (rows == 0) return;
-  const int cw = c < 256 ? ((c + 31) / 32) * 32 : 256;  // channel lanes
-  const int rl = 256 / cw;                              // row lanes
+  const int c4 = c >> 2;
+  const int cw = c4 < 256 ? c4 : 256;   // channel-quad lanes
+  const int rl = 256 / cw;              // row lanes
   const int tc = threadIdx.x % cw, tr = threadIdx.x / cw;
-  for (int c0 = 0; c0 < c; c0 += cw) {
-    const int ch = c0 + tc;
-    double s1 = 0.0, s2 = 0.0;
-    if (ch < c && tr < rl) {
-      const float* col = x + (size_t)row0 * c + ch;
+  for (int q0 = 0; q0 < c4; q0 += cw) {
+    const int qd = q0 + tc;
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (qd < c4 && tr < rl) {
+      const float4* col = reinterpret_cast<const float4*>(x + (size_t)row0 * c) + qd;
       int r = tr;
-      for (; r + 3 * rl < rows; r += 4 * rl) {  // four independent loads in flight per thread
-        const float v0 = col[(size_t)r * c], v1 = col[(size_t)(r + rl) * c], v2 = col[(size_t)(r + 2 * rl) * c],
-                    v3 = col[(size_t)(r + 3 * rl) * c];
-        s1 += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
-        s2 += ((double)v0 * v0 + (double)v1 * v1) + ((double)v2 * v2 + (double)v3 * v3);
+      for (; r + 3 * rl < rows; r += 4 * rl) {  // four independent 16-byte loads in flight
+        const float4 v0 = col[(size_t)r * c4], v1 = col[(size_t)(r + rl) * c4], v2 = col[(size_t)(r + 2 * rl) * c4],
+                     v3 = col[(size_t)(r + 3 * rl) * c4];
+        const float4 vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          a[0] += (double)vv[k].x; a[1] += (double)vv[k].x * vv[k].x;
+          a[2] += (double)vv[k].y; a[3] += (double)vv[k].y * vv[k].y;
+          a[4] += (double)vv[k].z; a[5] += (double)vv[k].z * vv[k].z;
+          a[6] += (double)vv[k].w; a[7] += (double)vv[k].w * vv[k].w;
+        }
       }
       for (; r < rows; r += rl) {
-        const double v = (double)col[(size_t)r * c];
-        s1 += v;
-        s2 += v * v;
+        const float4 v = col[(size_t)r * c4];
+        a[0] += (double)v.x; a[1] += (double)v.x * v.x;
+        a[2] += (double)v.y; a[3] += (double)v.y * v.y;
+        a[4] += (double)v.z; a[5] += (double)v.z * v.z;
+        a[6] += (double)v.w; a[7] += (double)v.w * v.w;
       }
     }
-    s_red[threadIdx.x] = make_double2(s1, s2);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s_red[k * 256 + threadIdx.x] = a[k];
     __syncthreads();
-    if (tr == 0 && ch < c) {
-      double a1 = s1, a2 = s2;
-      for (int t = 1; t < rl; ++t) {  // fixed order
-        a1 += s_red[t * cw + tc].x;
-        a2 += s_red[t * cw + tc].y;
-      }
-      part[(size_t)blockIdx.x * c + ch] = make_double2(a1, a2);
+    if (tr == 0 && qd < c4) {
+      for (int t = 1; t < rl; ++t)  // fixed order
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += s_red[k * 256 + t * cw + tc];
+      double2* dst = part + (size_t)blockIdx.x * c + qd * 4;
+      dst[0] = make_double2(a[0], a[1]);
+      dst[1] = make_double2(a[2], a[3]);
+      dst[2] = make_double2(a[4], a[5]);
+      dst[3] = make_double2(a[6], a[7]);
     }
     __syncthreads();
   }
@@ -148,7 +162,7 @@ __device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t j) {
 //   out_x16 / out_pts4 / amax_bits   pre-split feature rows, packed support points and max|y| of the next KPConv
 //             (kpconv_tc.cu pre-pass outputs)
 // A group of G = min(c/8, 32) lanes owns one row, a lane 8 consecutive channels per step of 8*G.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     k_in_apply_ex(const float* __restrict__ x, const int* __restrict__ offs, int B, int n, int c,
                   const float2* __restrict__ stats, float slope, const float* __restrict__ residual,
                   float* __restrict__ out_f32, unsigned char* __restrict__ out_img, float a_scale,

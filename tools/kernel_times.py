@@ -16,9 +16,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--pairs", type=int, default=8)
 ap.add_argument("--points", type=int, default=20000)
 ap.add_argument("--top", type=int, default=32)
+ap.add_argument("--arch", default="4stage", choices=["3stage", "4stage"])
 args = ap.parse_args()
 dev = "cuda:0"
-cfg = spr.threedmatch_config()
+cfg = spr.threedmatch_config() if args.arch == "3stage" else spr.threedmatch_4stage_config()
 torch.manual_seed(0); np.random.seed(0)
 model = spr.RegTR(cfg).to(dev).eval()
 model.return_attn = False

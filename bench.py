@@ -266,12 +266,12 @@ def run_ours(args):
     # the encoder blocks feed the tensor-core KPConv with operands written by the preceding normalisation kernel
     raw_prepared = ops.kpconv_forward_prepared
 
-    def timed_prepared(q_pts, neighb_inds, feats, weights, kernel_points, extent):
+    def timed_prepared(q_pts, neighb_inds, feats, weights, kernel_points, extent, **kw):
         if not recording["on"]:
-            return raw_prepared(q_pts, neighb_inds, feats, weights, kernel_points, extent)
+            return raw_prepared(q_pts, neighb_inds, feats, weights, kernel_points, extent, **kw)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        y = raw_prepared(q_pts, neighb_inds, feats, weights, kernel_points, extent)
+        y = raw_prepared(q_pts, neighb_inds, feats, weights, kernel_points, extent, **kw)
         e1.record()
         records.append((e0, e1, q_pts.shape[0], neighb_inds.shape[1], weights.shape[1], weights.shape[2]))
         return y

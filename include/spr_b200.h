@@ -86,6 +86,9 @@ SPR_API int spr_grid_subsample_batch(const float* d_points, const int32_t* d_len
 SPR_API size_t spr_cell_grid_workspace_bytes(int n_supports, int n_clouds);
 SPR_API int spr_cell_grid_build(const float* d_supports, const int32_t* d_s_lengths, int n_supports, int n_clouds, float radius,
                         void* d_grid_workspace, size_t workspace_bytes, void* stream);
+/* order[i] = index of the i-th support in (cloud, z, y, x) cell order of a built grid: a spatially coherent walk of
+ * the stacked clouds, used as the query processing order of the KPConv kernels (d_order) */
+SPR_API int spr_cell_grid_order(const void* d_grid_workspace, int n_supports, int n_clouds, int32_t* d_order, void* stream);
 SPR_API int spr_radius_query(const float* d_queries, const int32_t* d_q_lengths, int n_queries, int n_clouds,
                      const void* d_grid_workspace, int n_supports, float radius, int limit, void* d_out_idx,
                      int idx_is_64, int row_stride, int32_t* d_out_max_count, void* stream);
@@ -111,13 +114,15 @@ SPR_API int spr_kpconv_forward(const float* d_q, const float* d_s, const void* d
 /* KPConv (tensor-core path) with operands prepared by the producing kernels instead of the built-in pre-pass:
  *   spr_kpconv_prepare_weights: [W_hi | W_lo] stage images + max|W| (one word), once per weight
  *   spr_kpconv_forward_prepared: d_pts4 [ns] float4, d_x16 [ns, c] (hi | lo<<16), d_amax_x (one word) as written
- *   by spr_instance_norm_lrelu_ex.  Cin = Cout = c in {32, 64, 128, 256}. */
+ *   by spr_instance_norm_lrelu_ex.  Cin = Cout = c in {32, 64, 128, 256}.  d_order (optional, [nq] i32): a
+ *   permutation of the queries giving the processing order (results are written at the original rows). */
 SPR_API size_t spr_kpconv_weight_image_bytes(int c);
+SPR_API size_t spr_kpconv_scratch_bytes(int H, int c);   /* d_scratch of spr_kpconv_forward_prepared (0 for c = 32) */
 SPR_API int spr_kpconv_prepare_weights(const float* d_w, int c, void* d_img, void* d_amax_w, void* stream);
 SPR_API int spr_kpconv_forward_prepared(const float* d_q, const void* d_idx, int idx_is_64, int row_stride, int H,
                                 const void* d_pts4, const void* d_x16, const void* d_amax_x, int c, const void* d_wimg,
                                 const void* d_amax_w, const float* d_kp, float extent, float* d_out, int nq, int ns,
-                                void* stream);
+                                void* d_scratch, const int32_t* d_order, void* stream);
 
 /* Per-cloud instance normalisation + LeakyReLU (+ optional residual add before the activation).
  * Replaces BatchNormBlock.forward with nn.InstanceNorm1d (kpconv_blocks.py:474-530: per cloud, per

@@ -25,6 +25,7 @@ _SIGNATURES = {
     "spr_grid_subsample_batch": (c_int, [c_fp, c_fp, c_int, c_int, c_float, c_fp, c_fp, c_fp, c_fp, c_size_t, c_void_p]),
     "spr_cell_grid_workspace_bytes": (c_size_t, [c_int, c_int]),
     "spr_cell_grid_build": (c_int, [c_fp, c_fp, c_int, c_int, c_float, c_fp, c_size_t, c_void_p]),
+    "spr_cell_grid_order": (c_int, [c_fp, c_int, c_int, c_fp, c_void_p]),
     "spr_radius_query": (c_int, [c_fp, c_fp, c_int, c_int, c_fp, c_int, c_float, c_int, c_fp, c_int, c_int, c_fp,
                                  c_void_p]),
     "spr_kpconv_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
@@ -37,8 +38,9 @@ _SIGNATURES = {
                                            c_fp, c_fp, c_fp, c_fp, c_fp, c_size_t, c_void_p]),
     "spr_kpconv_weight_image_bytes": (c_size_t, [c_int]),
     "spr_kpconv_prepare_weights": (c_int, [c_fp, c_int, c_fp, c_fp, c_void_p]),
+    "spr_kpconv_scratch_bytes": (c_size_t, [c_int, c_int]),
     "spr_kpconv_forward_prepared": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp,
-                                            c_float, c_fp, c_int, c_int, c_void_p]),
+                                            c_float, c_fp, c_int, c_int, c_fp, c_fp, c_void_p]),
     "spr_max_pool": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp, c_void_p]),
     "spr_match_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "spr_dual_softmax_match": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -28,6 +28,13 @@
 #include "spr_common.cuh"
 #include "tc05.cuh"
 
+// scratch of the influence-fragment cache: one 16-byte vector per lane, neighbour block and query of a tile, per CTA
+extern "C" size_t spr_kpconv_scratch_bytes(int H, int c) {
+  if (c <= 32) return 0;
+  const size_t nb = (size_t)((H > 0 ? H : 1) + 7) / 8;
+  return (size_t)148 * 64 * nb * 32 * 16;
+}
+
 namespace spr {
 
 namespace {
@@ -171,7 +178,7 @@ struct TcCfg {
   static constexpr int OFF_RING = A_BYTES;
   static constexpr int OFF_WBUF = OFF_RING + NSTAGES * STAGE_BYTES;
   static constexpr int OFF_MISC = OFF_WBUF + WBUF_BYTES;
-  static constexpr int MISC_BYTES = 16 * 8 + 32 + 2 * TQ * 4 + 48 * 4;
+  static constexpr int MISC_BYTES = 16 * 8 + 32 + 2 * TQ * 4 + 48 * 4 + TQ * 4;
   static constexpr size_t SMEM = 1024 + OFF_MISC + MISC_BYTES;
   static constexpr size_t IMG_BYTES = (size_t)PASSES * BLOCKS_PER_PASS * STAGE_BYTES;
 };
@@ -218,7 +225,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
                 int H, const uint32_t* __restrict__ x16, const unsigned char* __restrict__ wimg,
                 const float* __restrict__ kp, const float4* __restrict__ pts4,
                 const unsigned int* __restrict__ amax_x_bits, const unsigned int* __restrict__ amax_w_bits, float extent, float* __restrict__ out, int nq, int ns, int tq,
-                int n_tiles) {
+                int n_tiles, uint4* __restrict__ frag_scratch, const int* __restrict__ order) {
   using K = TcCfg<C>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem =
@@ -233,7 +240,8 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
   int* s_ctr = reinterpret_cast<int*>(s_tmem + 4);      // [4] query dispensers, indexed by pass sequence & 3
   float* sInv = reinterpret_cast<float*>(s_tmem + 8);  // [2][TQ]
-  float* sKp = sInv + 2 * K::TQ;                       // [45]
+  float* sKp = sInv + 2 * K::TQ;                       // [45] (48 reserved)
+  volatile int* sFlag = reinterpret_cast<volatile int*>(sKp + 48);  // [TQ] tile number whose influence fragments are cached
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
@@ -245,6 +253,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
     mbar_init(bar_done, 1);
     fence_mbar_init();
     for (int i = 0; i < 4; ++i) s_ctr[i] = 0;
+    for (int i = 0; i < K::TQ; ++i) sFlag[i] = 0;
   }
   if (warp == K::WORKERS) tmem_alloc(s_tmem, K::TMEM_COLS);
   for (int i = tid; i < KP * 3; i += K::THREADS) sKp[i] = kp[i];
@@ -281,7 +290,13 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
     struct Item {
       float4 pa, pb;   // packed support points of neighbours 2t, 2t+1: x, y, z, w = +-2^-e (sign = rowsum flag)
       uint4 xa, xb;    // their feature pieces: channels 4g..4g+3 as (hi, lo) fp16 pairs scaled by 2^e
+      int b;           // block index within the row
     };  // an absent neighbour has pa/pb = 0: w = 0 zeroes its influences
+    // Influence fragments depend on the geometry only: pass 0 of a tile stores them (one 16-byte vector per lane and
+    // block) in an L2-resident scratch, passes 1.. of the same tile reload them instead of re-evaluating 4 influences
+    // and re-fetching two packed points per block.  sFlag[ql] publishes "fragments of query ql are written".
+    const int nb_max = (H + 7) >> 3;
+    uint4* frag = frag_scratch + (size_t)blockIdx.x * K::TQ * nb_max * 32;
     // Epilogue of a finished tile: D (TMEM) -> registers, add the hi/lo rows (adjacent lanes) and the two column
     // halves, scale, store.  Run DEFERRED: a warp executes it for tile t-1 just before its first A-tile store of
     // tile t, when the MMAs of tile t-1 have long completed, so no producer ever idles on the tensor pipe.
@@ -290,8 +305,8 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
       if (warp < 16) {  // 4 TMEM lane quadrants x 4 column groups
         const int qd = warp & 3, cg = warp >> 2;
         const int ql = qd * 16 + (lane >> 1);
-        const int n = q0 + ql;
         const bool ok = ql < cnt;
+        const int n = ok ? (order ? __ldg(order + q0 + ql) : q0 + ql) : 0;
         const float scale = ok ? inv_buf[ql] * o_scale : 0.f;
         const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16);
 #pragma unroll 1
@@ -342,12 +357,15 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
           float qx, qy, qz;     // query point, issue side
           float qnx = 0.f, qny = 0.f, qnz = 0.f;
           unsigned bm;          // blocks of the row still to issue
+          int ql_iss = ql;      // query whose row is being issued
           bool row_pending = false, new_query = true;
           float d[4][4];
           float fcount = 0.f;
           float cqx, cqy, cqz;  // query point of the item being multiplied
           auto issue_row = [&](int qq) {
-            const int n = q0 + qq;
+            // `order` (optional) walks the queries in cell order: the queries in flight on an SM are spatial
+            // neighbours, so their neighbourhoods overlap and the gathers hit L1 / L2
+            const int n = order ? __ldg(order + q0 + qq) : q0 + qq;
 #pragma unroll
             for (int i = 0; i < HR; ++i) {
               const int h = 32 * i + lane;
@@ -380,6 +398,10 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
             qx = qnx;
             qy = qny;
             qz = qnz;
+            if (K::PASSES > 1 && pass > 0) {
+              while (sFlag[ql_iss] != titer + 1) {
+              }
+            }
           };
           auto issue_item = [&](Item& it) {
             const int b = __ffs(bm) - 1;
@@ -392,10 +414,16 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
             const int ja = __shfl_sync(kFull, jsel, src);
             const int jb = __shfl_sync(kFull, jsel, src + 1);
             const size_t ra = ja >= 0 ? (size_t)ja : 0, rb = jb >= 0 ? (size_t)jb : 0;
+            it.b = b;
             it.pa = make_float4(0.f, 0.f, 0.f, 0.f);
             it.pb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ja >= 0) it.pa = __ldg(pts4 + ra);
-            if (jb >= 0) it.pb = __ldg(pts4 + rb);
+            if (K::PASSES > 1 && pass > 0) {
+              const uint4 f = __ldcg(frag + ((size_t)ql_iss * nb_max + b) * 32 + lane);
+              it.pa = make_float4(__uint_as_float(f.x), __uint_as_float(f.y), __uint_as_float(f.z), __uint_as_float(f.w));
+            } else {
+              if (ja >= 0) it.pa = __ldg(pts4 + ra);
+              if (jb >= 0) it.pb = __ldg(pts4 + rb);
+            }
             it.xa = __ldg(reinterpret_cast<const uint4*>(xcol + ra * C));
             it.xb = __ldg(reinterpret_cast<const uint4*>(xcol + rb * C));
           };
@@ -416,24 +444,37 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
             if (!last) {
               issue_item(nxt);
             } else if (row_pending) {
+              ql_iss = ql_next;
               consume_row();
               issue_item(nxt);
             }
             {
-              const float ax = cur.pa.x - cqx, ay = cur.pa.y - cqy, az = cur.pa.z - cqz;
-              const float bx = cur.pb.x - cqx, by = cur.pb.y - cqy, bz = cur.pb.z - cqz;
-              const float sa = fabsf(cur.pa.w) * a_scale;
-              const float sb = fabsf(cur.pb.w) * a_scale;
-              if (pass == 0) fcount += (cur.pa.w > 0.f ? 1.f : 0.f) + (cur.pb.w > 0.f ? 1.f : 0.f);
-              // A fragment: a0 = (k = g; h = 2t, 2t+1), a1 = (k = g+8; h = 2t, 2t+1), fp16 hi + lo
-              const float f00 = influence_fast(ax, ay, az, k0x, k0y, k0z, inv_extent) * sa;
-              const float f01 = influence_fast(bx, by, bz, k0x, k0y, k0z, inv_extent) * sb;
-              const float f10 = influence_fast(ax, ay, az, k1x, k1y, k1z, inv_extent) * (sa * k1_on);
-              const float f11 = influence_fast(bx, by, bz, k1x, k1y, k1z, inv_extent) * (sb * k1_on);
-              const __half2 h0 = __floats2half2_rn(f00, f01), h1 = __floats2half2_rn(f10, f11);
-              const float2 h0f = __half22float2(h0), h1f = __half22float2(h1);
-              const __half2 l0 = __floats2half2_rn(f00 - h0f.x, f01 - h0f.y), l1 = __floats2half2_rn(f10 - h1f.x, f11 - h1f.y);
-              const uint32_t ah0 = h2_bits(h0), ah1 = h2_bits(h1), al0 = h2_bits(l0), al1 = h2_bits(l1);
+              uint32_t ah0, ah1, al0, al1;
+              if (K::PASSES > 1 && pass > 0) {
+                ah0 = __float_as_uint(cur.pa.x);
+                ah1 = __float_as_uint(cur.pa.y);
+                al0 = __float_as_uint(cur.pa.z);
+                al1 = __float_as_uint(cur.pa.w);
+              } else {
+                const float ax = cur.pa.x - cqx, ay = cur.pa.y - cqy, az = cur.pa.z - cqz;
+                const float bx = cur.pb.x - cqx, by = cur.pb.y - cqy, bz = cur.pb.z - cqz;
+                const float sa = fabsf(cur.pa.w) * a_scale;
+                const float sb = fabsf(cur.pb.w) * a_scale;
+                fcount += (cur.pa.w > 0.f ? 1.f : 0.f) + (cur.pb.w > 0.f ? 1.f : 0.f);
+                // A fragment: a0 = (k = g; h = 2t, 2t+1), a1 = (k = g+8; h = 2t, 2t+1), fp16 hi + lo
+                const float f00 = influence_fast(ax, ay, az, k0x, k0y, k0z, inv_extent) * sa;
+                const float f01 = influence_fast(bx, by, bz, k0x, k0y, k0z, inv_extent) * sb;
+                const float f10 = influence_fast(ax, ay, az, k1x, k1y, k1z, inv_extent) * (sa * k1_on);
+                const float f11 = influence_fast(bx, by, bz, k1x, k1y, k1z, inv_extent) * (sb * k1_on);
+                const __half2 h0 = __floats2half2_rn(f00, f01), h1 = __floats2half2_rn(f10, f11);
+                const float2 h0f = __half22float2(h0), h1f = __half22float2(h1);
+                const __half2 l0 = __floats2half2_rn(f00 - h0f.x, f01 - h0f.y), l1 = __floats2half2_rn(f10 - h1f.x, f11 - h1f.y);
+                ah0 = h2_bits(h0);
+                ah1 = h2_bits(h1);
+                al0 = h2_bits(l0);
+                al1 = h2_bits(l1);
+                if (K::PASSES > 1) frag[((size_t)ql * nb_max + cur.b) * 32 + lane] = make_uint4(ah0, ah1, al0, al1);
+              }
               const uint32_t xa[4] = {cur.xa.x, cur.xa.y, cur.xa.z, cur.xa.w};
               const uint32_t xb[4] = {cur.xb.x, cur.xb.y, cur.xb.z, cur.xb.w};
               // B fragment of channel tile i: (h = 2t, 2t+1; channel 4g+i).  Product-major order: consecutive
@@ -480,6 +521,11 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
               const uint32_t j = (k & 1) * 4 + t;
               *reinterpret_cast<uint4*>(atom + sw128_offset(r0, j)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<uint4*>(atom + sw128_offset(r1, j)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            if (K::PASSES > 1 && pass == 0) {
+              __threadfence_block();   // this lane's fragment stores before the flag
+              __syncwarp();
+              if (lane == 0) sFlag[ql] = titer + 1;
             }
             if (pass == 0) {
               // a neighbour is replicated over g: count the g == 0 copies (lanes 0..3)
@@ -607,8 +653,10 @@ int prepare_weights(const float* w, unsigned char* img, unsigned int* amax_w_bit
 template <int C, typename IdxT>
 int launch_main(const float* q, const void* idx, int row_stride, int H, const uint32_t* x16, const unsigned char* img,
                 const float* kp, const float4* pts4, const unsigned int* amax_x_bits, const unsigned int* amax_w_bits,
-                float extent, float* out, int nq, int ns, cudaStream_t stream) {
+                float extent, float* out, int nq, int ns, void* scratch, const int* order, cudaStream_t stream) {
   using K = TcCfg<C>;
+  SPR_CHECK_ARG(K::PASSES == 1 || scratch, "kpconv_forward(mode 1): scratch buffer missing");
+  uint4* frag = static_cast<uint4*>(scratch);
   SPR_CHECK_ARG(H <= 96, "kpconv_forward(mode 1): at most 96 neighbour columns are supported (got %d)", H);
   // Tile size: the largest tq <= 64 that deals every SM the same number of tiles (a tile is the M extent of
   // one MMA; short tiles only leave MMA rows unused, which costs nothing on the critical path).
@@ -632,15 +680,15 @@ int launch_main(const float* q, const void* idx, int row_stride, int H, const ui
   if (H <= 32)
     k_kpconv_tc<C, IdxT, 1><<<grid, K::THREADS, K::SMEM, stream>>>(q, s_unused, idx_t, row_stride, H, x16, img, kp, pts4,
                                                                    amax_x_bits, amax_w_bits, extent, out, nq, ns, tq,
-                                                                   n_tiles);
+                                                                   n_tiles, frag, order);
   else if (H <= 64)
     k_kpconv_tc<C, IdxT, 2><<<grid, K::THREADS, K::SMEM, stream>>>(q, s_unused, idx_t, row_stride, H, x16, img, kp, pts4,
                                                                    amax_x_bits, amax_w_bits, extent, out, nq, ns, tq,
-                                                                   n_tiles);
+                                                                   n_tiles, frag, order);
   else
     k_kpconv_tc<C, IdxT, 3><<<grid, K::THREADS, K::SMEM, stream>>>(q, s_unused, idx_t, row_stride, H, x16, img, kp, pts4,
                                                                    amax_x_bits, amax_w_bits, extent, out, nq, ns, tq,
-                                                                   n_tiles);
+                                                                   n_tiles, frag, order);
   SPR_LAUNCH_CHECK("k_kpconv_tc");
   return SPR_OK;
 }
@@ -654,6 +702,7 @@ int launch_tc(const float* q, const float* s, const void* idx, int row_stride, i
   float4* pts4 = cv.take<float4>((size_t)ns);
   uint32_t* x16 = cv.take<uint32_t>((size_t)ns * C);
   unsigned char* img = cv.take<unsigned char>(K::IMG_BYTES);
+  void* scratch = cv.take<unsigned char>(spr_kpconv_scratch_bytes(H, C));
 
   SPR_CUDA(cudaMemsetAsync(sc, 0, sizeof(TcScales), stream));
   constexpr int rows_per_block = 8 * (C / 4 < 32 ? 32 / (C / 4) : 1);
@@ -665,12 +714,13 @@ int launch_tc(const float* q, const float* s, const void* idx, int row_stride, i
   k_weight_image<C><<<(chunks + 255) / 256, 256, 0, stream>>>(w, &sc->amax_w_bits, img);
   SPR_LAUNCH_CHECK("k_weight_image");
   return launch_main<C, IdxT>(q, idx, row_stride, H, x16, img, kp, pts4, &sc->amax_x_bits, &sc->amax_w_bits, extent, out,
-                              nq, ns, stream);
+                              nq, ns, scratch, nullptr, stream);
 }
 
 template <int C>
 size_t tc_ws(int ns) {
-  return 256 + align_up((size_t)ns * 16, 256) + align_up((size_t)ns * C * 4, 256) + 256 + TcCfg<C>::IMG_BYTES + 256;
+  return 256 + align_up((size_t)ns * 16, 256) + align_up((size_t)ns * C * 4, 256) + 256 + TcCfg<C>::IMG_BYTES + 256 +
+         spr_kpconv_scratch_bytes(96, C) + 256;
 }
 
 }  // namespace
@@ -736,7 +786,8 @@ extern "C" int spr_kpconv_prepare_weights(const float* d_w, int c, void* d_img, 
 extern "C" int spr_kpconv_forward_prepared(const float* d_q, const void* d_idx, int idx_is_64, int row_stride, int H,
                                            const void* d_pts4, const void* d_x16, const void* d_amax_x, int c,
                                            const void* d_wimg, const void* d_amax_w, const float* d_kp, float extent,
-                                           float* d_out, int nq, int ns, void* stream_) {
+                                           float* d_out, int nq, int ns, void* d_scratch, const int32_t* d_order,
+                                           void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SPR_CHECK_ARG(nq > 0 && ns > 0 && H > 0 && row_stride >= H, "kpconv_forward_prepared: bad shape");
   SPR_CHECK_ARG(extent > 0.f, "kpconv_forward_prepared: extent must be > 0");
@@ -750,9 +801,9 @@ extern "C" int spr_kpconv_forward_prepared(const float* d_q, const void* d_idx, 
 #define SPR_TCP(CC)                                                                                                  \
   case CC:                                                                                                           \
     return idx_is_64 ? launch_main<CC, long long>(d_q, d_idx, row_stride, H, x16, img, d_kp, pts4, ax, aw, extent, d_out, \
-                                                  nq, ns, stream)                                                    \
+                                                  nq, ns, d_scratch, d_order, stream)                                \
                      : launch_main<CC, int>(d_q, d_idx, row_stride, H, x16, img, d_kp, pts4, ax, aw, extent, d_out, nq, \
-                                            ns, stream);
+                                            ns, d_scratch, d_order, stream);
   switch (c) {
     SPR_TCP(32)
     SPR_TCP(64)

@@ -369,6 +369,26 @@ GridLayout carve_grid(void* ws, size_t ws_bytes, int ns, int B) {
 }
 }  // namespace
 
+namespace spr {
+namespace {
+__global__ void __launch_bounds__(256) k_grid_order(const float4* __restrict__ sorted, int n, int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float_as_int(sorted[i].w);
+}
+}  // namespace
+}  // namespace spr
+
+// order[i] = index of the i-th support in (cloud, z, y, x) cell order: a spatially coherent traversal of the cloud
+extern "C" int spr_cell_grid_order(const void* d_grid_workspace, int n_supports, int n_clouds, int32_t* d_order,
+                                   void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPR_CHECK_ARG(d_grid_workspace && d_order && n_supports > 0 && n_clouds > 0, "cell_grid_order: bad arguments");
+  GridLayout L = carve_grid(const_cast<void*>(d_grid_workspace), (size_t)-1, n_supports, n_clouds);
+  k_grid_order<<<(n_supports + 255) / 256, 256, 0, stream>>>(L.sorted, n_supports, d_order);
+  SPR_LAUNCH_CHECK("k_grid_order");
+  return SPR_OK;
+}
+
 extern "C" size_t spr_cell_grid_workspace_bytes(int n_supports, int n_clouds) {
   if (n_supports < 0 || n_clouds < 0) return 0;
   GridLayout L = carve_grid(nullptr, 0, n_supports, n_clouds);

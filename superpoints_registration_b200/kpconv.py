@@ -112,6 +112,7 @@ class Preprocessor(nn.Module):
         r = float(cfg.first_subsampling_dl) * float(cfg.conv_radius)
 
         out_points, out_neighbors, out_pools, out_ups, out_lens = [], [], [], [], []
+        out_order = []  # per level: the points in cell order (private: processing order of the KPConv kernels)
         widths = []  # (list, position, max_count tensor)
         grid = ops.CellGrid(points, lengths, r)
         empty_idx = lambda: torch.zeros((0, 1), dtype=torch.int64, device=device)
@@ -136,6 +137,7 @@ class Preprocessor(nn.Module):
                 pool_b = torch.zeros((0,), dtype=torch.int64, device=device)
                 next_grid = None
             out_points.append(points)
+            out_order.append(grid.order() if grid is not None else None)
             out_neighbors.append(conv_i)
             out_pools.append(pool_i)
             out_ups.append(up_i)
@@ -149,7 +151,7 @@ class Preprocessor(nn.Module):
                 w = min(int(mc), limit)
                 lst[li] = lst[li][:, :w]
         return {"points": out_points, "neighbors": out_neighbors, "pools": out_pools, "upsamples": out_ups,
-                "stack_lengths": out_lens}
+                "stack_lengths": out_lens, "_order": out_order}
 
 
 # ------------------------------------------------------------------------------------------------

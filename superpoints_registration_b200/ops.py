@@ -94,6 +94,13 @@ class CellGrid:
                                    self.ws.data_ptr(), self.ws.numel(), _stream())
         _lib.check(rc, "spr_cell_grid_build")
 
+    def order(self) -> torch.Tensor:
+        """int32 [ns]: the supports in (cloud, z, y, x) cell order (a spatially coherent permutation)."""
+        out = torch.empty(self.ns, dtype=torch.int32, device=self.supports.device)
+        rc = _lib.lib().spr_cell_grid_order(self.ws.data_ptr(), self.ns, self.b, out.data_ptr(), _stream())
+        _lib.check(rc, "spr_cell_grid_order")
+        return out
+
     def query(self, queries: torch.Tensor, q_lengths: torch.Tensor, limit: int, radius: Optional[float] = None,
               index_dtype: torch.dtype = torch.int64) -> Tuple[torch.Tensor, torch.Tensor]:
         """-> (idx [Nq, limit] index_dtype, max_count i32[1] on device)."""
@@ -247,20 +254,27 @@ def kpconv_weight_image(weights: torch.Tensor) -> KPConvWeightImage:
     return wi
 
 
-def kpconv_forward_prepared(q_pts, neighb_inds, feats: PreparedFeatures, weights, kernel_points, extent: float):
-    """KPConv on the tensor-core path from inputs prepared by instance_norm_lrelu_ex (no pre-pass kernels)."""
+def kpconv_forward_prepared(q_pts, neighb_inds, feats: PreparedFeatures, weights, kernel_points, extent: float,
+                            order=None):
+    """KPConv on the tensor-core path from inputs prepared by instance_norm_lrelu_ex (no pre-pass kernels).
+    order: optional int32 permutation of the queries (CellGrid.order()) = processing order."""
     L = _lib.lib()
     q = _f32c(q_pts, "q_pts")
     kp = _f32c(kernel_points, "kernel_points")
     idx, is64, stride, H = _idx_arg(neighb_inds)
     nq, ns = q.shape[0], feats.x16.shape[0]
+    if order is not None and (order.dtype != torch.int32 or order.shape[0] != nq or not order.is_cuda):
+        raise RuntimeError("kpconv_forward_prepared: order must be an int32 CUDA tensor with one entry per query")
     wi = kpconv_weight_image(weights)
     if wi.c != feats.c:
         raise RuntimeError("kpconv_forward_prepared: channel mismatch between features and weights")
     out = torch.empty((nq, feats.c), dtype=torch.float32, device=q.device)
+    sb = L.spr_kpconv_scratch_bytes(H, feats.c)
+    scratch = _ws(sb, q.device) if sb else None
     rc = L.spr_kpconv_forward_prepared(q.data_ptr(), idx.data_ptr(), is64, stride, H, feats.pts4.data_ptr(),
                                        feats.x16.data_ptr(), feats.amax.data_ptr(), feats.c, wi.img.data_ptr(),
-                                       wi.amax.data_ptr(), kp.data_ptr(), float(extent), out.data_ptr(), nq, ns, _stream())
+                                       wi.amax.data_ptr(), kp.data_ptr(), float(extent), out.data_ptr(), nq, ns,
+                                       _ptr(scratch), _ptr(order), _stream())
     _lib.check(rc, "spr_kpconv_forward_prepared")
     return out
 

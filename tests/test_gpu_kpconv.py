@@ -223,6 +223,37 @@ def test_format_aware_instance_norm_outputs_feed_gemm_and_kpconv():
         <= 1e-6 * 10
 
 
+@pytest.mark.parametrize("c", [32, 128])
+def test_cell_order_is_a_permutation_and_does_not_change_kpconv(c):
+    """CellGrid.order() lists every support once, cloud by cloud, in cell order; used as the KPConv processing order
+    it must leave every output row bit-identical (the per-query arithmetic does not depend on the tile it runs in)."""
+    rng = np.random.default_rng(5 + c)
+    lens = np.array([700, 0, 311, 90], dtype=np.int32)
+    n = int(lens.sum())
+    pts = rng.uniform(0, 1, size=(n, 3)).astype(np.float32)
+    grid = ops.CellGrid(_t(pts), _t(lens), 0.12)
+    order = grid.order()
+    o = order.cpu().numpy()
+    assert np.array_equal(np.sort(o), np.arange(n))
+    starts = np.concatenate([[0], np.cumsum(lens)])
+    for b in range(len(lens)):                                   # clouds stay contiguous
+        seg = o[starts[b]:starts[b + 1]]
+        assert seg.size == 0 or (seg.min() >= starts[b] and seg.max() < starts[b + 1])
+    big = slice(starts[0], starts[1])                            # spatially coherent: consecutive points are close
+    step = np.linalg.norm(np.diff(pts[o[big]], axis=0), axis=1).mean()
+    assert step < 0.5 * np.linalg.norm(np.diff(pts[big], axis=0), axis=1).mean()
+    idx, _ = grid.query(_t(pts), _t(lens), 24)
+    x = rng.normal(size=(n, c)).astype(np.float32)
+    prep = ops.instance_norm_lrelu_ex(_t(x), _t(lens), slope=0.1, kpconv_points=_t(pts))["kpconv"]
+    wk = (rng.normal(size=(15, c, c)) / np.sqrt(15 * c)).astype(np.float32)
+    kp = (rng.normal(size=(15, 3)) * 0.05).astype(np.float32)
+    a = ops.kpconv_forward_prepared(_t(pts), idx, prep, _t(wk), _t(kp), 0.1)
+    b = ops.kpconv_forward_prepared(_t(pts), idx, prep, _t(wk), _t(kp), 0.1, order=order)
+    assert torch.equal(a, b)
+    with pytest.raises(RuntimeError):
+        ops.kpconv_forward_prepared(_t(pts), idx, prep, _t(wk), _t(kp), 0.1, order=order[:-1])
+
+
 @pytest.mark.parametrize("cout", [32, 64, 128, 256])
 def test_kpconv_stem_cin1_against_oracle(cout):
     """First encoder block (Cin = 1): every supported output width, more than 64 neighbour columns, shadow entries."""

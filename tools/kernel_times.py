@@ -40,3 +40,30 @@ tot = sum(r[1] for r in rows)
 print(f"total device time per forward: {tot / 1e3:.3f} ms over {sum(r[2] for r in rows):.0f} kernels")
 for k, t, c in rows[:args.top]:
     print(f"{t / 1e3:8.3f} ms {100 * t / tot:5.1f}%  n={c:5.0f}  {k[:100]}")
+
+# ---- per-launch detail of the normalisation kernels against their byte counts (HBM-bound by design) ----
+if os.environ.get("SPR_IN_DETAIL"):
+    from superpoints_registration_b200 import ops
+    calls = []
+    raw = ops.instance_norm_lrelu_ex
+
+    def rec(x, lengths, *a, **kw):
+        out = raw(x, lengths, *a, **kw)
+        calls.append((x.shape[0], x.shape[1], kw.get("residual") is not None, out.get("f32") is not None,
+                      out.get("image") is not None, out.get("kpconv") is not None))
+        return out
+
+    ops.instance_norm_lrelu_ex = rec
+    import superpoints_registration_b200.kpconv_blocks as kb
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        model(dict(batch))
+        torch.cuda.synchronize()
+    ev = sorted([e for e in prof.events() if e.device_type.name == "CUDA"], key=lambda e: e.time_range.start)
+    part = [e.device_time for e in ev if "k_in_partial" in e.name]
+    appl = [e.device_time for e in ev if "k_in_apply_ex" in e.name]
+    print(f"{len(calls)} instance-norm calls, {len(part)} partial, {len(appl)} apply launches")
+    for (n, c, res, f32, img, kp), tp, ta in zip(calls, part, appl):
+        rd = n * c * 4 * (2 if res else 1)
+        wr = n * c * 4 * (int(f32) + int(img) + int(kp)) + (n * 16 if kp else 0)
+        print(f"n={n:7d} c={c:4d} res={int(res)} f32={int(f32)} img={int(img)} kp={int(kp)}  partial {tp:6.1f} us "
+              f"{n * c * 4 / tp / 1e3:7.0f} GB/s   apply {ta:6.1f} us {(rd + wr) / ta / 1e3:7.0f} GB/s")

@@ -197,6 +197,33 @@ SPR_API int spr_gather_rows3(const float* d_src, const int64_t* d_ind, const int
                      void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Optional correspondence refinements of RegTR.softmax_correlation (use_ratio_test / use_lgr / use_ransac; all off in
+ * the shipped configs).  Pairs are packed back to back like everywhere else.
+ *
+ * spr_top2_ratio       RegTR.ratio_test, qk_regtr_full.py:370-384: per output element (one per target when
+ *                      N_p > M_p, one per source otherwise) the two largest attention values v1 >= v2 over the other
+ *                      axis; val = v1 if v2/v1 < lowe_thres else 0; ind = position of v1.  d_attn is the packed
+ *                      attention written by spr_dual_softmax_match.  The reduced axis needs >= 2 entries (torch.topk
+ *                      raises otherwise; the host mirror checks).
+ * spr_inlier_reweight  RegTR.recompute_weights, :386-391: w_out = w * (|b - (R a + t)| < acceptance_radius), the pose
+ *                      of each row's pair taken from d_poses [n_pairs, 12].  local_global_registration (:393-398)
+ *                      alternates it with spr_weighted_procrustes num_refinement_steps times.
+ * spr_select_hypothesis RegTR.ransac, :400-421, after the hypotheses are solved (spr_weighted_procrustes over the
+ *                      sampled rows): d_loss[p, h] = mean_r |b_r - T_{p,h} a_r| over all rows of pair p, d_out[p] =
+ *                      the first hypothesis with a strictly smaller loss than all before it, d_best[p] (optional)
+ *                      its number.  d_poses is [n_pairs, n_hypotheses, 12].
+ * ------------------------------------------------------------------------------------------- */
+SPR_API int spr_top2_ratio(const float* d_attn, const int64_t* d_corr_offsets, const int32_t* d_src_offsets,
+                           const int32_t* d_tgt_offsets, const int32_t* d_out_offsets, int n_pairs, int total_out,
+                           float lowe_thres, float* d_val, int64_t* d_ind, void* stream);
+SPR_API int spr_inlier_reweight(const float* d_a, const float* d_b, const float* d_w, const float* d_poses,
+                                const int32_t* d_offsets, int n_pairs, int total, float acceptance_radius,
+                                float* d_w_out, void* stream);
+SPR_API int spr_select_hypothesis(const float* d_a, const float* d_b, const int32_t* d_offsets, int n_pairs,
+                                  const float* d_poses, int n_hypotheses, float* d_loss, float* d_out, int32_t* d_best,
+                                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Cross-encoder building blocks (reference: models/transformer/transformers.py:18-259, nn.MultiheadAttention
  * with d_model 256 / 8 heads).  Tokens of all clouds are PACKED ([total_tokens, d]); the reference pads every
  * cloud to the longest one and masks (utils/seq_manipulation.py:6-48).

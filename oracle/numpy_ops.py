@@ -128,6 +128,46 @@ def compute_rigid_transform(a, b, weights=None, dtype=np.float32):
     return np.concatenate([rot, t[:, None]], 1).astype(np.float32)
 
 
+def ratio_test(attn, axis: int, lowe_thres: float):
+    """RegTR.ratio_test (models/qk_regtr_full.py:370-384): the largest value along `axis` where second/first is below
+    the threshold, else 0, and the position of the largest."""
+    order = np.argsort(-attn, axis=axis, kind="stable")
+    first = np.take(order, 0, axis=axis)
+    top = np.take_along_axis(attn, order, axis=axis)
+    v1, v2 = np.take(top, 0, axis=axis), np.take(top, 1, axis=axis)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        keep = (v2 / v1) < lowe_thres
+    return np.where(keep, v1, 0).astype(attn.dtype), first
+
+
+def recompute_weights(src, tgt, weights, pose, acceptance_radius: float, dtype=np.float32):
+    """RegTR.recompute_weights (:386-391)."""
+    src, tgt, pose = src.astype(dtype), tgt.astype(dtype), pose.astype(dtype)
+    res = np.linalg.norm(tgt - (src @ pose[:, :3].T + pose[:, 3]), axis=1)
+    return weights.astype(dtype) * (res < acceptance_radius)
+
+
+def local_global_registration(src, tgt, weights, pose, acceptance_radius: float, steps: int, dtype=np.float32):
+    """RegTR.local_global_registration (:393-398)."""
+    for _ in range(steps):
+        weights = recompute_weights(src, tgt, weights, pose, acceptance_radius, dtype)
+        pose = compute_rigid_transform(src, tgt, weights, dtype=dtype)
+    return pose
+
+
+def ransac(src, tgt, weights, sample_idx, dtype=np.float32):
+    """RegTR.ransac (:400-421) with the index draws given (sample_idx [hypotheses, sample_size]); the reference draws
+    them from the CUDA generator, so only this restatement can be compared number for number."""
+    best, best_loss, losses = None, None, []
+    for idx in sample_idx:
+        T = compute_rigid_transform(src[idx], tgt[idx], weights[idx], dtype=dtype)
+        loss = np.linalg.norm(tgt.astype(dtype) - (src.astype(dtype) @ T[:, :3].T + T[:, 3]), axis=1).mean()
+        losses.append(loss)
+        if best is None or loss < best_loss:
+            best, best_loss = T, loss
+    return best, np.asarray(losses)
+
+
 def pose_error(pred, gt) -> Tuple[float, float]:
     """Chordal rotation error (deg) and translation error in fp64 -- see SURVEY.md row a13 for why this is used
     instead of the reference's se3_compare."""

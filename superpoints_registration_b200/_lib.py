@@ -50,6 +50,9 @@ _SIGNATURES = {
                                               c_float, c_int, c_int, c_fp, c_fp, c_fp, c_size_t, c_void_p]),
     "spr_weighted_procrustes": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_void_p]),
     "spr_gather_rows3": (c_int, [c_fp, c_fp, c_fp, c_int, c_fp, c_void_p]),
+    "spr_top2_ratio": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_float, c_fp, c_fp, c_void_p]),
+    "spr_inlier_reweight": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_float, c_fp, c_void_p]),
+    "spr_select_hypothesis": (c_int, [c_fp, c_fp, c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_fp, c_void_p]),
     "spr_split_f16": (c_int, [c_fp, c_int, c_int, c_int, c_fp, c_fp, c_int, c_int, c_float, c_void_p]),
     "spr_attention_varlen": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp, c_int, c_fp, c_int,
                                      c_fp, c_float, c_void_p]),

@@ -46,7 +46,7 @@ def _base(**kw) -> Config:
         # model
         remove_points_from_val=False, threshold_corr=False, remove_outliers_overlap=False, use_overlap_as_weights=False,
         use_ratio_test=False, use_sinkhorn=False, sinkhorn_itr=1, slack=False, use_attn_affinity=False,
-        use_corr_affinity=False, use_lgr=False, use_ransac=False,
+        use_corr_affinity=False, use_lgr=False, use_ransac=False, lowe_thres=0.9,
         attention_type="dot_prod", nhead=8, d_embed=256, d_feedforward=1024, dropout=0.0, pre_norm=True,
         transformer_act="relu", num_encoder_layers=6, transformer_encoder_has_pos_emb=True, sa_val_has_pos_emb=True,
         ca_val_has_pos_emb=True, pos_emb_type="sine",
@@ -62,7 +62,8 @@ def threedmatch_config(**overrides) -> Config:
         conv_radius=2.5, num_layers=4,
         architecture=["simple", "resnetb", "resnetb_strided", "resnetb", "resnetb", "resnetb_strided", "resnetb",
                       "resnetb"],
-        use_sinkhorn=True, sinkhorn_itr=3, slack=True)
+        use_sinkhorn=True, sinkhorn_itr=3, slack=True,
+        num_refinement_steps=4, acceptance_radius=0.1, val_threshold=0.15)
     cfg.update(overrides)
     return cfg
 
@@ -83,7 +84,7 @@ def kitti_config(**overrides) -> Config:
         conv_radius=4.25, num_layers=4,
         architecture=["simple", "resnetb", "resnetb_strided", "resnetb", "resnetb", "resnetb_strided", "resnetb",
                       "resnetb", "resnetb_strided", "resnetb", "resnetb"],
-        use_sinkhorn=False)
+        use_sinkhorn=False, num_refinement_steps=10, acceptance_radius=0.6, val_threshold=0.25)
     cfg.update(overrides)
     return cfg
 
@@ -94,6 +95,6 @@ def modelnet_config(**overrides) -> Config:
         dataset="modelnet", neighborhood_limits=[50, 50], first_subsampling_dl=0.03, first_feats_dim=512,
         conv_radius=2.75, num_layers=2,
         architecture=["simple", "resnetb", "resnetb", "resnetb_strided", "resnetb", "resnetb"],
-        use_sinkhorn=False, sinkhorn_itr=1, slack=False)
+        use_sinkhorn=False, sinkhorn_itr=1, slack=False, num_refinement_steps=5, acceptance_radius=0.05)
     cfg.update(overrides)
     return cfg

@@ -27,8 +27,9 @@ import torch.nn.functional as F
 from . import ops
 from .kpconv import KPFEncoder, Preprocessor
 
-_UNSUPPORTED_FLAGS = ("use_ratio_test", "threshold_corr", "remove_outliers_overlap", "remove_points_from_val",
-                      "use_lgr", "use_ransac", "use_attn_affinity", "use_corr_affinity", "use_overlap_as_weights")
+# use_attn_affinity raises ValueError inside the reference itself (qk_regtr_full.py:509-513,619-623) and
+# use_corr_affinity is shape-inconsistent there for N > M (:516-519); neither is reproduced.
+_UNSUPPORTED_FLAGS = ("use_attn_affinity", "use_corr_affinity")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -235,7 +236,16 @@ class RegTR(nn.Module):
         self.cfg = cfg
         for flag in _UNSUPPORTED_FLAGS:
             if cfg.get(flag, False):
-                raise NotImplementedError(f"{flag}=True: optional refinement, off in every shipped configuration")
+                raise NotImplementedError(f"{flag}=True: not usable in the reference either")
+        if cfg.get('use_sinkhorn', False) and (cfg.get('use_lgr', False) or cfg.get('use_ransac', False)):
+            # the reference hands all N source and all M target points to the refinement (:538-542), which only
+            # type-checks when N == M
+            raise NotImplementedError("use_lgr / use_ransac need one-to-one correspondences: not with use_sinkhorn")
+        if cfg.get('use_overlap_as_weights', False) and not cfg.get('remove_outliers_overlap', False):
+            raise NotImplementedError("use_overlap_as_weights needs remove_outliers_overlap (overlap_prob, :481-487)")
+        if cfg.get('use_overlap_as_weights', False) and cfg.get('remove_points_from_val', False):
+            raise NotImplementedError("use_overlap_as_weights with remove_points_from_val: weights and points differ "
+                                      "in length in the reference (:497-500, :546)")
         self.preprocessor = Preprocessor(cfg)
         self.kpf_encoder = KPFEncoder(cfg, cfg.d_embed)
         self.feat_proj = nn.Linear(self.kpf_encoder.encoder_skip_dims[-1], cfg.d_embed, bias=True)
@@ -253,6 +263,9 @@ class RegTR(nn.Module):
         self.overlap_predictor = nn.Linear(cfg.d_embed, 1)
         self.dual_normalization = True  # hard-coded in the reference (:120)
         self.return_attn = True          # outputs['attn'] (:295); set False to skip materialising N x M matrices
+        # RegTR.ransac draws 500 x 100 rows from the global CUDA generator (:402-405); pass a torch.Generator to
+        # make a run reproducible
+        self.ransac_hypotheses, self.ransac_sample_size, self.ransac_generator = 500, 100, None
         self.packed_transformer = True   # packed tokens + our attention kernel; False = padded PyTorch modules
 
     def load_reference_state_dict(self, state_dict):
@@ -314,8 +327,11 @@ class RegTR(nn.Module):
             # packed (sum N, D) features in pair order for the batched matching kernels
             src_packed = src_cond[0].transpose(0, 1)[~src_mask]
             tgt_packed = tgt_cond[0].transpose(0, 1)[~tgt_mask]
+        overlap_packed = None
+        if cfg.get('remove_outliers_overlap', False):
+            overlap_packed = torch.cat([o.reshape(-1) for o in list(src_overlap_list) + list(tgt_overlap_list)])
         pose, attn_list, val_list, ind_list, src_pts_list, tgt_pts_list = self._match_and_solve(
-            src_packed, tgt_packed, pts_c, src_slens_c, tgt_slens_c)
+            src_packed, tgt_packed, pts_c, src_slens_c, tgt_slens_c, overlap_packed)
 
         return {
             'pose': pose, 'attn': attn_list, 'src_feat': src_cond_list, 'tgt_feat': tgt_cond_list,
@@ -332,7 +348,10 @@ class RegTR(nn.Module):
         src_packed = torch.cat([f.reshape(-1, f.shape[-1]) for f in src_feats], dim=0)
         tgt_packed = torch.cat([f.reshape(-1, f.shape[-1]) for f in tgt_feats], dim=0)
         pts = torch.cat(list(src_xyz) + list(tgt_xyz), dim=0)
-        return self._match_and_solve(src_packed, tgt_packed, pts, src_lens, tgt_lens)
+        overlap_packed = None
+        if self.cfg.get('remove_outliers_overlap', False):
+            overlap_packed = torch.cat([o.reshape(-1) for o in list(src_overlap_list) + list(tgt_overlap_list)])
+        return self._match_and_solve(src_packed, tgt_packed, pts, src_lens, tgt_lens, overlap_packed)
 
     def _affinity_scalars(self):
         """softplus(alpha), exp(beta) as host floats, cached per parameter version (one sync per weight load)."""
@@ -342,19 +361,45 @@ class RegTR(nn.Module):
             self._aff_key = key
         return self._aff_val
 
-    def _match_and_solve(self, src_packed, tgt_packed, pts_c, src_lens, tgt_lens):
+    def _match_and_solve(self, src_packed, tgt_packed, pts_c, src_lens, tgt_lens, overlap_packed=None):
         cfg = self.cfg
         dev = src_packed.device
         pairs = ops.PackedPairs(src_lens, tgt_lens, dev)
         total_src = pairs.total_src
         src_xyz_packed, tgt_xyz_packed = pts_c[:total_src], pts_c[total_src:]
-        corr, attn, val, ind = ops.dual_softmax_match(src_packed, tgt_packed, pairs, want_attn=self.return_attn)
-
+        ratio_test = bool(cfg.get('use_ratio_test', False))
+        corr, attn, val, ind = ops.dual_softmax_match(src_packed, tgt_packed, pairs,
+                                                      want_attn=self.return_attn or ratio_test)
         P = pairs.P
         attn_list = ([attn[pairs.h_co[p]:pairs.h_co[p + 1]].view(1, src_lens[p], tgt_lens[p]) for p in range(P)]
-                     if attn is not None else [None] * P)
-        val_list = [val[pairs.h_oo[p]:pairs.h_oo[p + 1]] for p in range(P)]
-        ind_list = [ind[pairs.h_oo[p]:pairs.h_oo[p + 1]] for p in range(P)]
+                     if attn is not None and self.return_attn else [None] * P)
+        if ratio_test:  # :465-466 / :573-574
+            val, ind = ops.top2_ratio(attn, pairs, float(cfg.lowe_thres))
+
+        offsets, h_off = pairs.oo, pairs.h_oo
+        need_rows = (not cfg.use_sinkhorn) or cfg.get('threshold_corr', False) or cfg.get('remove_outliers_overlap', False)
+        if need_rows:
+            # one row per correspondence: which pair it belongs to, which side the argmax indexes
+            rows_per_pair = torch.tensor([h_off[p + 1] - h_off[p] for p in range(P)], device=dev)
+            pair_of_row = torch.repeat_interleave(torch.arange(P, device=dev), rows_per_pair)
+            gather_from_src = torch.tensor([1 if n > m else 0 for n, m in zip(src_lens, tgt_lens)], device=dev)
+            from_src = gather_from_src[pair_of_row].bool()
+            base = torch.where(from_src, pairs.so[:-1][pair_of_row], pairs.to[:-1][pair_of_row] + total_src)
+            local = torch.arange(pairs.total_out, device=dev) - pairs.oo[:-1][pair_of_row]
+            other_base = torch.where(from_src, pairs.to[:-1][pair_of_row] + total_src, pairs.so[:-1][pair_of_row])
+        if cfg.get('threshold_corr', False):  # :471-473 / :579-581: keep values above the pair's (lower) median
+            val = torch.where(val > _segment_median(val, h_off, pair_of_row), val, torch.zeros_like(val))
+        weights = val
+        if cfg.get('remove_outliers_overlap', False):  # :481-492 / :596-607
+            if overlap_packed is None:
+                raise RuntimeError("remove_outliers_overlap needs the overlap predictions of both clouds")
+            ov = overlap_packed.reshape(-1).to(torch.float32)
+            overlap_prob = ov[(base + ind).long()] * ov[(other_base + local).long()]
+            if cfg.get('use_overlap_as_weights', False):
+                weights = overlap_prob  # :546 / :651; val stays the reported match weight
+            else:
+                val = val * overlap_prob
+                weights = val
 
         if cfg.use_sinkhorn:
             # :532-536 / :641-647 -- all source points against Sinkhorn-weighted targets
@@ -364,21 +409,52 @@ class RegTR(nn.Module):
             pose = ops.weighted_procrustes(src_xyz_packed, wt, w, pairs.so)
             src_pts_list = [src_xyz_packed[pairs.h_so[p]:pairs.h_so[p + 1]] for p in range(P)]
             tgt_pts_list = [tgt_xyz_packed[pairs.h_to[p]:pairs.h_to[p + 1]] for p in range(P)]
+            if cfg.get('remove_points_from_val', False):
+                raise NotImplementedError("remove_points_from_val with use_sinkhorn: the reference gathers both clouds "
+                                          "with one index list (:497-500), out of range whenever N != M")
         else:
             # :478,548 (N > M: one source per target) / :589,653 (one target per source)
-            gather_from_src = torch.tensor([1 if n > m else 0 for n, m in zip(src_lens, tgt_lens)], device=dev)
-            rows_per_pair = torch.tensor([pairs.h_oo[p + 1] - pairs.h_oo[p] for p in range(P)], device=dev)
-            pair_of_row = torch.repeat_interleave(torch.arange(P, device=dev), rows_per_pair)
-            from_src = gather_from_src[pair_of_row].bool()
-            base = torch.where(from_src, pairs.so[:-1][pair_of_row], pairs.to[:-1][pair_of_row] + total_src)
             picked = ops.gather_rows3(pts_c, ind, base.to(torch.int32))
             # the side that is NOT gathered is simply that pair's full cloud, in order
-            local = torch.arange(pairs.total_out, device=dev) - pairs.oo[:-1][pair_of_row]
-            other_base = torch.where(from_src, pairs.to[:-1][pair_of_row] + total_src, pairs.so[:-1][pair_of_row])
             other = pts_c[(other_base + local).long()]
             a = torch.where(from_src[:, None], picked, other)  # source-side points
             b = torch.where(from_src[:, None], other, picked)  # target-side points
-            pose = ops.weighted_procrustes(a, b, val, pairs.oo)
-            src_pts_list = [a[pairs.h_oo[p]:pairs.h_oo[p + 1]] for p in range(P)]
-            tgt_pts_list = [b[pairs.h_oo[p]:pairs.h_oo[p + 1]] for p in range(P)]
+            if cfg.get('remove_points_from_val', False):  # :497-500 / :612-615: keep the top int(thr * len) rows
+                keep, new_off = [], [0]
+                for p in range(P):
+                    k = int(float(cfg.val_threshold) * (h_off[p + 1] - h_off[p]))
+                    top = torch.topk(val[h_off[p]:h_off[p + 1]], k).indices
+                    keep.append(top + h_off[p])
+                    new_off.append(new_off[-1] + k)
+                keep = torch.cat(keep)
+                a, b, val = a[keep].contiguous(), b[keep].contiguous(), val[keep].contiguous()
+                ind = keep - pairs.oo[:-1][pair_of_row[keep]].long()  # the reference reports the top-k positions
+                weights, h_off = val, new_off
+                offsets = torch.tensor(new_off, dtype=torch.int32, device=dev)
+            pose = ops.weighted_procrustes(a, b, weights, offsets)
+            if cfg.get('use_lgr', False):  # :553-554 / :658-659, starting from val (not the overlap weights)
+                pose = ops.local_global_registration(a, b, val, pose, offsets, float(cfg.acceptance_radius),
+                                                     int(cfg.num_refinement_steps))
+            if cfg.get('use_ransac', False):  # :556-557 / :661-662: 500 hypotheses from 100 rows drawn with replacement
+                counts = torch.tensor([h_off[p + 1] - h_off[p] for p in range(P)], device=dev, dtype=torch.float32)
+                u = torch.rand((P, self.ransac_hypotheses, self.ransac_sample_size), device=dev,
+                               generator=self.ransac_generator)
+                idx = torch.minimum((u * counts[:, None, None]).long(), (counts[:, None, None] - 1).long())
+                pose, _, _ = ops.ransac(a, b, val, offsets, idx)
+            src_pts_list = [a[h_off[p]:h_off[p + 1]] for p in range(P)]
+            tgt_pts_list = [b[h_off[p]:h_off[p + 1]] for p in range(P)]
+        val_list = [val[h_off[p]:h_off[p + 1]] for p in range(P)]
+        ind_list = [ind[h_off[p]:h_off[p + 1]] for p in range(P)]
         return pose, attn_list, val_list, ind_list, src_pts_list, tgt_pts_list
+
+
+def _segment_median(val, h_off, pair_of_row):
+    """torch.median of each pair's values (the lower of the two middle ones), broadcast back to the rows."""
+    P = len(h_off) - 1
+    lens = [h_off[p + 1] - h_off[p] for p in range(P)]
+    pad = torch.full((P, max(max(lens), 1)), float('inf'), dtype=val.dtype, device=val.device)
+    local = torch.arange(val.shape[0], device=val.device) - torch.tensor(h_off[:-1], device=val.device)[pair_of_row]
+    pad[pair_of_row, local] = val
+    srt, _ = torch.sort(pad, dim=1)
+    mid = torch.tensor([max(l - 1, 0) // 2 for l in lens], device=val.device)
+    return srt[torch.arange(P, device=val.device), mid][pair_of_row]

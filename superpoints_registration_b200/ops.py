@@ -378,6 +378,67 @@ def gather_rows3(src, ind, row_base) -> torch.Tensor:
     return out
 
 
+def top2_ratio(attn, pairs: PackedPairs, lowe_thres: float):
+    """RegTR.ratio_test (qk_regtr_full.py:370-384) on the packed attention -> val f32[total_out], ind i64[total_out]."""
+    for n, m in zip(pairs.src_lens, pairs.tgt_lens):
+        if (n if n > m else m) < 2:
+            raise RuntimeError("ratio test: selected index k out of range (the reduced axis needs two entries)")
+    a = _f32c(attn, "attn")
+    val = torch.empty(pairs.total_out, dtype=torch.float32, device=a.device)
+    ind = torch.empty(pairs.total_out, dtype=torch.int64, device=a.device)
+    rc = _lib.lib().spr_top2_ratio(a.data_ptr(), pairs.co.data_ptr(), pairs.so.data_ptr(), pairs.to.data_ptr(),
+                                   pairs.oo.data_ptr(), pairs.P, pairs.total_out, float(lowe_thres), val.data_ptr(),
+                                   ind.data_ptr(), _stream())
+    _lib.check(rc, "spr_top2_ratio")
+    return val, ind
+
+
+def inlier_reweight(a, b, w, poses, offsets, acceptance_radius: float) -> torch.Tensor:
+    """RegTR.recompute_weights (qk_regtr_full.py:386-391) for packed pairs."""
+    aa, bb, ww = _f32c(a, "a"), _f32c(b, "b"), _f32c(w, "weights")
+    pp, offs = _f32c(poses, "poses"), _i32c(offsets, "offsets")
+    out = torch.empty_like(ww)
+    rc = _lib.lib().spr_inlier_reweight(aa.data_ptr(), bb.data_ptr(), ww.data_ptr(), pp.data_ptr(), offs.data_ptr(),
+                                        offs.shape[0] - 1, ww.shape[0], float(acceptance_radius), out.data_ptr(),
+                                        _stream())
+    _lib.check(rc, "spr_inlier_reweight")
+    return out
+
+
+def local_global_registration(a, b, w, poses, offsets, acceptance_radius: float, num_refinement_steps: int):
+    """RegTR.local_global_registration (qk_regtr_full.py:393-398): alternate inlier re-weighting and the pose solve."""
+    for _ in range(int(num_refinement_steps)):
+        w = inlier_reweight(a, b, w, poses, offsets, acceptance_radius)
+        poses = weighted_procrustes(a, b, w, offsets)
+    return poses
+
+
+def ransac(a, b, w, offsets, sample_idx: torch.Tensor):
+    """RegTR.ransac (qk_regtr_full.py:400-421) for packed pairs.  sample_idx i64 [P, n_hypotheses, sample_size]:
+    per pair, row numbers local to the pair (the reference draws torch.randint(0, N, (100,)) 500 times).
+    -> poses f32[P,3,4], loss f32[P,n_hypotheses], best i32[P]."""
+    aa, bb, ww = _f32c(a, "a"), _f32c(b, "b"), _f32c(w, "weights")
+    offs = _i32c(offsets, "offsets")
+    P = offs.shape[0] - 1
+    _need_cuda(sample_idx, "sample_idx")
+    if sample_idx.dim() != 3 or sample_idx.shape[0] != P:
+        raise RuntimeError("ransac: sample_idx must be [pairs, hypotheses, sample_size]")
+    H, S = int(sample_idx.shape[1]), int(sample_idx.shape[2])
+    flat = sample_idx.long().reshape(-1)
+    base = offs[:-1].repeat_interleave(H * S)
+    sa, sb = gather_rows3(aa, flat, base), gather_rows3(bb, flat, base)
+    sw = ww[(flat + base).long()]
+    seg = torch.arange(0, P * H * S + 1, S, dtype=torch.int32, device=aa.device)
+    hyp = weighted_procrustes(sa, sb, sw, seg)                     # [P*H, 3, 4]
+    loss = torch.empty((P, H), dtype=torch.float32, device=aa.device)
+    out = torch.empty((P, 3, 4), dtype=torch.float32, device=aa.device)
+    best = torch.empty(P, dtype=torch.int32, device=aa.device)
+    rc = _lib.lib().spr_select_hypothesis(aa.data_ptr(), bb.data_ptr(), offs.data_ptr(), P, hyp.data_ptr(), H,
+                                          loss.data_ptr(), out.data_ptr(), best.data_ptr(), _stream())
+    _lib.check(rc, "spr_select_hypothesis")
+    return out, loss, best
+
+
 # ------------------------------------------------------------------------------------------------
 # cross-encoder building blocks (packed tokens)
 # ------------------------------------------------------------------------------------------------

@@ -199,6 +199,63 @@ def gen_matching(ref):
     save("matching.npz", **arrays)
 
 
+REFINEMENT_VARIANTS = {
+    "ratio": dict(use_ratio_test=True, lowe_thres=2e-4),   # dual-softmax ratios are ~1e-4 on these features
+    "median": dict(threshold_corr=True),
+    "overlap": dict(remove_outliers_overlap=True),
+    "overlap_w": dict(remove_outliers_overlap=True, use_overlap_as_weights=True),
+    "lgr": dict(use_lgr=True, acceptance_radius=0.3, num_refinement_steps=4),
+    "topk": dict(remove_points_from_val=True, val_threshold=0.25),
+    "combo": dict(use_ratio_test=True, lowe_thres=5e-4, threshold_corr=True, remove_outliers_overlap=True, use_lgr=True,
+                  acceptance_radius=0.3, num_refinement_steps=3),
+}
+
+
+def gen_refinements(ref):
+    """softmax_correlation of the reference model with each optional refinement switched on (KITTI settings: argmax
+    correspondences + Procrustes).  RegTR.ransac is absent: it moves its draws to .cuda() (:404)."""
+    rng = np.random.default_rng(43)
+    shapes = [(95, 70), (60, 101), (48, 48)]
+    ang = 0.4
+    R = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]], dtype=np.float32)
+    t = np.array([0.5, -0.3, 0.2], dtype=np.float32)
+    src_f, tgt_f, src_xyz, tgt_xyz, src_ov, tgt_ov = [], [], [], [], [], []
+    for n, m in shapes:
+        k = max(n, m)
+        base = rng.normal(size=(k, 256)).astype(np.float32) * 0.6   # moderately peaked attention
+        xyz = rng.uniform(-2, 2, size=(k, 3)).astype(np.float32)
+        perm = rng.permutation(k)[:m]
+        sf = base[:n] + 0.1 * rng.normal(size=(n, 256)).astype(np.float32)
+        tf = base[perm] + 0.1 * rng.normal(size=(m, 256)).astype(np.float32)
+        txyz = xyz[perm] @ R.T + t + 0.02 * rng.normal(size=(m, 3)).astype(np.float32)
+        bad = rng.uniform(size=m) < 0.25                       # gross outliers for the inlier test to reject
+        txyz[bad] += rng.uniform(-1.5, 1.5, size=(int(bad.sum()), 3)).astype(np.float32)
+        src_f.append(torch.from_numpy(sf)[None])
+        tgt_f.append(torch.from_numpy(tf)[None])
+        src_xyz.append(torch.from_numpy(xyz[:n].copy()))
+        tgt_xyz.append(torch.from_numpy(txyz.astype(np.float32)))
+        src_ov.append(torch.from_numpy(rng.uniform(0.05, 1, size=(1, n, 1)).astype(np.float32)))
+        tgt_ov.append(torch.from_numpy(rng.uniform(0.05, 1, size=(1, m, 1)).astype(np.float32)))
+    arrays = {"n_pairs": np.asarray(len(shapes)), "variants": np.asarray(sorted(REFINEMENT_VARIANTS))}
+    for i in range(len(shapes)):
+        arrays[f"src_f_{i}"], arrays[f"tgt_f_{i}"] = t2n(src_f[i][0]), t2n(tgt_f[i][0])
+        arrays[f"src_xyz_{i}"], arrays[f"tgt_xyz_{i}"] = t2n(src_xyz[i]), t2n(tgt_xyz[i])
+        arrays[f"src_ov_{i}"], arrays[f"tgt_ov_{i}"] = t2n(src_ov[i]), t2n(tgt_ov[i])
+    for tag, overrides in REFINEMENT_VARIANTS.items():
+        cfg = ref_torch.load_cfg("qk_regtr_full_kitti.yaml", **overrides)
+        model = ref_torch.build_model(cfg, seed=0)
+        with torch.no_grad():
+            pose, attn, val, ind, sp, tp = model.softmax_correlation(src_f, tgt_f, src_xyz, tgt_xyz, src_ov, tgt_ov)
+        arrays[f"{tag}_pose"] = t2n(pose)
+        for i in range(len(shapes)):
+            arrays[f"{tag}_val_{i}"] = t2n(val[i])
+            arrays[f"{tag}_ind_{i}"] = t2n(ind[i])
+            arrays[f"{tag}_src_pts_{i}"] = t2n(sp[i])
+            arrays[f"{tag}_tgt_pts_{i}"] = t2n(tp[i])
+        print(tag, [int((t2n(v) > 0).sum()) for v in val], "non-zero weights of", [t2n(v).size for v in val])
+    save("refinements.npz", **arrays)
+
+
 def gen_forward(ref):
     """Encoder features and the full forward of the reference model (weights from tests/golden/weights.py)."""
     for tag, yaml_name, data in (
@@ -240,6 +297,7 @@ def main():
     gen_blocks(ref)
     gen_pose(ref)
     gen_matching(ref)
+    gen_refinements(ref)
     gen_forward(ref)
 
 

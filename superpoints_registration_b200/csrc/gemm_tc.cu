@@ -56,6 +56,7 @@ struct GemmArgs {
   int n_scaled;            // OUT_PLANES: columns < n_scaled are multiplied by col_scale (query pre-scaling)
   float col_scale;
   float next_scale;        // OUT_AIMG: activation scale of the next GEMM's A operand
+  float2* stats16;         // OUT_F32, optional: [ceil(T/16), N] (sum, sum of squares) of each 16-row block of the output
 };
 
 __device__ long long g_gemm_dbg[4096];
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
       float* stg = s_epi + (warp - 2) * (EPI_STAGE_BYTES / 4);
 #pragma unroll
       for (int grp = 0; grp < 2; ++grp) {
+        // (skipping the empty column groups of narrow outputs with a branch here costs more than it saves)
         // bias and residual of this group's coalesced phase are requested first: their latency overlaps the transpose
         const int pcol = nt * BN + chalf * 64 + grp * 32 + (lane & 7) * 4;
         float4 pbias = make_float4(0.f, 0.f, 0.f, 0.f), pres[4];
@@ -241,6 +243,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
         }
         __syncwarp();
         const int ncol0 = nt * BN + chalf * 64 + grp * 32 + (lane & 7) * 4;  // first of this lane's 4 columns
+        float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};      // column sums of the warp's 16 tokens
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int tl = k * 4 + (lane >> 3);                    // token within the warp's 16
@@ -257,6 +260,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
               for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], 0.f);
             }
             *reinterpret_cast<float4*>(g.out_f32 + (size_t)token * g.ld_out + ncol0) = make_float4(y[0], y[1], y[2], y[3]);
+            if (g.stats16) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                cs[e] += y[e];
+                cq[e] = fmaf(y[e], y[e], cq[e]);
+              }
+            }
           } else {
             if (g.relu) {
 #pragma unroll
@@ -281,6 +291,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
               *reinterpret_cast<uint2*>(blk + sw128_offset(r2, chunk) + inb) = hv;
               *reinterpret_cast<uint2*>(blk + sw128_offset(r2 + 1, chunk) + inb) = lv;
             }
+          }
+        }
+        if (mode == OUT_F32 && g.stats16) {
+          // InstanceNorm statistics of the consumer: fold the 4 token groups (lanes 8 apart) in a fixed order and
+          // write (sum, sumsq) of this warp's 16-token block; the normalisation kernel never re-reads the rows
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            cs[e] += __shfl_xor_sync(kFull, cs[e], 8);
+            cq[e] += __shfl_xor_sync(kFull, cq[e], 8);
+            cs[e] += __shfl_xor_sync(kFull, cs[e], 16);
+            cq[e] += __shfl_xor_sync(kFull, cq[e], 16);
+          }
+          const int tok0 = mt * BM_TOK + qd * 16;
+          if (lane < 8 && tok0 < g.T && ncol0 < g.N && dbg < 2) {
+            float4* dst = reinterpret_cast<float4*>(g.stats16 + (size_t)(tok0 >> 4) * g.N + ncol0);
+            dst[0] = make_float4(cs[0], cq[0], cs[1], cq[1]);
+            dst[1] = make_float4(cs[2], cq[2], cs[3], cq[3]);
           }
         }
         __syncwarp();
@@ -452,9 +479,11 @@ extern "C" int spr_layernorm256_prepare(const float* d_x, const float* d_gamma, 
 
 extern "C" int spr_gemm_tc(const void* d_a_img, const void* d_w_img, const float* d_bias, const float* d_residual,
                            int ld_res, int T, int N, int K, float out_scale, int relu, int out_mode, void* d_out,
-                           void* d_out_lo, int ld_out, int n_scaled, float col_scale, float next_scale, void* stream_) {
+                           void* d_out_lo, int ld_out, int n_scaled, float col_scale, float next_scale,
+                           float* d_stats16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SPR_CHECK_ARG(d_a_img && d_w_img && d_out && T > 0 && N > 0 && K > 0, "gemm_tc: bad arguments");
+  SPR_CHECK_ARG(!d_stats16 || out_mode == OUT_F32, "gemm_tc: block statistics only with fp32 output");
   SPR_CHECK_ARG((N & 3) == 0, "gemm_tc: N must be a multiple of 4 (got %d)", N);
   SPR_CHECK_ARG(out_mode >= 0 && out_mode <= 2, "gemm_tc: unknown output mode %d", out_mode);
   SPR_CHECK_ARG(out_mode != OUT_PLANES || d_out_lo, "gemm_tc: plane output needs both planes");
@@ -478,6 +507,7 @@ extern "C" int spr_gemm_tc(const void* d_a_img, const void* d_w_img, const float
   g.n_scaled = n_scaled;
   g.col_scale = col_scale;
   g.next_scale = next_scale;
+  g.stats16 = reinterpret_cast<float2*>(d_stats16);
   static bool attr_set = false;
   if (!attr_set) {
     SPR_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));

@@ -101,13 +101,13 @@ class BatchNormBlock(nn.Module):
         return y if slope == 1.0 else torch.nn.functional.leaky_relu(y, slope)
 
     def forward_ex(self, x, stack_lengths, slope: float = 1.0, residual=None, want_f32=True, want_image=False,
-                   kpconv_points=None):
+                   kpconv_points=None, stats16=None):
         """Format-aware variant (ops.instance_norm_lrelu_ex): the consumer's operand formats come out of the
         normalisation kernel itself.  Only with instance norm (every shipped config)."""
         if not self.use_bn:
             raise NotImplementedError("format-aware outputs need use_batch_norm=True")
         return ops.instance_norm_lrelu_ex(x, stack_lengths, IN_EPS, slope, residual, want_f32=want_f32,
-                                          want_image=want_image, kpconv_points=kpconv_points)
+                                          want_image=want_image, kpconv_points=kpconv_points, stats16=stats16)
 
     def __repr__(self):
         return f'BatchNormBlock(in_feat: {self.in_dim:d}, momentum: {self.bn_momentum:.3f}, only_bias: {not self.use_bn})'
@@ -137,8 +137,10 @@ class UnaryBlock(nn.Module):
         """Same operator from an operand image of x; `wants` selects the output formats (BatchNormBlock.forward_ex)."""
         if slope is None:
             slope = 1.0 if self.no_relu else LRELU_SLOPE
-        y = ops.gemm_tc(x_image, ops.weight_image(self.mlp.weight), self.mlp.bias, n_rows, ops.OUT_F32)
-        return self.batch_norm.forward_ex(y, stack_lengths, slope=slope, residual=residual, **wants)
+        # the GEMM epilogue also sums its rows in 16-row blocks, so the normalisation reads them once, not twice
+        stats = ops.block_stats(n_rows, self.out_dim, x_image.device) if self.use_bn else None
+        y = ops.gemm_tc(x_image, ops.weight_image(self.mlp.weight), self.mlp.bias, n_rows, ops.OUT_F32, stats16=stats)
+        return self.batch_norm.forward_ex(y, stack_lengths, slope=slope, residual=residual, stats16=stats, **wants)
 
     def __repr__(self):
         return (f'UnaryBlock(in_feat: {self.in_dim:d}, out_feat: {self.out_dim:d}, BN: {self.use_bn}, '

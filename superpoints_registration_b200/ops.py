@@ -193,8 +193,14 @@ def instance_norm_lrelu(x, lengths, eps: float = 1e-5, slope: float = 1.0, resid
     return out
 
 
+def block_stats(n_rows: int, c: int, device) -> torch.Tensor:
+    """Buffer for the (sum, sumsq) of every 16-row block that a producer (gemm_tc, kpconv_forward_prepared) writes
+    for the instance normalisation that consumes its rows."""
+    return torch.empty(((n_rows + 15) // 16, c, 2), dtype=torch.float32, device=device)
+
+
 def instance_norm_lrelu_ex(x, lengths, eps: float = 1e-5, slope: float = 1.0, residual=None, want_f32: bool = True,
-                           want_image: bool = False, kpconv_points=None):
+                           want_image: bool = False, kpconv_points=None, stats16=None):
     """InstanceNorm (+ residual) + LeakyReLU with format-aware outputs.  Returns a dict with any of
     'f32' (rows), 'image' (operand image of the next tensor-core GEMM, K = c), 'kpconv' (PreparedFeatures for
     kpconv_forward_prepared; needs kpconv_points = the [n,3] points the rows belong to)."""
@@ -212,10 +218,12 @@ def instance_norm_lrelu_ex(x, lengths, eps: float = 1e-5, slope: float = 1.0, re
         x16 = torch.empty((n, c), dtype=torch.int32, device=xx.device)
         pts4 = torch.empty((n, 4), dtype=torch.float32, device=xx.device)
         amax = torch.empty(1, dtype=torch.int32, device=xx.device)
+    if stats16 is not None and tuple(stats16.shape) != ((n + 15) // 16, c, 2):
+        raise RuntimeError("instance_norm_lrelu_ex: stats16 does not match x")
     ws = _ws(L.spr_instance_norm_workspace_bytes(n, lens.shape[0], c), xx.device)
     rc = L.spr_instance_norm_lrelu_ex(xx.data_ptr(), lens.data_ptr(), n, lens.shape[0], c, float(eps), float(slope),
                                       _ptr(res), _ptr(f32), _ptr(img), A_SCALE, _ptr(x16), _ptr(pts4), _ptr(pts),
-                                      _ptr(amax), ws.data_ptr(), ws.numel(), _stream())
+                                      _ptr(amax), _ptr(stats16), ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "spr_instance_norm_lrelu_ex")
     if f32 is not None:
         out["f32"] = f32
@@ -552,7 +560,7 @@ def layernorm256_prepare(x, gamma, beta, pos, eps: float, img: Optional[torch.Te
 
 
 def gemm_tc(a_img: torch.Tensor, wi: WeightImage, bias, T: int, mode: int = OUT_F32, residual=None, relu: bool = False,
-            out=None, out_lo=None, n_scaled: int = 0, col_scale: float = 1.0):
+            out=None, out_lo=None, n_scaled: int = 0, col_scale: float = 1.0, stats16=None):
     """Y = act(X W^T + b) (+ residual) on the tcgen05 tensor cores from operand images; see include/spr_b200.h."""
     L = _lib.lib()
     N, K = wi.N, wi.K
@@ -571,7 +579,7 @@ def gemm_tc(a_img: torch.Tensor, wi: WeightImage, bias, T: int, mode: int = OUT_
     rc = L.spr_gemm_tc(a_img.data_ptr(), wi.img.data_ptr(), _ptr(bias), _ptr(residual),
                        residual.shape[1] if residual is not None else 0, int(T), N, K, 1.0 / (A_SCALE * wi.w_scale),
                        1 if relu else 0, int(mode), out.data_ptr(), _ptr(out_lo), ld_out, int(n_scaled),
-                       float(col_scale), A_SCALE, _stream())
+                       float(col_scale), A_SCALE, _ptr(stats16), _stream())
     _lib.check(rc, "spr_gemm_tc")
     return (out, out_lo) if mode == OUT_PLANES else out
 

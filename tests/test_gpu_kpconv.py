@@ -223,6 +223,32 @@ def test_format_aware_instance_norm_outputs_feed_gemm_and_kpconv():
         <= 1e-6 * 10
 
 
+@pytest.mark.parametrize("n_out,lens", [(64, [300, 157, 43]), (96, [16, 0, 5, 33, 1, 160, 7]), (256, [1000])])
+def test_producer_block_statistics_feed_instance_norm(n_out, lens):
+    """spr_gemm_tc's 16-row block sums (stats16) replace the statistics pass of the instance normalisation: same
+    result as the two-pass route, for clouds that start and end anywhere relative to the 16-row blocks."""
+    rng = np.random.default_rng(n_out)
+    lens = np.array(lens, dtype=np.int32)
+    n, k = int(lens.sum()), 64
+    x = _t(rng.normal(size=(n, k)).astype(np.float32))
+    w = torch.randn(n_out, k, device=DEV) / 8 + 0.05              # non-zero column means
+    img = ops.gemm_prepare_input(x)
+    stats = ops.block_stats(n, n_out, DEV)
+    stats.fill_(float("nan"))
+    y = ops.gemm_tc(img, ops.weight_image(w), None, n, ops.OUT_F32, stats16=stats)
+    assert torch.equal(y, ops.gemm_tc(img, ops.weight_image(w), None, n, ops.OUT_F32))
+    full = n // 16
+    blocks = y[:full * 16].double().view(full, 16, n_out)
+    assert (stats[:full, :, 0].double() - blocks.sum(1)).abs().max().item() <= 1e-5 * blocks.abs().sum(1).max().item()
+    assert (stats[:full, :, 1].double() - (blocks ** 2).sum(1)).abs().max().item() <= 1e-5 * (blocks ** 2).sum(1).max().item()
+    res = _t(rng.normal(size=(n, n_out)).astype(np.float32))
+    a = ops.instance_norm_lrelu_ex(y, _t(lens), slope=0.1, residual=res)["f32"]
+    b = ops.instance_norm_lrelu_ex(y, _t(lens), slope=0.1, residual=res, stats16=stats)["f32"]
+    assert (a - b).abs().max().item() <= 2e-6 * a.abs().max().item()
+    with pytest.raises(RuntimeError):
+        ops.instance_norm_lrelu_ex(y, _t(lens), stats16=stats[:-1])
+
+
 @pytest.mark.parametrize("c", [32, 128])
 def test_cell_order_is_a_permutation_and_does_not_change_kpconv(c):
     """CellGrid.order() lists every support once, cloud by cloud, in cell order; used as the KPConv processing order

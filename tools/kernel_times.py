@@ -67,3 +67,34 @@ if os.environ.get("SPR_IN_DETAIL"):
         wr = n * c * 4 * (int(f32) + int(img) + int(kp)) + (n * 16 if kp else 0)
         print(f"n={n:7d} c={c:4d} res={int(res)} f32={int(f32)} img={int(img)} kp={int(kp)}  partial {tp:6.1f} us "
               f"{n * c * 4 / tp / 1e3:7.0f} GB/s   apply {ta:6.1f} us {(rd + wr) / ta / 1e3:7.0f} GB/s")
+
+# ---- per-launch detail of the tensor-core GEMMs against their operand / result bytes ----
+if os.environ.get("SPR_GEMM_DETAIL"):
+    from superpoints_registration_b200 import ops
+    calls = []
+    raw_gemm = ops.gemm_tc
+
+    def rec_gemm(a_img, wi, bias, T, mode=ops.OUT_F32, residual=None, **kw):
+        calls.append((int(T), wi.N, wi.K, int(mode), residual is not None, kw.get("stats16") is not None))
+        return raw_gemm(a_img, wi, bias, T, mode, residual=residual, **kw)
+
+    ops.gemm_tc = rec_gemm
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        model(dict(batch))
+        torch.cuda.synchronize()
+    ev = sorted([e for e in prof.events() if e.device_type.name == "CUDA" and "k_gemm_tc" in e.name],
+                key=lambda e: e.time_range.start)
+    print(f"{len(calls)} gemm calls, {len(ev)} launches")
+    agg = {}
+    for (T, N, K, mode, res, st), e in zip(calls, ev):
+        kp = (K + 63) // 64 * 64
+        rd = T * kp * 4 + N * kp * 4 + (T * N * 4 if res else 0)
+        wr = T * N * 4 + (T // 16 * N * 8 if st else 0)
+        key = (T, N, K, mode, res, st)
+        a = agg.setdefault(key, [0, 0.0, rd + wr, 2.0 * T * N * K])
+        a[0] += 1
+        a[1] += e.device_time
+    for key, (cnt, t, by, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        T, N, K, mode, res, st = key
+        print(f"T={T:8d} N={N:5d} K={K:5d} mode={mode} res={int(res)} stats={int(st)} x{cnt:2d}  {t:8.1f} us total "
+              f"{t / cnt:7.1f} us each  {by / (t / cnt) / 1e3:6.0f} GB/s  {fl / (t / cnt) / 1e6:6.1f} TFLOP/s")

@@ -107,25 +107,32 @@ class Preprocessor(nn.Module):
         limits = cfg.neighborhood_limits
         levels = _split_levels(cfg.architecture)
 
-        lengths = torch.tensor([p.shape[0] for p in pts], dtype=torch.int32, device=device)
         points = torch.cat([p.to(torch.float32) for p in pts], dim=0).contiguous()
+        host_lengths = [int(p.shape[0]) for p in pts]
+        lengths = ops.to_device_async(host_lengths, torch.int32, device)
         r = float(cfg.first_subsampling_dl) * float(cfg.conv_radius)
 
         out_points, out_neighbors, out_pools, out_ups, out_lens = [], [], [], [], []
         out_order = []  # per level: the points in cell order (private: processing order of the KPConv kernels)
+        out_host_lens = []  # per level: stack_lengths as a host list (private: saves consumers a device read)
         widths = []  # (list, position, max_count tensor)
         grid = ops.CellGrid(points, lengths, r)
         empty_idx = lambda: torch.zeros((0, 1), dtype=torch.int64, device=device)
         for li, (has_conv, strided) in enumerate(levels):
             limit = int(limits[li])
+            pending = None
+            if strided:
+                # the subsampling goes first and its sizes travel to the host while the convolution neighbours
+                # (independent of them) are searched: the device is never idle waiting for the host to learn M
+                dl = 2.0 * r / float(cfg.conv_radius)
+                pending = ops.grid_subsample_batch_async(points, lengths, dl)
             if has_conv:
                 conv_i, mc = grid.query(points, lengths, limit, index_dtype=self.index_dtype)
                 widths.append((out_neighbors, li, mc, limit))
             else:
                 conv_i = empty_idx()
             if strided:
-                dl = 2.0 * r / float(cfg.conv_radius)
-                pool_p, pool_b = ops.grid_subsample_batch(points, lengths, dl)
+                pool_p, pool_b, pool_host = pending.finish()
                 pool_i, mc = grid.query(pool_p, pool_b, limit, index_dtype=self.index_dtype)
                 widths.append((out_pools, li, mc, limit))
                 next_grid = ops.CellGrid(pool_p, pool_b, 2.0 * r)
@@ -135,14 +142,15 @@ class Preprocessor(nn.Module):
                 pool_i, up_i = empty_idx(), empty_idx()
                 pool_p = torch.zeros((0, 3), dtype=torch.float32, device=device)
                 pool_b = torch.zeros((0,), dtype=torch.int64, device=device)
-                next_grid = None
+                next_grid, pool_host = None, []
             out_points.append(points)
             out_order.append(grid.order() if grid is not None else None)
             out_neighbors.append(conv_i)
             out_pools.append(pool_i)
             out_ups.append(up_i)
             out_lens.append(lengths)
-            points, lengths, grid = pool_p, pool_b, next_grid
+            out_host_lens.append(host_lengths)
+            points, lengths, grid, host_lengths = pool_p, pool_b, next_grid, pool_host
             r *= 2.0
 
         if self.exact_width and widths:
@@ -150,8 +158,18 @@ class Preprocessor(nn.Module):
             for (lst, li, _, limit), mc in zip(widths, counts):
                 w = min(int(mc), limit)
                 lst[li] = lst[li][:, :w]
-        return {"points": out_points, "neighbors": out_neighbors, "pools": out_pools, "upsamples": out_ups,
-                "stack_lengths": out_lens, "_order": out_order}
+        meta = Pyramid({"points": out_points, "neighbors": out_neighbors, "pools": out_pools, "upsamples": out_ups,
+                        "stack_lengths": out_lens})
+        meta.order, meta.host_lengths = out_order, out_host_lens
+        return meta
+
+
+class Pyramid(dict):
+    """The reference's collate dict (exactly its five keys) plus two by-products of building it, kept as attributes
+    so that code iterating over the dict sees nothing new: `order[l]` = the level's points in cell order (the
+    KPConv kernels walk their queries in it), `host_lengths[l]` = stack_lengths[l] as a host list."""
+    order = None
+    host_lengths = None
 
 
 # ------------------------------------------------------------------------------------------------

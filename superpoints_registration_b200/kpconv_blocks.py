@@ -17,7 +17,6 @@ from __future__ import annotations
 
 import math
 
-import os
 import torch
 import torch.nn as nn
 from torch.nn.parameter import Parameter
@@ -226,7 +225,7 @@ class ResnetBottleneckBlock(nn.Module):
         f_img = stash[1] if stash is not None and stash[0] is features else ops.gemm_prepare_input(features)
 
         x = self.unary1.forward_ex(f_img, n_in, pre_lengths, want_f32=False, kpconv_points=s_pts)['kpconv']
-        orders = batch.get('_order') if not os.environ.get('SPR_NO_ORDER') else None
+        orders = getattr(batch, 'order', None)
         order = orders[self.layer_ind + 1 if strided else self.layer_ind] if orders is not None else None
         x = ops.kpconv_forward_prepared(q_pts, inds, x, self.KPConv.weights, self.KPConv.kernel_points,
                                         self.KPConv.KP_extent, order=order)

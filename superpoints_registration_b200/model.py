@@ -284,7 +284,8 @@ class RegTR(nn.Module):
         B = len(batch['src_xyz'])
         meta = self.preprocessor(list(batch['src_xyz']) + list(batch['tgt_xyz']))
         batch['kpconv_meta'] = meta
-        slens_c = meta['stack_lengths'][-1].tolist()
+        host_lens = getattr(meta, 'host_lengths', None)
+        slens_c = list(host_lens[-1]) if host_lens else meta['stack_lengths'][-1].tolist()
         src_slens_c, tgt_slens_c = slens_c[:B], slens_c[B:]
         pts_c = meta['points'][-1]
         feats0 = torch.ones_like(meta['points'][0][:, 0:1])

@@ -56,13 +56,31 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 # preprocessing
 # ------------------------------------------------------------------------------------------------
 
-def grid_subsample_batch(points: torch.Tensor, lengths: torch.Tensor, sample_dl: float
-                         ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Barycentre voxel subsampling of stacked clouds. -> (points f32[M,3], lengths i32[B]) on device.
+def to_device_async(values, dtype, device) -> torch.Tensor:
+    """Small host list -> device tensor through pinned memory, without blocking the host (torch.tensor(...,
+    device=cuda) is a pageable copy that waits for everything queued on the stream)."""
+    host = torch.tensor(values, dtype=dtype)
+    if torch.device(device).type != "cuda":  # host-side bookkeeping objects (tests of the offset logic)
+        return host
+    return host.pin_memory().to(device, non_blocking=True)
 
-    One host synchronisation (reading M), as in the reference where the lengths come back as a NumPy array
-    (cpp_subsampling/wrapper.cpp:300-322).
-    """
+
+class PendingSubsample:
+    """A grid subsampling whose output size is still on its way to the host (see grid_subsample_batch_async)."""
+
+    def __init__(self, out, meta, host_meta, event, b):
+        self._out, self._meta, self._host, self._event, self._b = out, meta, host_meta, event, b
+
+    def finish(self) -> Tuple[torch.Tensor, torch.Tensor, list]:
+        """-> (points f32[M,3], lengths i32[B] on device, the same lengths as a host list)."""
+        self._event.synchronize()
+        host = self._host.tolist()
+        return self._out[:host[self._b]], self._meta[:self._b], host[:self._b]
+
+
+def grid_subsample_batch_async(points: torch.Tensor, lengths: torch.Tensor, sample_dl: float) -> PendingSubsample:
+    """Launch the barycentre voxel subsampling and request its sizes; the caller queues independent work and then
+    calls .finish(), so the device never waits for the host to learn M."""
     L = _lib.lib()
     pts = _f32c(points, "points")
     lens = _i32c(lengths, "lengths")
@@ -76,8 +94,22 @@ def grid_subsample_batch(points: torch.Tensor, lengths: torch.Tensor, sample_dl:
     rc = L.spr_grid_subsample_batch(pts.data_ptr(), lens.data_ptr(), n, b, float(sample_dl), out.data_ptr(),
                                     meta.data_ptr(), meta.data_ptr() + 4 * b, ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "spr_grid_subsample_batch")
-    m = int(meta[b].item())
-    return out[:m], meta[:b]
+    host = torch.empty(b + 1, dtype=torch.int32, pin_memory=True)
+    host.copy_(meta, non_blocking=True)
+    event = torch.cuda.Event()
+    event.record()
+    return PendingSubsample(out, meta, host, event, b)
+
+
+def grid_subsample_batch(points: torch.Tensor, lengths: torch.Tensor, sample_dl: float
+                         ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Barycentre voxel subsampling of stacked clouds. -> (points f32[M,3], lengths i32[B]) on device.
+
+    One host synchronisation (reading M), as in the reference where the lengths come back as a NumPy array
+    (cpp_subsampling/wrapper.cpp:300-322).
+    """
+    pts, lens, _ = grid_subsample_batch_async(points, lengths, sample_dl).finish()
+    return pts, lens
 
 
 class CellGrid:
@@ -318,10 +350,12 @@ class PackedPairs:
         self.total_src, self.total_tgt, self.total_corr, self.total_out = so[-1], to[-1], co[-1], oo[-1]
         self.max_n, self.max_m = max(self.src_lens), max(self.tgt_lens)
         self.h_so, self.h_to, self.h_co, self.h_oo = so, to, co, oo
-        self.so = torch.tensor(so, dtype=torch.int32, device=device)
-        self.to = torch.tensor(to, dtype=torch.int32, device=device)
-        self.co = torch.tensor(co, dtype=torch.int64, device=device)
-        self.oo = torch.tensor(oo, dtype=torch.int32, device=device)
+        # one pinned staging buffer, one asynchronous copy: int64 so that the N x M offsets fit
+        P1 = self.P + 1
+        packed = to_device_async(so + to + oo + co, torch.int64, device)
+        i32 = packed[:3 * P1].to(torch.int32)
+        self.so, self.to, self.oo = i32[:P1], i32[P1:2 * P1], i32[2 * P1:]
+        self.co = packed[3 * P1:]
 
 
 def dual_softmax_match(src_feats, tgt_feats, pairs: PackedPairs, want_attn: bool = False):
@@ -475,7 +509,7 @@ def attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q: int
             raise RuntimeError("attention over an empty key segment")
         for q0 in range(0, qn, block_q):
             rows.append((qo + q0, min(block_q, qn - q0), ko, kn))
-    return torch.tensor(rows, dtype=torch.int32).to(device, non_blocking=True)
+    return to_device_async(rows, torch.int32, device)
 
 
 def attention_varlen(hi: torch.Tensor, lo: torch.Tensor, tiles: torch.Tensor, n_heads: int, q_col: int, k_col: int,

@@ -98,3 +98,31 @@ if os.environ.get("SPR_GEMM_DETAIL"):
         T, N, K, mode, res, st = key
         print(f"T={T:8d} N={N:5d} K={K:5d} mode={mode} res={int(res)} stats={int(st)} x{cnt:2d}  {t:8.1f} us total "
               f"{t / cnt:7.1f} us each  {by / (t / cnt) / 1e3:6.0f} GB/s  {fl / (t / cnt) / 1e6:6.1f} TFLOP/s")
+
+# ---- every launch of one kernel, in launch order:  SPR_LAUNCHES=k_radius_query ----
+if os.environ.get("SPR_LAUNCHES"):
+    pat = os.environ["SPR_LAUNCHES"]
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        model(dict(batch))
+        torch.cuda.synchronize()
+    ev = sorted([e for e in prof.events() if e.device_type.name == "CUDA" and pat in e.name],
+                key=lambda e: e.time_range.start)
+    print(pat, [round(e.device_time, 1) for e in ev])
+
+# ---- idle time of the GPU between consecutive kernels of one forward:  SPR_GAPS=1 ----
+if os.environ.get("SPR_GAPS"):
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        model(dict(batch))
+        torch.cuda.synchronize()
+    ev = sorted([e for e in prof.events() if e.device_type.name == "CUDA"], key=lambda e: e.time_range.start)
+    gaps = []
+    for a, b in zip(ev[:-1], ev[1:]):
+        gaps.append((b.time_range.start - a.time_range.end, a.name[:50], b.name[:50]))
+    span = ev[-1].time_range.end - ev[0].time_range.start
+    busy = sum(e.device_time for e in ev)
+    print(f"span {span / 1e3:.2f} ms, busy {busy / 1e3:.2f} ms, idle {sum(g[0] for g in gaps) / 1e3:.2f} ms over {len(gaps)} gaps")
+    big = sorted(gaps, key=lambda g: -g[0])[:14]
+    for g in big:
+        print(f"{g[0]:8.1f} us  after {g[1]}  before {g[2]}")
+    small = [g[0] for g in gaps if g[0] < 10]
+    print(f"{len(small)} gaps under 10 us, mean {sum(small) / max(len(small), 1):.2f} us, total {sum(small) / 1e3:.2f} ms")

@@ -19,7 +19,6 @@ namespace spr {
 namespace {
 
 constexpr int HD = 32;       // head dimension
-constexpr int BQ = 64;       // query rows per CTA
 constexpr int BK = 64;       // key rows per shared-memory tile
 constexpr int PLANE_BYTES = BK * HD * 2;  // one fp16 plane of a tile: 4 KB
 

@@ -180,15 +180,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
     // i are in flight while group i is reduced, so the per-tile latency chain is one TMEM round trip, not sixteen.
     const int qd = warp & 3;                       // TMEM lane quadrant this warp may read
     const int chalf = (warp - 2) >> 2;             // which 64 columns of the tile
-    const int row = qd * 32 + lane;                // stacked row: token 2r = hi, 2r+1 = lo
-    const int tok_l = row >> 1;
+    // TMEM lane qd * 32 + lane is stacked row 2r (hi) / 2r + 1 (lo) of token r
     const int half_sel = lane & 1;                 // even lane stores columns c0..c0+3, odd lane c0+4..c0+7
     int it = 0;
     for (int tile = first; tile < limit; tile += step, ++it) {
       const int buf = it & 1;
       const int mt = resident ? tile : tile / n_tiles, nt = resident ? nt_fixed : tile % n_tiles;
-      const int token = mt * BM_TOK + tok_l;
-      const bool tok_ok = token < g.T;
       const bool erec = dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 60;
       if (erec) g_gemm_dbg[1024 + it * 4 + 0] = clock64();
       mbar_wait(&bar_accf[buf], (it >> 1) & 1);

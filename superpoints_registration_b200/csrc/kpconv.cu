@@ -47,17 +47,9 @@ __device__ __forceinline__ int load_idx(const IdxT* __restrict__ p) {
   return (int)__ldg(p);
 }
 
-// influence of kernel point (kx,ky,kz) on the centred neighbour (cx,cy,cz); fp32, reference op order
-// (kpconv_blocks.py:325-329 differences**2 summed over xyz, :368 clamp(1 - sqrt(d2)/extent, min=0))
-__device__ __forceinline__ float influence(float cx, float cy, float cz, float kx, float ky, float kz, float extent) {
-  const float dx = cx - kx, dy = cy - ky, dz = cz - kz;
-  const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-  const float v = 1.f - __fdiv_rn(__fsqrt_rn(d2), extent);
-  return fmaxf(v, 0.f);
-}
-
-// Same quantity on the fast path of the fused kernel: FMA-contracted distance, MUFU.RSQ square root and a
-// multiplication by 1/extent.  Differs from the exactly-rounded expression by a few ulp of the influence
+// Influence of kernel point (kx,ky,kz) on the centred neighbour (cx,cy,cz): kpconv_blocks.py:325-329 (differences**2
+// summed over xyz) and :368 (clamp(1 - sqrt(d2)/extent, min=0)), evaluated with an FMA-contracted distance, the
+// MUFU square root and a multiplication by 1/extent.  Differs from the exactly-rounded expression by a few ulp of the influence
 // (<= ~3e-7 absolute on values in [0,1]), far inside the feature tolerance, and costs ~10 instructions
 // instead of ~28 (IEEE sqrt and division are multi-instruction sequences).
 __device__ __forceinline__ float influence_fast(float cx, float cy, float cz, float kx, float ky, float kz,

@@ -96,25 +96,6 @@ struct SinkElem {
   }
 };
 
-__device__ __forceinline__ void online_add(float& m, float& s, float v) {
-  if (v > m) {
-    s = s * __expf(m - v) + 1.f;
-    m = v;
-  } else {
-    s += __expf(v - m);
-  }
-}
-__device__ __forceinline__ void online_merge(float& m, float& s, float m2, float s2) {
-  if (m2 == -INFINITY) return;
-  if (m == -INFINITY) {
-    m = m2;
-    s = s2;
-    return;
-  }
-  const float mm = fmaxf(m, m2);
-  s = s * __expf(m - mm) + s2 * __expf(m2 - mm);
-  m = mm;
-}
 
 // Two-pass (max then sum) statistics per row: exact expf, matches torch.softmax / logsumexp numerics closely.
 template <typename F>

@@ -27,7 +27,7 @@ constexpr int kStage = 320;  // staged hits per warp (>= 2*SPR_MAX_NEIGHBOR_LIMI
 constexpr int kMaxDim = 1024;
 
 struct CellGrid {  // per cloud
-  float lox, loy, loz, cell;
+  float lox, loy, loz, inv_cell;  // cell edge stored as its reciprocal: coordinates are one subtract + one multiply
   int dx, dy, dz;
   int base;  // first cell of this cloud in the global cell table
 };
@@ -127,7 +127,7 @@ __global__ void k_plan_grids(const uint32_t* __restrict__ bb, const int* __restr
       g.lox = lo[0];
       g.loy = lo[1];
       g.loz = lo[2];
-      g.cell = cell;
+      g.inv_cell = 1.f / cell;
       g.dx = d[0];
       g.dy = d[1];
       g.dz = d[2];
@@ -155,9 +155,10 @@ __global__ void k_plan_grids(const uint32_t* __restrict__ bb, const int* __restr
   if (threadIdx.x == 0) hdr->total_cells = carry;
 }
 
-__device__ __forceinline__ int cell_coord(float p, float lo, float cell, int dim) {
-  // fp32, same expression at build and query time
-  float u = floorf(__fdiv_rn(__fsub_rn(p, lo), cell));
+__device__ __forceinline__ int cell_coord(float p, float lo, float inv_cell, int dim) {
+  // fp32, same expression at build and query time.  The quotient is off by < 1e-6 relative, the cell edge exceeds
+  // the radius by 1/256: two points within the radius still land at most one cell apart (floor is monotonic).
+  float u = floorf(__fmul_rn(__fsub_rn(p, lo), inv_cell));
   u = fminf(fmaxf(u, -2.f), (float)dim + 1.f);
   return (int)u;
 }
@@ -169,9 +170,9 @@ __global__ void __launch_bounds__(kThreads)
   if (i >= n) return;
   const int b = find_cloud(offs, B, i);
   const CellGrid g = grids[b];
-  int cx = min(max(cell_coord(s[3 * (size_t)i + 0], g.lox, g.cell, g.dx), 0), g.dx - 1);
-  int cy = min(max(cell_coord(s[3 * (size_t)i + 1], g.loy, g.cell, g.dy), 0), g.dy - 1);
-  int cz = min(max(cell_coord(s[3 * (size_t)i + 2], g.loz, g.cell, g.dz), 0), g.dz - 1);
+  int cx = min(max(cell_coord(s[3 * (size_t)i + 0], g.lox, g.inv_cell, g.dx), 0), g.dx - 1);
+  int cy = min(max(cell_coord(s[3 * (size_t)i + 1], g.loy, g.inv_cell, g.dy), 0), g.dy - 1);
+  int cz = min(max(cell_coord(s[3 * (size_t)i + 2], g.loz, g.inv_cell, g.dz), 0), g.dz - 1);
   const int c = g.base + (cz * g.dy + cy) * g.dx + cx;
   point_cell[i] = c;
   atomicAdd(cell_cnt + c, 1);
@@ -219,25 +220,29 @@ __device__ __forceinline__ int compact_stage(unsigned long long* __restrict__ sk
 }
 
 template <typename IdxT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
     k_radius_query(const float* __restrict__ q, const int* __restrict__ q_offs, int B, int nq,
                    const CellGrid* __restrict__ grids, const int* __restrict__ cell_start,
                    const float4* __restrict__ sorted, int ns_total, float r2, int limit, IdxT* __restrict__ out,
                    int row_stride, int* __restrict__ max_count) {
-  __shared__ unsigned long long s_k[kWarpsPerBlock][kStage];
+  __shared__ __align__(16) unsigned long long s_k[kWarpsPerBlock][kStage];
   __shared__ int s_beg[kWarpsPerBlock][9];
-  __shared__ int s_pre[kWarpsPerBlock][10];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long* sk = s_k[warp];
   int block_max = 0;
 
   for (int qi = blockIdx.x * kWarpsPerBlock + warp; qi < nq; qi += gridDim.x * kWarpsPerBlock) {
-    const int b = find_cloud(q_offs, B, qi);
+    // cloud of the query: the lanes compare the end offsets of 32 clouds at a time
+    int b = 0;
+    for (int c0 = 0; c0 < B; c0 += 32) {
+      const int end = c0 + lane < B ? __ldg(q_offs + c0 + lane + 1) : 0x7fffffff;
+      b += __popc(__ballot_sync(kFull, end <= qi));
+    }
     const CellGrid g = grids[b];
     const float px = __ldg(q + 3 * (size_t)qi), py = __ldg(q + 3 * (size_t)qi + 1), pz = __ldg(q + 3 * (size_t)qi + 2);
-    const int cx = cell_coord(px, g.lox, g.cell, g.dx);
-    const int cy = cell_coord(py, g.loy, g.cell, g.dy);
-    const int cz = cell_coord(pz, g.loz, g.cell, g.dz);
+    const int cx = cell_coord(px, g.lox, g.inv_cell, g.dx);
+    const int cy = cell_coord(py, g.loy, g.inv_cell, g.dy);
+    const int cz = cell_coord(pz, g.loz, g.inv_cell, g.dz);
 
     // 9 runs: lane r -> (dz, dy) = (r/3-1, r%3-1)
     int beg = 0, len = 0;
@@ -250,19 +255,18 @@ __global__ void __launch_bounds__(kThreads)
         len = __ldg(cell_start + row + xhi + 1) - beg;
       }
     }
-    int inc = len;
+    int inc = len;  // inclusive prefix of the run lengths over lanes 0..8
 #pragma unroll
     for (int o = 1; o < 16; o <<= 1) {
       int t = __shfl_up_sync(kFull, inc, o);
       if (lane >= o) inc += t;
     }
-    if (lane < 9) {
-      s_beg[warp][lane] = beg;
-      s_pre[warp][lane + 1] = inc;
-    }
-    if (lane == 0) s_pre[warp][0] = 0;
+    if (lane < 9) s_beg[warp][lane] = beg - (inc - len);  // candidate t of run r lives at sorted[s_beg[r] + t]
     __syncwarp();
-    const int total = s_pre[warp][9];
+    int pre[8];  // pre[k] = first flat candidate index of run k + 1, in registers for the run lookup of every pass
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pre[k] = __shfl_sync(kFull, inc, k);
+    const int total = __shfl_sync(kFull, inc, 8);
 
     int cnt = 0;         // staged hits
     int in_radius = 0;   // all hits (for max_count)
@@ -274,8 +278,8 @@ __global__ void __launch_bounds__(kThreads)
       if (t < total) {
         int r = 0;
 #pragma unroll
-        for (int k = 1; k < 9; ++k) r += (t >= s_pre[warp][k]) ? 1 : 0;
-        const float4 c = __ldg(sorted + s_beg[warp][r] + (t - s_pre[warp][r]));
+        for (int k = 0; k < 8; ++k) r += (t >= pre[k]) ? 1 : 0;
+        const float4 c = __ldg(sorted + s_beg[warp][r] + t);
         const float d2 = sqdist_exact(px, py, pz, c.x, c.y, c.z);
         hit = d2 < r2;
         key = make_key(d2, __float_as_int(c.w));
@@ -304,14 +308,32 @@ __global__ void __launch_bounds__(kThreads)
 
     // rank the staged hits and emit the row
     IdxT* __restrict__ row = out + (size_t)qi * row_stride;
-    if (cnt <= 64) {
-      // common case: a lane owns staged hits `lane` and `lane + 32`; ONE pass over the stage ranks both
+    if (cnt <= 32) {
+      // most rows: one staged hit per lane, ranked by counting the smaller keys (two keys per 16-byte load)
+      const unsigned long long k0 = lane < cnt ? sk[lane] : ~0ull;
+      if (lane == 0) sk[cnt] = ~0ull;  // sentinel for the odd tail (kStage > 32, slot cnt is free)
+      __syncwarp();
+      int r0 = 0;
+      const ulonglong2* sk2 = reinterpret_cast<const ulonglong2*>(sk);
+      for (int f = 0; f < cnt; f += 2) {
+        const ulonglong2 kf = sk2[f >> 1];
+        r0 += kf.x < k0 ? 1 : 0;
+        r0 += kf.y < k0 ? 1 : 0;
+      }
+      if (lane < cnt && r0 < limit) row[r0] = (IdxT)(unsigned int)k0;
+    } else if (cnt <= 64) {
+      // a lane owns staged hits `lane` and `lane + 32`; ONE pass over the stage ranks both
       const unsigned long long k0 = lane < cnt ? sk[lane] : ~0ull, k1 = lane + 32 < cnt ? sk[lane + 32] : ~0ull;
+      if (lane == 0) sk[cnt] = ~0ull;  // sentinel for the odd tail
+      __syncwarp();
       int r0 = 0, r1 = 0;
-      for (int f = 0; f < cnt; ++f) {
-        const unsigned long long kf = sk[f];
-        r0 += kf < k0 ? 1 : 0;
-        r1 += kf < k1 ? 1 : 0;
+      const ulonglong2* sk2 = reinterpret_cast<const ulonglong2*>(sk);
+      for (int f = 0; f < cnt; f += 2) {
+        const ulonglong2 kf = sk2[f >> 1];
+        r0 += kf.x < k0 ? 1 : 0;
+        r1 += kf.x < k1 ? 1 : 0;
+        r0 += kf.y < k0 ? 1 : 0;
+        r1 += kf.y < k1 ? 1 : 0;
       }
       if (lane < cnt && r0 < limit) row[r0] = (IdxT)(unsigned int)k0;
       if (lane + 32 < cnt && r1 < limit) row[r1] = (IdxT)(unsigned int)k1;

@@ -45,8 +45,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // for the single-thread role warps, whose waits are long: back off so the spin does not take issue slots
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns = 64) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
 }
 
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core / TMA reads)

@@ -567,11 +567,11 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int pass = 0; pass < K::PASSES; ++pass, ++seq) {
-          mbar_wait_sleep(bar_afull, seq & 1, kRoleSleepNs);
+          mbar_wait_sleep(bar_afull, seq & 1);
           tc_fence_after();
           for (int a = 0; a < 8; ++a) {
             for (int sub = 0; sub < K::NSUB; ++sub) {
-              mbar_wait_sleep(&bar_full[stage], phase, kRoleSleepNs);
+              mbar_wait_sleep(&bar_full[stage], phase);
               tc_fence_after();
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int blk = 0; blk < K::PASSES * K::BLOCKS_PER_PASS; ++blk) {
-          mbar_wait_sleep(&bar_empty[stage], phase ^ 1, kRoleSleepNs);
+          mbar_wait_sleep(&bar_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bar_full[stage], K::STAGE_BYTES);
           bulk_g2s(sRing + stage * K::STAGE_BYTES, wimg + (size_t)blk * K::STAGE_BYTES, K::STAGE_BYTES,
                    &bar_full[stage]);

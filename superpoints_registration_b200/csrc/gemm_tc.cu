@@ -12,8 +12,10 @@
 // K <= 256 (every projection of the cross-encoder except FFN2): the CTA is pinned to ONE n tile, loads that tile's
 // whole W image (<= 128 KB) into shared memory once and streams only A tiles afterwards -- the kernel is bound by
 // L2 -> SM operand traffic, and this cuts it 3x.  Larger K streams W through the ring with A.
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-9 = epilogue.
-// Two accumulator buffers (2 x 256 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-17 = epilogue in two
+// sets of 8, one per accumulator buffer (2 x 256 TMEM columns): the tiles of a CTA alternate between the sets, so
+// two tiles are drained concurrently while the MMAs of the next run (the epilogue, not the MMA, bounds the encoder's
+// tall-skinny GEMMs).
 // The epilogue can emit fp32 rows, fp16 hi/lo planes (for the attention kernel), or the A image of the next GEMM.
 #include "spr_common.cuh"
 #include "tc05.cuh"
@@ -29,10 +31,11 @@ constexpr int BM_TOK = 64;                 // tokens per tile (128 stacked rows)
 constexpr int BN = 128;                    // output columns per tile (256 B rows: hi | lo)
 constexpr int A_STAGE = 128 * 128;         // 16 KB
 constexpr int B_STAGE = 2 * 128 * 128;     // 32 KB
-constexpr int NSTAGES = 4;
-constexpr int EPI_WARPS = 8;               // 2 per TMEM lane quadrant, each owning 64 of the 128 tile columns
+constexpr int NSTAGES = 3;
+constexpr int EPI_SET = 8;                 // warps per epilogue set: 2 per TMEM lane quadrant, each owning 64 tile columns
+constexpr int EPI_WARPS = 2 * EPI_SET;     // two sets, one per accumulator buffer: tiles i and i+1 are drained concurrently
 constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;
-constexpr int RES_STAGES = 4;               // A ring depth when W is resident
+constexpr int RES_STAGES = 3;               // A ring depth when W is resident
 constexpr int RES_KA = 4;                   // W atoms kept resident (K <= 256)
 constexpr int EPI_ROW = 36;                 // floats per staged row (32 + 4 padding: conflict-free 16-byte accesses)
 constexpr int EPI_STAGE_BYTES = 16 * EPI_ROW * 4;   // per epilogue warp: 16 tokens x 32 columns
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_accf[i], 1);
-      mbar_init(&bar_acce[i], EPI_WARPS);
+      mbar_init(&bar_acce[i], EPI_SET);
     }
     mbar_init(bar_w, 1);
     fence_mbar_init();
@@ -179,12 +182,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
     // Software-pipelined over 8-column groups: the TMEM loads of group i+1 and the bias / residual loads of group
     // i are in flight while group i is reduced, so the per-tile latency chain is one TMEM round trip, not sixteen.
     const int qd = warp & 3;                       // TMEM lane quadrant this warp may read
-    const int chalf = (warp - 2) >> 2;             // which 64 columns of the tile
+    const int ew = warp - 2;
+    const int set = ew / EPI_SET;                  // accumulator buffer (= tile parity) this warp drains
+    const int chalf = (ew >> 2) & 1;               // which 64 columns of the tile
     // TMEM lane qd * 32 + lane is stacked row 2r (hi) / 2r + 1 (lo) of token r
     const int half_sel = lane & 1;                 // even lane stores columns c0..c0+3, odd lane c0+4..c0+7
-    int it = 0;
-    for (int tile = first; tile < limit; tile += step, ++it) {
-      const int buf = it & 1;
+    for (int it = set, tile = first + set * step; tile < limit; tile += 2 * step, it += 2) {
+      const int buf = set;
       const int mt = resident ? tile : tile / n_tiles, nt = resident ? nt_fixed : tile % n_tiles;
       const bool erec = dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 60;
       if (erec) g_gemm_dbg[1024 + it * 4 + 0] = clock64();
@@ -192,21 +196,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
       tc_fence_after();
       if (erec) g_gemm_dbg[1024 + it * 4 + 1] = clock64();
       const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16) + buf * 256 + chalf * 64;
-      // all 16 TMEM loads of this warp's 64 columns are issued back to back, then ONE wait
-      float v1[8][8], v2[8][8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        tmem_ld8(trow + i * 8, v1[i]);
-        tmem_ld8(trow + 128 + i * 8, v2[i]);
-      }
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) tmem_ld_fence(v1[i], v2[i]);
-      // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before the stores
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_acce[buf]);
-      if (erec) g_gemm_dbg[1024 + it * 4 + 2] = clock64();
       // The accumulator rows are per-lane (lane = stacked token row): writing them directly costs one memory
       // transaction per token per instruction.  Each group of 32 columns is transposed through a small per-warp
       // shared-memory stage so that global accesses (bias, residual, output) are row-contiguous: a warp
@@ -214,7 +203,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
       float* stg = s_epi + (warp - 2) * (EPI_STAGE_BYTES / 4);
 #pragma unroll
       for (int grp = 0; grp < 2; ++grp) {
-        // (skipping the empty column groups of narrow outputs with a branch here costs more than it saves)
+        // the 8 TMEM loads of this group's 32 columns (hi and lo halves) are issued back to back, then ONE wait
+        float v1[4][8], v2[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          tmem_ld8(trow + (grp * 4 + i) * 8, v1[i]);
+          tmem_ld8(trow + 128 + (grp * 4 + i) * 8, v2[i]);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tmem_ld_fence(v1[i], v2[i]);
+        if (grp == 1) {
+          // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_acce[buf]);
+          if (erec) g_gemm_dbg[1024 + it * 4 + 2] = clock64();
+        }
         // bias and residual of this group's coalesced phase are requested first: their latency overlaps the transpose
         const int pcol = nt * BN + chalf * 64 + grp * 32 + (lane & 7) * 4;
         float4 pbias = make_float4(0.f, 0.f, 0.f, 0.f), pres[4];
@@ -228,11 +233,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
         }
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) {
-          const int i = grp * 4 + ii;
           float sum[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            sum[e] = v1[i][e] + v2[i][e];
+            sum[e] = v1[ii][e] + v2[ii][e];
             sum[e] += __shfl_xor_sync(kFull, sum[e], 1);
           }
           const float4 y = half_sel ? make_float4(sum[4], sum[5], sum[6], sum[7]) : make_float4(sum[0], sum[1], sum[2], sum[3]);

@@ -311,3 +311,46 @@ def test_kpconv_tensor_core_wide_rows():
     out = ops.kpconv_forward(_t(q), _t(s), _t(idx), _t(x), _t(w), _t(kp), 0.3, mode=1).cpu().numpy()
     exact = oracle.kpconv_forward(q, s, idx, x, w, kp, 0.3)
     assert np.abs(out - exact).max() <= FEAT_RTOL * np.abs(exact).max()
+
+
+def test_kpconv_full_size_properties():
+    """BASELINE-size layer (level 1 of the 32-pair bench step: ~300k queries, H = 40, C = 64): properties that do
+    not need a CPU evaluation -- linearity in the features, invariance to the order of a row's neighbours,
+    independence of rows, shadow columns contributing nothing -- plus a sampled comparison with the oracle."""
+    rng = np.random.default_rng(99)
+    n, H, c = 300_000, 40, 64
+    # a random walk: rows close in index are close in space, so the +-60-row neighbourhoods below give kernel-point
+    # influences of every size between 0 and 1
+    pts = np.cumsum(rng.normal(0, 0.01, size=(n, 3)), axis=0).astype(np.float32)
+    idx = (np.arange(n)[:, None] + rng.integers(-60, 60, size=(n, H))).clip(0, n - 1)
+    idx[rng.uniform(size=(n, H)) < 0.2] = n                                # shadow entries anywhere in the row
+    idx.sort(axis=1)                                                        # shadows last, like the searcher writes
+    x1 = rng.normal(size=(n, c)).astype(np.float32)
+    x2 = rng.normal(size=(n, c)).astype(np.float32)
+    w = (rng.normal(size=(15, c, c)) / np.sqrt(15 * c)).astype(np.float32)
+    kp = (rng.normal(size=(15, 3)) * 0.05).astype(np.float32)
+    ext = 0.12
+    tp, tw, tk = _t(pts), _t(w), _t(kp)
+    f = lambda x, ind: ops.kpconv_forward(tp, tp, ind, x, tw, tk, ext, mode=1)
+    ti = _t(idx)
+    y1, y2 = f(_t(x1), ti), f(_t(x2), ti)
+    scale = y1.abs().max().item()
+    assert scale > 1e-3
+    # linearity.  The neighbour count divides by #{h: rowsum(x) > 0} (kpconv_blocks.py:409-412), which is not
+    # linear, so the check uses inputs whose row sums are all positive for x1, x2 and the combination
+    p1, p2 = np.abs(x1) + 0.1, np.abs(x2) + 0.1
+    z1, z2, z12 = f(_t(p1), ti), f(_t(p2), ti), f(_t(2.0 * p1 + 0.5 * p2), ti)
+    assert (z12 - (2.0 * z1 + 0.5 * z2)).abs().max().item() <= 2e-5 * z12.abs().max().item()
+    # neighbour order inside a row does not matter (a sum over h)
+    perm = rng.permutation(H)
+    yp = f(_t(x1), _t(np.ascontiguousarray(idx[:, perm])))
+    assert (yp - y1).abs().max().item() <= 2e-5 * scale
+    # rows are independent: changing the neighbours of the second half leaves the first half bit-identical
+    idx2 = idx.copy()
+    idx2[n // 2:] = n
+    yh = f(_t(x1), _t(idx2))
+    assert torch.equal(yh[: n // 2], y1[: n // 2]) and yh[n // 2:].abs().max().item() == 0.0
+    # sampled rows against the fp64-accumulated oracle
+    rows = rng.choice(n, size=512, replace=False)
+    exact = oracle.kpconv_forward(pts[rows], pts, idx[rows], x1, w, kp, ext)
+    assert np.abs(y1[_t(rows)].cpu().numpy() - exact).max() <= FEAT_RTOL * np.abs(exact).max()

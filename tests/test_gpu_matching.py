@@ -262,3 +262,59 @@ def test_full_forward_against_golden(golden_dir):
         rot, tr = pose_error(out["pose"].cpu().numpy(), g["pose"])
         print(f"[{tag}] end-to-end pose difference vs reference: rot {rot.max():.2e} deg, trans {tr.max():.2e} m")
         assert rot.max() < 0.05 and tr.max() < 1e-3, (tag, rot, tr)
+
+
+@pytest.mark.parametrize("kind,cfg,kw", [("3dlomatch", cfgs.threedmatch_config(), dict(n_points=4000)),
+                                         ("kitti", cfgs.kitti_config(), dict(n_points=6000))])
+def test_forward_lomatch_and_kitti_shapes_against_oracle(kind, cfg, kw):
+    """BASELINE configs[3] (low-overlap 3DLoMatch-shape pairs, Sinkhorn) and configs[4] (KITTI-shape scans, 4-stage,
+    wide neighbourhoods, argmax + Procrustes) through the whole CUDA forward against the CPU restatement of the
+    reference network on the same clouds and weights (reduced point counts so that the CPU side runs in seconds)."""
+    from oracle import pipeline
+    from superpoints_registration_b200 import synthetic
+    torch.manual_seed(7)
+    model = RegTR(cfg).to(DEV).eval()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    data = synthetic.make_batch(kind, 2, seed=3, **kw)
+    B = len(data["src_xyz"])
+    out = model({"src_xyz": [_t(c) for c in data["src_xyz"]], "tgt_xyz": [_t(c) for c in data["tgt_xyz"]]})
+    exact = pipeline.forward(sd, cfg, data["src_xyz"], data["tgt_xyz"], backend="port")
+    sp_alpha, e_beta = float(np.log1p(np.exp(sd["alpha"].item()))), float(np.exp(sd["beta"].item()))
+    for i in range(B):
+        S, T = out["src_feat"][i][0].cpu().numpy(), out["tgt_feat"][i][0].cpu().numpy()
+        assert S.shape == exact["src_feat"][i].shape and T.shape == exact["tgt_feat"][i].shape   # same superpoints
+        ref_scale = max(np.abs(exact["src_feat"][i]).max(), np.abs(exact["tgt_feat"][i]).max())
+        assert np.abs(S - exact["src_feat"][i]).max() <= 2e-3 * ref_scale                        # conditioned features
+        assert np.abs(T - exact["tgt_feat"][i]).max() <= 2e-3 * ref_scale
+        # stage-wise: OUR features through the fp64 restatement of matching + pose
+        sx, tx = out["src_kp"][i].cpu().numpy(), out["tgt_kp"][i].cpu().numpy()
+        corr, _, _, ind_o = numpy_ops.dual_softmax_match(S, T, dtype=np.float64)
+        if cfg.use_sinkhorn:
+            wt, w = numpy_ops.sinkhorn_weighted_targets(corr, tx, sp_alpha, e_beta, cfg.sinkhorn_itr, dtype=np.float64)
+            pose64 = numpy_ops.compute_rigid_transform(sx, wt, w, dtype=np.float64)
+            wt32, w32 = numpy_ops.sinkhorn_weighted_targets(corr.astype(np.float32), tx, sp_alpha, e_beta, cfg.sinkhorn_itr)
+            pose32 = numpy_ops.compute_rigid_transform(sx, wt32, w32)
+        else:
+            # untrained weights make the argmax a lottery between nearly equal attention values: the pose solve is
+            # checked on OUR correspondences and weights, the correspondences and weights themselves below
+            got = out["ind_list"][i].cpu().numpy()
+            val = out["overlap_prob_list"][i].cpu().numpy()
+            a, b = (sx[got], tx) if len(S) > len(T) else (sx, tx[got])
+            pose64 = numpy_ops.compute_rigid_transform(a, b, val.astype(np.float64), dtype=np.float64)
+            pose32 = numpy_ops.compute_rigid_transform(a, b, val)
+            v_o = _v64(corr, 0 if len(S) > len(T) else 1)
+            same = got == ind_o
+            assert same.mean() > 0.99
+            assert np.allclose(val[same], v_o[same], rtol=5e-4, atol=1e-12)
+            # where the argmax differs, the two candidates are within fp32 noise of each other
+            attn = numpy_ops._softmax(corr, 0) * numpy_ops._softmax(corr, 1)
+            for k in np.nonzero(~same)[0]:
+                x, y = (attn[got[k], k], attn[ind_o[k], k]) if len(S) > len(T) else (attn[k, got[k]], attn[k, ind_o[k]])
+                assert abs(x - y) <= 1e-4 * abs(y)
+        noise_rot, noise_tr = pose_error(pose32, pose64)           # what fp32 evaluation of the same formulas costs
+        rot, tr = pose_error(out["pose"][i].cpu().numpy(), pose64)
+        scale = max(1.0, float(np.abs(tx).max()))
+        print(f"[{kind}] pair {i}: N={len(S)} M={len(T)} ours vs exact {rot:.2e} deg / {tr:.2e} m (fp32 noise "
+              f"{noise_rot:.2e} / {noise_tr:.2e})")
+        assert rot <= max(ROT_TOL_DEG, 4 * noise_rot) and tr <= max(TRANS_TOL * scale, 4 * noise_tr), (kind, i, rot, tr)
+    assert tuple(out["pose"].shape) == (B, 3, 4) and torch.isfinite(out["pose"]).all()

@@ -139,6 +139,75 @@ __global__ void k_cloud_offsets(const int32_t* __restrict__ lens, int B, int32_t
   if (threadIdx.x == 0) offs[B] = carry;
 }
 
+namespace {
+__global__ void k_bbox_init(uint32_t* __restrict__ bb, int B) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * 3) {
+    bb[i] = 0xffffffffu;  // min
+    bb[B * 3 + i] = 0u;   // max
+  }
+}
+
+constexpr int kBboxChunk = 256;  // points per warp
+
+// A warp folds a contiguous chunk of points in registers and issues six atomics when the chunk lies in one cloud
+// (all but 2 B of the chunks); a chunk that straddles a cloud boundary falls back to per-point atomics.
+__global__ void __launch_bounds__(256) k_bbox(const float* __restrict__ pts, const int* __restrict__ offs, int B, int n,
+                                              uint32_t* __restrict__ bb) {
+  const int lane = threadIdx.x & 31;
+  const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kBboxChunk;
+  if (base >= n) return;
+  const int end = min(base + kBboxChunk, n);
+  const int b0 = find_cloud(offs, B, base), b1 = find_cloud(offs, B, end - 1);
+  if (b0 == b1) {
+    uint32_t mnx = 0xffffffffu, mny = mnx, mnz = mnx, mxx = 0u, mxy = 0u, mxz = 0u;
+    for (int i = base + lane; i < end; i += 32) {
+      const uint32_t x = f2ord(pts[3 * (size_t)i]), y = f2ord(pts[3 * (size_t)i + 1]), z = f2ord(pts[3 * (size_t)i + 2]);
+      mnx = min(mnx, x); mny = min(mny, y); mnz = min(mnz, z);
+      mxx = max(mxx, x); mxy = max(mxy, y); mxz = max(mxz, z);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+      mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+      mnz = min(mnz, __shfl_xor_sync(0xffffffffu, mnz, o));
+      mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+      mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+      mxz = max(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
+    }
+    if (lane == 0) {
+      atomicMin(bb + 3 * b0 + 0, mnx);
+      atomicMin(bb + 3 * b0 + 1, mny);
+      atomicMin(bb + 3 * b0 + 2, mnz);
+      atomicMax(bb + 3 * (B + b0) + 0, mxx);
+      atomicMax(bb + 3 * (B + b0) + 1, mxy);
+      atomicMax(bb + 3 * (B + b0) + 2, mxz);
+    }
+  } else {
+    for (int i = base + lane; i < end; i += 32) {
+      const int b = find_cloud(offs, B, i);
+      const uint32_t x = f2ord(pts[3 * (size_t)i]), y = f2ord(pts[3 * (size_t)i + 1]), z = f2ord(pts[3 * (size_t)i + 2]);
+      atomicMin(bb + 3 * b + 0, x);
+      atomicMin(bb + 3 * b + 1, y);
+      atomicMin(bb + 3 * b + 2, z);
+      atomicMax(bb + 3 * (B + b) + 0, x);
+      atomicMax(bb + 3 * (B + b) + 1, y);
+      atomicMax(bb + 3 * (B + b) + 2, z);
+    }
+  }
+}
+}  // namespace
+
+// bb[3 b + a] / bb[3 (B + b) + a] = ordered-int min / max of coordinate a over cloud b (f2ord / ord2f)
+int cloud_bboxes(const float* d_pts, const int32_t* d_offs, int B, int n, uint32_t* d_bb, cudaStream_t stream) {
+  k_bbox_init<<<(B * 3 + 255) / 256, 256, 0, stream>>>(d_bb, B);
+  SPR_LAUNCH_CHECK("k_bbox_init");
+  const int warps = (n + kBboxChunk - 1) / kBboxChunk;
+  k_bbox<<<(warps + 7) / 8, 256, 0, stream>>>(d_pts, d_offs, B, n, d_bb);
+  SPR_LAUNCH_CHECK("k_bbox");
+  return SPR_OK;
+}
+
 int cloud_offsets(const int32_t* d_lens, int B, int32_t* d_offs, cudaStream_t stream) {
   k_cloud_offsets<<<1, 256, 0, stream>>>(d_lens, B, d_offs);
   SPR_LAUNCH_CHECK("k_cloud_offsets");

@@ -31,57 +31,6 @@ __device__ __forceinline__ unsigned long long f2u64(float v) {
   return (unsigned long long)(long long)v;
 }
 
-__global__ void k_bbox_init(uint32_t* __restrict__ bb, int B) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B * 3) {
-    bb[i] = 0xffffffffu;          // min
-    bb[B * 3 + i] = 0u;           // max
-  }
-}
-
-__global__ void __launch_bounds__(kThreads) k_bbox(const float* __restrict__ pts, const int* __restrict__ offs, int B,
-                                                   int n, uint32_t* __restrict__ bb) {
-  // Each block covers a contiguous chunk of points; reduce per cloud within the warp when the whole warp
-  // is in one cloud (the common case), fall back to per-thread atomics at cloud boundaries.
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = i < n;
-  int b = valid ? find_cloud(offs, B, i) : -1;
-  float x = 0, y = 0, z = 0;
-  if (valid) {
-    x = pts[3 * (size_t)i];
-    y = pts[3 * (size_t)i + 1];
-    z = pts[3 * (size_t)i + 2];
-  }
-  const int b0 = __shfl_sync(kFull, b, 0);
-  const bool uniform = __all_sync(kFull, b == b0) && b0 >= 0;
-  if (uniform) {
-    uint32_t mnx = f2ord(x), mny = f2ord(y), mnz = f2ord(z), mxx = mnx, mxy = mny, mxz = mnz;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mnx = min(mnx, __shfl_xor_sync(kFull, mnx, o));
-      mny = min(mny, __shfl_xor_sync(kFull, mny, o));
-      mnz = min(mnz, __shfl_xor_sync(kFull, mnz, o));
-      mxx = max(mxx, __shfl_xor_sync(kFull, mxx, o));
-      mxy = max(mxy, __shfl_xor_sync(kFull, mxy, o));
-      mxz = max(mxz, __shfl_xor_sync(kFull, mxz, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-      atomicMin(bb + 3 * b0 + 0, mnx);
-      atomicMin(bb + 3 * b0 + 1, mny);
-      atomicMin(bb + 3 * b0 + 2, mnz);
-      atomicMax(bb + 3 * (B + b0) + 0, mxx);
-      atomicMax(bb + 3 * (B + b0) + 1, mxy);
-      atomicMax(bb + 3 * (B + b0) + 2, mxz);
-    }
-  } else if (valid) {
-    atomicMin(bb + 3 * b + 0, f2ord(x));
-    atomicMin(bb + 3 * b + 1, f2ord(y));
-    atomicMin(bb + 3 * b + 2, f2ord(z));
-    atomicMax(bb + 3 * (B + b) + 0, f2ord(x));
-    atomicMax(bb + 3 * (B + b) + 1, f2ord(y));
-    atomicMax(bb + 3 * (B + b) + 2, f2ord(z));
-  }
-}
 
 __global__ void k_cloud_grid(const uint32_t* __restrict__ bb, int B, float dl, CloudGrid* __restrict__ g) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -316,10 +265,8 @@ extern "C" int spr_grid_subsample_batch(const float* d_points, const int32_t* d_
 
   int rc = cloud_offsets(d_lengths, B, offs, stream);
   if (rc) return rc;
-  k_bbox_init<<<(B * 3 + 255) / 256, 256, 0, stream>>>(bb, B);
-  SPR_LAUNCH_CHECK("k_bbox_init");
-  k_bbox<<<gp, kThreads, 0, stream>>>(d_points, offs, B, n, bb);
-  SPR_LAUNCH_CHECK("k_bbox");
+  rc = cloud_bboxes(d_points, offs, B, n, bb, stream);
+  if (rc) return rc;
   k_cloud_grid<<<(B + 127) / 128, 128, 0, stream>>>(bb, B, sample_dl, grids);
   SPR_LAUNCH_CHECK("k_cloud_grid");
   SPR_CUDA(cudaMemsetAsync(slot_rep, 0xff, (size_t)T * 4, stream));  // -1

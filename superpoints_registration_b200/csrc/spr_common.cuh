@@ -136,6 +136,8 @@ int exclusive_scan_i32(const int32_t* d_in, int32_t* d_out, size_t n, int32_t* d
                        cudaStream_t stream);
 // offs[0..B] = exclusive prefix of lens[0..B-1] (single small kernel).
 int cloud_offsets(const int32_t* d_lens, int B, int32_t* d_offs, cudaStream_t stream);
+// per-cloud bounding boxes as ordered ints: bb[3 b + a] = min, bb[3 (B + b) + a] = max of coordinate a
+int cloud_bboxes(const float* d_pts, const int32_t* d_offs, int B, int n, uint32_t* d_bb, cudaStream_t stream);
 
 
 // kpconv_tc.cu: tensor-core (tcgen05) KPConv path, Cin = Cout = c in {32, 64, 128, 256}

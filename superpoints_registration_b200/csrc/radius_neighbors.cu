@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(kThreads, 4)
                    int row_stride, int* __restrict__ max_count) {
   __shared__ __align__(16) unsigned long long s_k[kWarpsPerBlock][kStage];
   __shared__ int s_beg[kWarpsPerBlock][9];
+  __shared__ int s_out[kWarpsPerBlock][SPR_MAX_NEIGHBOR_LIMIT];  // the row in rank order
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long* sk = s_k[warp];
   int block_max = 0;
@@ -259,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 
     // rank the staged hits and emit the row
     IdxT* __restrict__ row = out + (size_t)qi * row_stride;
+    int* so = s_out[warp];
     if (cnt <= 32) {
       // most rows: one staged hit per lane, ranked by counting the smaller keys (two keys per 16-byte load)
       const unsigned long long k0 = lane < cnt ? sk[lane] : ~0ull;
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 4)
         r0 += kf.x < k0 ? 1 : 0;
         r0 += kf.y < k0 ? 1 : 0;
       }
-      if (lane < cnt && r0 < limit) row[r0] = (IdxT)(unsigned int)k0;
+      if (lane < cnt && r0 < limit) so[r0] = (int)(unsigned int)k0;
     } else if (cnt <= 64) {
       // a lane owns staged hits `lane` and `lane + 32`; ONE pass over the stage ranks both
       const unsigned long long k0 = lane < cnt ? sk[lane] : ~0ull, k1 = lane + 32 < cnt ? sk[lane + 32] : ~0ull;
@@ -286,17 +288,21 @@ __global__ void __launch_bounds__(kThreads, 4)
         r0 += kf.y < k0 ? 1 : 0;
         r1 += kf.y < k1 ? 1 : 0;
       }
-      if (lane < cnt && r0 < limit) row[r0] = (IdxT)(unsigned int)k0;
-      if (lane + 32 < cnt && r1 < limit) row[r1] = (IdxT)(unsigned int)k1;
+      if (lane < cnt && r0 < limit) so[r0] = (int)(unsigned int)k0;
+      if (lane + 32 < cnt && r1 < limit) so[r1] = (int)(unsigned int)k1;
     } else {
       for (int e = lane; e < cnt; e += 32) {
         const unsigned long long k = sk[e];
         int r = 0;
         for (int f = 0; f < cnt; ++f) r += sk[f] < k ? 1 : 0;
-        if (r < limit) row[r] = (IdxT)(unsigned int)k;
+        if (r < limit) so[r] = (int)(unsigned int)k;
       }
     }
-    for (int j = min(cnt, limit) + lane; j < limit; j += 32) row[j] = (IdxT)ns_total;
+    // the ranks are a permutation of 0..cnt-1 (keys are distinct): the ordered row sits in shared memory and goes out
+    // as contiguous stores, shadow-padded
+    __syncwarp();
+    const int nvalid = min(cnt, limit);
+    for (int j = lane; j < limit; j += 32) row[j] = (IdxT)(j < nvalid ? so[j] : ns_total);
     __syncwarp();
   }
   if (lane == 0 && block_max > 0) atomicMax(max_count, block_max);

@@ -128,9 +128,12 @@ class CellGrid:
 
     def order(self) -> torch.Tensor:
         """int32 [ns]: the supports in (cloud, z, y, x) cell order (a spatially coherent permutation)."""
+        if getattr(self, "_order", None) is not None:
+            return self._order
         out = torch.empty(self.ns, dtype=torch.int32, device=self.supports.device)
         rc = _lib.lib().spr_cell_grid_order(self.ws.data_ptr(), self.ns, self.b, out.data_ptr(), _stream())
         _lib.check(rc, "spr_cell_grid_order")
+        self._order = out
         return out
 
     def query(self, queries: torch.Tensor, q_lengths: torch.Tensor, limit: int, radius: Optional[float] = None,

@@ -381,9 +381,12 @@ class RegTR(nn.Module):
         need_rows = (not cfg.use_sinkhorn) or cfg.get('threshold_corr', False) or cfg.get('remove_outliers_overlap', False)
         if need_rows:
             # one row per correspondence: which pair it belongs to, which side the argmax indexes
-            rows_per_pair = torch.tensor([h_off[p + 1] - h_off[p] for p in range(P)], device=dev)
-            pair_of_row = torch.repeat_interleave(torch.arange(P, device=dev), rows_per_pair)
-            gather_from_src = torch.tensor([1 if n > m else 0 for n, m in zip(src_lens, tgt_lens)], device=dev)
+            # (small host lists travel through pinned staging: torch.tensor(..., device=cuda) would block the host
+            # until the device has drained)
+            rows_per_pair = ops.to_device_async([h_off[p + 1] - h_off[p] for p in range(P)], torch.int64, dev)
+            pair_of_row = torch.repeat_interleave(torch.arange(P, device=dev), rows_per_pair,
+                                                  output_size=pairs.total_out)  # (output_size: no device read-back)
+            gather_from_src = ops.to_device_async([1 if n > m else 0 for n, m in zip(src_lens, tgt_lens)], torch.int64, dev)
             from_src = gather_from_src[pair_of_row].bool()
             base = torch.where(from_src, pairs.so[:-1][pair_of_row], pairs.to[:-1][pair_of_row] + total_src)
             local = torch.arange(pairs.total_out, device=dev) - pairs.oo[:-1][pair_of_row]
@@ -431,13 +434,13 @@ class RegTR(nn.Module):
                 a, b, val = a[keep].contiguous(), b[keep].contiguous(), val[keep].contiguous()
                 ind = keep - pairs.oo[:-1][pair_of_row[keep]].long()  # the reference reports the top-k positions
                 weights, h_off = val, new_off
-                offsets = torch.tensor(new_off, dtype=torch.int32, device=dev)
+                offsets = ops.to_device_async(new_off, torch.int32, dev)
             pose = ops.weighted_procrustes(a, b, weights, offsets)
             if cfg.get('use_lgr', False):  # :553-554 / :658-659, starting from val (not the overlap weights)
                 pose = ops.local_global_registration(a, b, val, pose, offsets, float(cfg.acceptance_radius),
                                                      int(cfg.num_refinement_steps))
             if cfg.get('use_ransac', False):  # :556-557 / :661-662: 500 hypotheses from 100 rows drawn with replacement
-                counts = torch.tensor([h_off[p + 1] - h_off[p] for p in range(P)], device=dev, dtype=torch.float32)
+                counts = ops.to_device_async([float(h_off[p + 1] - h_off[p]) for p in range(P)], torch.float32, dev)
                 u = torch.rand((P, self.ransac_hypotheses, self.ransac_sample_size), device=dev,
                                generator=self.ransac_generator)
                 idx = torch.minimum((u * counts[:, None, None]).long(), (counts[:, None, None] - 1).long())
@@ -454,8 +457,8 @@ def _segment_median(val, h_off, pair_of_row):
     P = len(h_off) - 1
     lens = [h_off[p + 1] - h_off[p] for p in range(P)]
     pad = torch.full((P, max(max(lens), 1)), float('inf'), dtype=val.dtype, device=val.device)
-    local = torch.arange(val.shape[0], device=val.device) - torch.tensor(h_off[:-1], device=val.device)[pair_of_row]
+    local = torch.arange(val.shape[0], device=val.device) - ops.to_device_async(h_off[:-1], torch.int64, val.device)[pair_of_row]
     pad[pair_of_row, local] = val
     srt, _ = torch.sort(pad, dim=1)
-    mid = torch.tensor([max(l - 1, 0) // 2 for l in lens], device=val.device)
+    mid = ops.to_device_async([max(l - 1, 0) // 2 for l in lens], torch.int64, val.device)
     return srt[torch.arange(P, device=val.device), mid][pair_of_row]

@@ -32,7 +32,7 @@
 extern "C" size_t spr_kpconv_scratch_bytes(int H, int c) {
   if (c <= 32) return 0;
   const size_t nb = (size_t)((H > 0 ? H : 1) + 7) / 8;
-  return (size_t)148 * 64 * nb * 32 * 16;
+  return (size_t)148 * 2 * 64 * nb * 32 * 16;  // per CTA: two tile buffers x 64 queries x nb blocks x 32 lanes x uint4
 }
 
 namespace spr {
@@ -283,7 +283,9 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
     // block) in an L2-resident scratch, passes 1.. of the same tile reload them instead of re-evaluating 4 influences
     // and re-fetching two packed points per block.  sFlag[ql] publishes "fragments of query ql are written".
     const int nb_max = (H + 7) >> 3;
-    uint4* frag = frag_scratch + (size_t)blockIdx.x * K::TQ * nb_max * 32;
+    // two buffers, by tile parity: a warp already in pass 0 of tile t+1 must not overwrite fragments that a slower
+    // warp still reads in the last pass of tile t (warps are at most one pass apart, see bar_done)
+    uint4* frag0 = frag_scratch + (size_t)blockIdx.x * 2 * K::TQ * nb_max * 32;
     // Epilogue of a finished tile: D (TMEM) -> registers, add the hi/lo rows (adjacent lanes) and the two column
     // halves, scale, store.  Run DEFERRED: a warp executes it for tile t-1 just before its first A-tile store of
     // tile t, when the MMAs of tile t-1 have long completed, so no producer ever idles on the tensor pipe.
@@ -386,8 +388,11 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
             qy = qny;
             qz = qnz;
             if (K::PASSES > 1 && pass > 0) {
-              while (sFlag[ql_iss] != titer + 1) {
+              // (>=: a faster warp may already have published this slot for the NEXT tile, whose fragments live in
+              // the other buffer; the flags only grow)
+              while (sFlag[ql_iss] < titer + 1) {
               }
+              __threadfence_block();  // acquire: the fragment loads below stay behind the flag
             }
           };
           auto issue_item = [&](Item& it) {
@@ -405,7 +410,9 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
             it.pa = make_float4(0.f, 0.f, 0.f, 0.f);
             it.pb = make_float4(0.f, 0.f, 0.f, 0.f);
             if (K::PASSES > 1 && pass > 0) {
-              const uint4 f = __ldcg(frag + ((size_t)ql_iss * nb_max + b) * 32 + lane);
+              // ordinary (L1-coherent within the SM) load: ld.cg would read L2, where a CTA-scope release does not
+              // promise the data yet
+              const uint4 f = *(frag0 + (((size_t)(titer & 1) * K::TQ + ql_iss) * nb_max + b) * 32 + lane);
               it.pa = make_float4(__uint_as_float(f.x), __uint_as_float(f.y), __uint_as_float(f.z), __uint_as_float(f.w));
             } else {
               if (ja >= 0) it.pa = __ldg(pts4 + ra);
@@ -460,7 +467,8 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
                 ah1 = h2_bits(h1);
                 al0 = h2_bits(l0);
                 al1 = h2_bits(l1);
-                if (K::PASSES > 1) frag[((size_t)ql * nb_max + cur.b) * 32 + lane] = make_uint4(ah0, ah1, al0, al1);
+                if (K::PASSES > 1)
+                  frag0[(((size_t)(titer & 1) * K::TQ + ql) * nb_max + cur.b) * 32 + lane] = make_uint4(ah0, ah1, al0, al1);
               }
               const uint32_t xa[4] = {cur.xa.x, cur.xa.y, cur.xa.z, cur.xa.w};
               const uint32_t xb[4] = {cur.xb.x, cur.xb.y, cur.xb.z, cur.xb.w};
@@ -510,7 +518,9 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
               *reinterpret_cast<uint4*>(atom + sw128_offset(r1, j)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
             if (K::PASSES > 1 && pass == 0) {
-              __threadfence_block();   // this lane's fragment stores before the flag
+              // release at CTA scope: the fragments are read back by other warps of this CTA with ordinary loads
+              // (same SM, same L1), after an acquire fence on the flag
+              __threadfence_block();
               __syncwarp();
               if (lane == 0) sFlag[ql] = titer + 1;
             }

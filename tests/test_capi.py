@@ -33,6 +33,24 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.EXPORTED_SYMBOLS) == _declared_symbols()
 
 
+def _declared_arity():
+    """name -> number of parameters of every prototype in include/spr_b200.h."""
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "spr_b200.h")).read(), flags=re.S)
+    out = {}
+    for name, params in re.findall(r"SPR_API[^;(]*?\b(spr_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        params = params.strip()
+        out[name] = 0 if params in ("", "void") else params.count(",") + 1
+    return out
+
+
+def test_binding_argument_counts_match_the_header():
+    """A prototype that gains a parameter must gain it in the ctypes table too (a mismatch would pass garbage)."""
+    arity = _declared_arity()
+    assert sorted(arity) == _declared_symbols()
+    for name, (_restype, argtypes) in _lib._SIGNATURES.items():
+        assert len(argtypes) == arity[name], (name, len(argtypes), arity[name])
+
+
 def test_binding_loads_and_reports_version():
     L = _lib.lib()
     assert L.spr_version() >= 100

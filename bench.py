@@ -216,8 +216,20 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # rank 0 prints ONE JSON line on stdout: whatever NCCL writes while the communicator comes up (its version
+        # banner at NCCL_DEBUG=WARN/VERSION/INFO) is sent to stderr by pointing fd 1 at fd 2 for that moment
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # later NCCL log lines (NCCL_DEBUG=INFO) too
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)  # the first collective creates the communicator
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
 

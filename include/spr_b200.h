@@ -47,6 +47,13 @@ SPR_API const char* spr_last_error(void);
 /* Number of kernels this library has launched from the calling process (all threads); bench.py reports
  * the delta over the timed region as gpu_launches. */
 SPR_API unsigned long long spr_launch_count(void);
+/* Sticky numeric flags of the current device, raised by kernels that write fp16 (hi, lo) operand images for the
+ * tensor-core GEMMs (spr_gemm_prepare_input, spr_layernorm256_prepare, spr_instance_norm_lrelu_ex, spr_attention_varlen
+ * with an image output, spr_gemm_tc with plane / image output).  SPR_FLAG_FP16_OVERFLOW: an activation times the
+ * image scale exceeded the fp16 range (|x| > 65504 / scale, i.e. ~4094 at the host layer's scale of 16) or was not
+ * finite; the affected outputs are NaN (never silently wrong).  Synchronises the device.  reset != 0 clears them. */
+#define SPR_FLAG_FP16_OVERFLOW 1u
+SPR_API unsigned int spr_numeric_flags(int reset);
 
 /* ---------------------------------------------------------------------------------------------
  * Grid (voxel) subsampling.
@@ -184,6 +191,15 @@ SPR_API int spr_sinkhorn_weighted_targets(const float* d_corr, const int64_t* d_
                                   float* d_weighted_tgt, float* d_weights, void* d_workspace, size_t workspace_bytes,
                                   void* stream);
 
+/* The same Sinkhorn normalisation on a caller-supplied affinity (log_alpha) matrix per pair, packed like d_corr:
+ * utils/se3_torch.py:166-202 `sinkhorn(log_alpha, n_iters, slack)` -> d_log_perm (packed N_p x M_p, optional) and
+ * :204-239 `compute_rigid_transform_with_sinkhorn` up to the pose solve -> d_weighted_tgt / d_weights (optional, need
+ * d_tgt_xyz).  At least one of the two outputs must be requested.  Workspace: spr_sinkhorn_workspace_bytes. */
+SPR_API int spr_sinkhorn_affinity(const float* d_affinity, const int64_t* d_mat_offsets, const int32_t* d_src_offsets,
+                          const int32_t* d_tgt_offsets, int n_pairs, int total_src, int total_tgt, int max_n, int max_m,
+                          int n_iters, int slack, float* d_log_perm, const float* d_tgt_xyz, float* d_weighted_tgt,
+                          float* d_weights, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Batched weighted Procrustes (Kabsch).  Replaces compute_rigid_transform(a, b, weights)
  *   utils/se3_torch.py:109-163 : w~ = w / max(sum w, 1e-6); weighted centroids; cov = (a-ca)^T ((b-cb) * w~);
@@ -196,9 +212,10 @@ SPR_API int spr_weighted_procrustes(const float* d_a, const float* d_b, const fl
                             float* d_out, void* stream);
 
 /* Gather rows: out[i,:] = src[base_offset(pair of i) + ind[i], :]  (the torch.gather at qk_regtr_full.py:478,589
- * that turns argmax indices into corresponding points). */
-SPR_API int spr_gather_rows3(const float* d_src, const int64_t* d_ind, const int32_t* d_row_pair_base, int n_rows, float* d_out,
-                     void* stream);
+ * that turns argmax indices into corresponding points).  d_src has n_src rows; a row number outside [0, n_src) is
+ * clamped into range (never dereferenced out of bounds). */
+SPR_API int spr_gather_rows3(const float* d_src, int n_src, const int64_t* d_ind, const int32_t* d_row_pair_base, int n_rows,
+                     float* d_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Optional correspondence refinements of RegTR.softmax_correlation (use_ratio_test / use_lgr / use_ransac; all off in

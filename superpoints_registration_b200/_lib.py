@@ -21,6 +21,7 @@ _SIGNATURES = {
     "spr_version": (c_int, []),
     "spr_last_error": (ctypes.c_char_p, []),
     "spr_launch_count": (ctypes.c_ulonglong, []),
+    "spr_numeric_flags": (ctypes.c_uint, [c_int]),
     "spr_grid_subsample_workspace_bytes": (c_size_t, [c_int, c_int]),
     "spr_grid_subsample_batch": (c_int, [c_fp, c_fp, c_int, c_int, c_float, c_fp, c_fp, c_fp, c_fp, c_size_t, c_void_p]),
     "spr_cell_grid_workspace_bytes": (c_size_t, [c_int, c_int]),
@@ -48,8 +49,10 @@ _SIGNATURES = {
     "spr_sinkhorn_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "spr_sinkhorn_weighted_targets": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp, c_float,
                                               c_float, c_int, c_int, c_fp, c_fp, c_fp, c_size_t, c_void_p]),
+    "spr_sinkhorn_affinity": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_fp, c_fp,
+                                      c_fp, c_fp, c_fp, c_size_t, c_void_p]),
     "spr_weighted_procrustes": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_void_p]),
-    "spr_gather_rows3": (c_int, [c_fp, c_fp, c_fp, c_int, c_fp, c_void_p]),
+    "spr_gather_rows3": (c_int, [c_fp, c_int, c_fp, c_fp, c_int, c_fp, c_void_p]),
     "spr_top2_ratio": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_float, c_fp, c_fp, c_void_p]),
     "spr_inlier_reweight": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_float, c_fp, c_void_p]),
     "spr_select_hypothesis": (c_int, [c_fp, c_fp, c_fp, c_int, c_fp, c_int, c_fp, c_fp, c_fp, c_void_p]),
@@ -89,6 +92,14 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = lib().spr_last_error()
         raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else 'unknown error'}")
+
+
+FLAG_FP16_OVERFLOW = 1
+
+
+def numeric_flags(reset: bool = True) -> int:
+    """Sticky numeric flags of the current device (spr_numeric_flags); synchronises the device."""
+    return int(lib().spr_numeric_flags(1 if reset else 0))
 
 
 def launch_count() -> int:

@@ -18,6 +18,10 @@
 namespace spr {
 namespace {
 
+// sticky numeric flags of this translation unit (bit 0: an fp16 operand image overflowed), see spr_numeric_flags
+__device__ unsigned int g_attention_flags;
+
+
 constexpr int HD = 32;       // head dimension
 constexpr int BK = 64;       // key rows per shared-memory tile
 constexpr int PLANE_BYTES = BK * HD * 2;  // one fp16 plane of a tile: 4 KB
@@ -264,6 +268,7 @@ __global__ void __launch_bounds__(128)
   if (out_img) {
     // A image of the output projection (gemm_tc.cu): token -> tile token/64, stacked rows 2r (hi), 2r+1 (lo);
     // column c -> K atom c/64, 16-byte chunk (c%64)/8, SWIZZLE_128B
+    float amax16 = 0.f;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int r = half ? r1 : r0;
@@ -275,6 +280,7 @@ __global__ void __launch_bounds__(128)
       for (int i = 0; i < 4; ++i) {
         const int c = head * HD + 8 * i + 2 * t;
         const float v0 = o[i][2 * half] * inv, v1 = o[i][2 * half + 1] * inv;
+        amax16 = fmaxf(amax16, fmaxf(fabsf(v0), fabsf(v1)));
         const __half2 hh = __floats2half2_rn(v0, v1);
         const float2 hf = __half22float2(hh);
         const __half2 ll = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
@@ -286,6 +292,7 @@ __global__ void __launch_bounds__(128)
         *reinterpret_cast<uint32_t*>(blk + o_lo) = h2u(ll);
       }
     }
+    if (!(amax16 <= 65504.f)) atomicOr(&g_attention_flags, SPR_FLAG_FP16_OVERFLOW);  // false for NaN as well
   }
 }
 
@@ -296,6 +303,7 @@ __global__ void __launch_bounds__(256) k_split_f16(const float* __restrict__ x, 
                                                     int n_scaled, float scale) {
   const int c4 = cols >> 2;
   const size_t total = (size_t)rows * c4;
+  float amax16 = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / c4), c = (int)(i % c4) * 4;
     float4 v = *reinterpret_cast<const float4*>(x + (size_t)r * ld_in + c);
@@ -305,15 +313,28 @@ __global__ void __launch_bounds__(256) k_split_f16(const float* __restrict__ x, 
       v.z *= scale;
       v.w *= scale;
     }
+    amax16 = fmaxf(amax16, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
     const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
     const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
     *reinterpret_cast<uint2*>(hi + (size_t)r * ld_out + c) = make_uint2(h2u(h0), h2u(h1));
     *reinterpret_cast<uint2*>(lo + (size_t)r * ld_out + c) = make_uint2(h2u(l0), h2u(l1));
   }
+  if (!(amax16 <= 65504.f)) atomicOr(&g_attention_flags, SPR_FLAG_FP16_OVERFLOW);
 }
 
 }  // namespace
+
+unsigned int attention_numeric_flags(bool reset) {
+  unsigned int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_attention_flags, sizeof(v)) != cudaSuccess) return 0;
+  if (reset && v) {
+    const unsigned int zero = 0;
+    cudaMemcpyToSymbol(g_attention_flags, &zero, sizeof(zero));
+  }
+  return v;
+}
+
 }  // namespace spr
 
 using namespace spr;

@@ -224,6 +224,9 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// sticky numeric flags of this translation unit (bit 0: an fp16 operand image overflowed), see spr_numeric_flags
+__device__ unsigned int g_blocks_flags;
+
 // byte offset of 16-byte chunk j of row r inside a (rows x 128 B) SWIZZLE_128B operand tile (tc05.cuh)
 __device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t j) {
   return (r >> 3) * 1024u + (r & 7u) * 128u + ((j ^ (r & 7u)) << 4);
@@ -311,6 +314,8 @@ __global__ void __launch_bounds__(256, STEPS == 1 ? 6 : 4)
       }
     }
   }
+  // (rmax is still this lane's own maximum here; the comparison is false for NaN, so NaN raises the flag too)
+  if (out_img && live && !(rmax * a_scale <= 65504.f)) atomicOr(&g_blocks_flags, SPR_FLAG_FP16_OVERFLOW);
   if (out_x16) {
     for (int o = G >> 1; o > 0; o >>= 1) {
       rsum += __shfl_xor_sync(kFull, rsum, o);
@@ -371,6 +376,17 @@ __global__ void __launch_bounds__(256)
 }
 
 }  // namespace
+
+unsigned int blocks_numeric_flags(bool reset) {
+  unsigned int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_blocks_flags, sizeof(v)) != cudaSuccess) return 0;
+  if (reset && v) {
+    const unsigned int zero = 0;
+    cudaMemcpyToSymbol(g_blocks_flags, &zero, sizeof(zero));
+  }
+  return v;
+}
+
 }  // namespace spr
 
 using namespace spr;

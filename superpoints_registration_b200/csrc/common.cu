@@ -2,11 +2,27 @@
 #include "spr_common.cuh"
 
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
 
 namespace spr {
 
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+
+cudaError_t ensure_max_dynamic_smem(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({func, dev})) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) done.insert({func, dev});
+  return e;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -220,4 +236,8 @@ extern "C" {
 int spr_version(void) { return 100; }
 const char* spr_last_error(void) { return spr::g_err; }
 unsigned long long spr_launch_count(void) { return spr::g_launches.load(); }
+unsigned int spr_numeric_flags(int reset) {
+  return spr::gemm_numeric_flags(reset != 0) | spr::blocks_numeric_flags(reset != 0) |
+         spr::attention_numeric_flags(reset != 0);
+}
 }

@@ -20,8 +20,6 @@
 #include "spr_common.cuh"
 #include "tc05.cuh"
 
-#include <cstdlib>
-
 namespace spr {
 namespace {
 
@@ -62,9 +60,14 @@ struct GemmArgs {
   float2* stats16;         // OUT_F32, optional: [ceil(T/16), N] (sum, sum of squares) of each 16-row block of the output
 };
 
-__device__ long long g_gemm_dbg[4096];
+// sticky numeric flags of this translation unit (bit 0: an fp16 operand image overflowed), see spr_numeric_flags
+__device__ unsigned int g_gemm_flags;
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, int mode, int dbg) {
+__device__ __forceinline__ void flag_overflow(float amax_scaled) {
+  if (!(amax_scaled <= 65504.f)) atomicOr(&g_gemm_flags, SPR_FLAG_FP16_OVERFLOW);  // also catches NaN
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, int mode) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem =
       reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -144,20 +147,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      const bool rec = dbg && blockIdx.x == 0;
-      if (rec) g_gemm_dbg[0] = clock64();
       if (resident && first < limit) mbar_wait(bar_w, 0);
-      if (rec) g_gemm_dbg[1] = clock64();
       for (int tile = first; tile < limit; tile += step, ++it) {
         const int buf = it & 1;
-        if (rec && it < 60) g_gemm_dbg[8 + it * 8 + 0] = clock64();
         mbar_wait(&bar_acce[buf], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        if (rec && it < 60) g_gemm_dbg[8 + it * 8 + 1] = clock64();
         for (int a = 0; a < KA; ++a) {
           mbar_wait(&bar_full[stage], phase);
           tc_fence_after();
-          if (rec && it < 60 && a < 4) g_gemm_dbg[8 + it * 8 + 2 + a] = clock64();
           const int bslot = resident ? a : stage;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
@@ -172,9 +169,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
           }
         }
         umma_commit(&bar_accf[buf]);
-        if (rec && it < 60) g_gemm_dbg[8 + it * 8 + 6] = clock64();
       }
-      if (rec) g_gemm_dbg[2] = clock64();
     }
     __syncwarp();
   } else {
@@ -187,14 +182,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
     const int chalf = (ew >> 2) & 1;               // which 64 columns of the tile
     // TMEM lane qd * 32 + lane is stacked row 2r (hi) / 2r + 1 (lo) of token r
     const int half_sel = lane & 1;                 // even lane stores columns c0..c0+3, odd lane c0+4..c0+7
+    float amax16 = 0.f;                            // largest |value| this lane wrote into an fp16 output
     for (int it = set, tile = first + set * step; tile < limit; tile += 2 * step, it += 2) {
       const int buf = set;
       const int mt = resident ? tile : tile / n_tiles, nt = resident ? nt_fixed : tile % n_tiles;
-      const bool erec = dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 60;
-      if (erec) g_gemm_dbg[1024 + it * 4 + 0] = clock64();
       mbar_wait(&bar_accf[buf], (it >> 1) & 1);
       tc_fence_after();
-      if (erec) g_gemm_dbg[1024 + it * 4 + 1] = clock64();
       const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16) + buf * 256 + chalf * 64;
       // The accumulator rows are per-lane (lane = stacked token row): writing them directly costs one memory
       // transaction per token per instruction.  Each group of 32 columns is transposed through a small per-warp
@@ -218,17 +211,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_acce[buf]);
-          if (erec) g_gemm_dbg[1024 + it * 4 + 2] = clock64();
         }
         // bias and residual of this group's coalesced phase are requested first: their latency overlaps the transpose
         const int pcol = nt * BN + chalf * 64 + grp * 32 + (lane & 7) * 4;
         float4 pbias = make_float4(0.f, 0.f, 0.f, 0.f), pres[4];
-        if (g.bias && pcol < g.N && dbg < 2) pbias = __ldg(reinterpret_cast<const float4*>(g.bias + pcol));
+        if (g.bias && pcol < g.N) pbias = __ldg(reinterpret_cast<const float4*>(g.bias + pcol));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           pres[k] = make_float4(0.f, 0.f, 0.f, 0.f);
           const int ptok = mt * BM_TOK + qd * 16 + k * 4 + (lane >> 3);
-          if (mode == OUT_F32 && g.residual && ptok < g.T && pcol < g.N && dbg < 2)
+          if (mode == OUT_F32 && g.residual && ptok < g.T && pcol < g.N)
             pres[k] = *reinterpret_cast<const float4*>(g.residual + (size_t)ptok * g.ld_res + pcol);
         }
 #pragma unroll
@@ -249,7 +241,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
         for (int k = 0; k < 4; ++k) {
           const int tl = k * 4 + (lane >> 3);                    // token within the warp's 16
           const int token = mt * BM_TOK + qd * 16 + tl;
-          const bool ok = token < g.T && ncol0 < g.N && dbg < 2;
+          const bool ok = token < g.T && ncol0 < g.N;
           if (!ok) continue;
           const float4 a = *reinterpret_cast<const float4*>(stg + tl * EPI_ROW + (lane & 7) * 4);
           float y[4] = {a.x * g.out_scale, a.y * g.out_scale, a.z * g.out_scale, a.w * g.out_scale};
@@ -275,7 +267,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
             }
             const float sc = mode == OUT_AIMG ? g.next_scale : (ncol0 < g.n_scaled ? g.col_scale : 1.f);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) y[e] *= sc;
+            for (int e = 0; e < 4; ++e) {
+              y[e] *= sc;
+              amax16 = fmaxf(amax16, fabsf(y[e]));
+            }
             const __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
             const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
             const __half2 l0 = __floats2half2_rn(y[0] - f0.x, y[1] - f0.y), l1 = __floats2half2_rn(y[2] - f1.x, y[3] - f1.y);
@@ -305,7 +300,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
             cq[e] += __shfl_xor_sync(kFull, cq[e], 16);
           }
           const int tok0 = mt * BM_TOK + qd * 16;
-          if (lane < 8 && tok0 < g.T && ncol0 < g.N && dbg < 2) {
+          if (lane < 8 && tok0 < g.T && ncol0 < g.N) {
             float4* dst = reinterpret_cast<float4*>(g.stats16 + (size_t)(tok0 >> 4) * g.N + ncol0);
             dst[0] = make_float4(cs[0], cq[0], cs[1], cq[1]);
             dst[1] = make_float4(cs[2], cq[2], cs[3], cq[3]);
@@ -313,8 +308,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
         }
         __syncwarp();
       }
-      if (erec) g_gemm_dbg[1024 + it * 4 + 3] = clock64();
     }
+    if (mode != OUT_F32) flag_overflow(amax16);
   }
   tc_fence_before();
   __syncthreads();
@@ -363,9 +358,11 @@ __global__ void __launch_bounds__(256) k_ln_to_aimg(const float* __restrict__ x,
   }
   if (img) {
     uint32_t hi[4], lo[4];
+    float amax16 = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float y0 = v[2 * i] * a_scale, y1 = v[2 * i + 1] * a_scale;
+      amax16 = fmaxf(amax16, fmaxf(fabsf(y0), fabsf(y1)));
       const __half2 hh = __floats2half2_rn(y0, y1);
       const float2 hf = __half22float2(hh);
       const __half2 ll = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
@@ -377,6 +374,7 @@ __global__ void __launch_bounds__(256) k_ln_to_aimg(const float* __restrict__ x,
     const uint32_t r2 = 2 * (token & 63);
     *reinterpret_cast<uint4*>(blk + sw128_offset(r2, lane & 7)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(blk + sw128_offset(r2 + 1, lane & 7)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    flag_overflow(amax16);
   }
 }
 
@@ -386,12 +384,16 @@ __global__ void __launch_bounds__(256) k_f32_to_aimg(const float* __restrict__ x
   const int KA = (K + 63) / 64;
   const int chunks_per_row = KA * 8;
   const size_t total = (size_t)T * chunks_per_row;
+  float amax16 = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int token = (int)(i / chunks_per_row), ch = (int)(i % chunks_per_row);
     const int k0 = ch * 8;
     float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = (k0 + e < K) ? x[(size_t)token * ld + k0 + e] * a_scale : 0.f;
+    for (int e = 0; e < 8; ++e) {
+      v[e] = (k0 + e < K) ? x[(size_t)token * ld + k0 + e] * a_scale : 0.f;
+      amax16 = fmaxf(amax16, fabsf(v[e]));
+    }
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -406,6 +408,7 @@ __global__ void __launch_bounds__(256) k_f32_to_aimg(const float* __restrict__ x
     *reinterpret_cast<uint4*>(blk + sw128_offset(r2, ch & 7)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(blk + sw128_offset(r2 + 1, ch & 7)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
+  flag_overflow(amax16);
 }
 
 // W [N, K] fp32 -> W image (scaled fp16 hi | lo), one thread per 16-byte chunk
@@ -434,6 +437,17 @@ __global__ void __launch_bounds__(256) k_weight_to_img(const float* __restrict__
 }
 
 }  // namespace
+
+unsigned int gemm_numeric_flags(bool reset) {
+  unsigned int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_gemm_flags, sizeof(v)) != cudaSuccess) return 0;
+  if (reset && v) {
+    const unsigned int zero = 0;
+    cudaMemcpyToSymbol(g_gemm_flags, &zero, sizeof(zero));
+  }
+  return v;
+}
+
 }  // namespace spr
 
 using namespace spr;
@@ -490,6 +504,8 @@ extern "C" int spr_gemm_tc(const void* d_a_img, const void* d_w_img, const float
   SPR_CHECK_ARG(out_mode != OUT_PLANES || d_out_lo, "gemm_tc: plane output needs both planes");
   SPR_CHECK_ARG(out_mode == OUT_AIMG || (ld_out >= N && (ld_out & 3) == 0), "gemm_tc: bad output row stride");
   SPR_CHECK_ARG(!d_residual || (out_mode == OUT_F32 && (ld_res & 3) == 0), "gemm_tc: residual only with fp32 output");
+  // the next GEMM reads whole 64-wide K atoms of the image this one writes: no pad columns may stay unwritten
+  SPR_CHECK_ARG(out_mode != OUT_AIMG || (N & 63) == 0, "gemm_tc: operand-image output needs N to be a multiple of 64 (got %d)", N);
   GemmArgs g;
   g.a_img = static_cast<const unsigned char*>(d_a_img);
   g.w_img = static_cast<const unsigned char*>(d_w_img);
@@ -509,11 +525,7 @@ extern "C" int spr_gemm_tc(const void* d_a_img, const void* d_w_img, const float
   g.col_scale = col_scale;
   g.next_scale = next_scale;
   g.stats16 = reinterpret_cast<float2*>(d_stats16);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SPR_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    attr_set = true;
-  }
+  SPR_CUDA(ensure_max_dynamic_smem(reinterpret_cast<const void*>(k_gemm_tc), GEMM_SMEM));
   const int m_tiles = (T + BM_TOK - 1) / BM_TOK, n_tiles = (N + BN - 1) / BN;
   int grid;
   if (g.K / 64 <= RES_KA) {  // W-resident walk: a multiple of n_tiles CTAs, each pinned to one n tile
@@ -525,25 +537,7 @@ extern "C" int spr_gemm_tc(const void* d_a_img, const void* d_w_img, const float
     const int total = m_tiles * n_tiles;
     grid = total < kNumSMs ? total : kNumSMs;
   }
-  static int dbg = -1;
-  if (dbg < 0) dbg = getenv("SPR_GEMM_DEBUG") ? atoi(getenv("SPR_GEMM_DEBUG")) : 0;
-  k_gemm_tc<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(g, out_mode, dbg);
+  k_gemm_tc<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(g, out_mode);
   SPR_LAUNCH_CHECK("k_gemm_tc");
-  if (dbg) {
-    long long h[4096];
-    cudaStreamSynchronize(stream);
-    cudaMemcpyFromSymbol(h, g_gemm_dbg, sizeof(h));
-    fprintf(stderr, "[gemm dbg] T=%d N=%d K=%d grid=%d: start->W %lld, total %lld cycles\n", T, N, K, grid, h[1] - h[0],
-            h[2] - h[0]);
-    const int tiles = (g.K / 64 <= RES_KA) ? (m_tiles - 0 + grid / n_tiles - 1) / (grid / n_tiles) : (m_tiles * n_tiles + grid - 1) / grid;
-    for (int i = 0; i < tiles && i < 8; ++i) {
-      long long* r = h + 8 + i * 8;
-      long long* e = h + 1024 + i * 4;
-      fprintf(stderr, "  tile %d: +%lld wait_acce %lld | full0 +%lld full1 +%lld full2 +%lld full3 +%lld | issued +%lld"
-                      " || epi: wait_accf %lld, tmem loads %lld, math+stores %lld\n", i,
-              r[0] - h[0], r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], e[1] - e[0],
-              e[2] - e[1], e[3] - e[2]);
-    }
-  }
   return SPR_OK;
 }

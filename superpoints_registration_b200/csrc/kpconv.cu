@@ -486,12 +486,7 @@ int launch_fused(const float* q, const float* s, const void* idx, int row_stride
                  cudaStream_t stream) {
   using K = Cfg<C, V>;
   const int n_tiles = (nq + K::TQ - 1) / K::TQ;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    SPR_CUDA(cudaFuncSetAttribute(k_kpconv_fused<C, V, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)K::SMEM));
-    attr_set = true;
-  }
+  SPR_CUDA(ensure_max_dynamic_smem(reinterpret_cast<const void*>(k_kpconv_fused<C, V, IdxT>), K::SMEM));
   // persistent CTAs: one (or MIN_BLOCKS) per SM, tiles dealt round-robin, so that the next tile's first loads
   // can be prefetched behind the current tile's contraction
   const int resident = kNumSMs * K::MIN_BLOCKS;

@@ -32,7 +32,8 @@
 extern "C" size_t spr_kpconv_scratch_bytes(int H, int c) {
   if (c <= 32) return 0;
   const size_t nb = (size_t)((H > 0 ? H : 1) + 7) / 8;
-  return (size_t)148 * 2 * 64 * nb * 32 * 16;  // per CTA: two tile buffers x 64 queries x nb blocks x 32 lanes x uint4
+  // per CTA (the grid never exceeds kNumSMs): two tile buffers x 64 queries x nb blocks x 32 lanes x uint4
+  return (size_t)spr::kNumSMs * 2 * 64 * nb * 32 * 16;
 }
 
 namespace spr {
@@ -664,13 +665,9 @@ int launch_main(const float* q, const void* idx, int row_stride, int H, const ui
     tq = per < 16 ? 16 : (per > K::TQ ? K::TQ : per);
   }
   const int n_tiles = (nq + tq - 1) / tq;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SPR_CUDA(cudaFuncSetAttribute(k_kpconv_tc<C, IdxT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
-    SPR_CUDA(cudaFuncSetAttribute(k_kpconv_tc<C, IdxT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
-    SPR_CUDA(cudaFuncSetAttribute(k_kpconv_tc<C, IdxT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
-    attr_set = true;
-  }
+  SPR_CUDA(ensure_max_dynamic_smem(reinterpret_cast<const void*>(k_kpconv_tc<C, IdxT, 1>), K::SMEM));
+  SPR_CUDA(ensure_max_dynamic_smem(reinterpret_cast<const void*>(k_kpconv_tc<C, IdxT, 2>), K::SMEM));
+  SPR_CUDA(ensure_max_dynamic_smem(reinterpret_cast<const void*>(k_kpconv_tc<C, IdxT, 3>), K::SMEM));
   const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
   const IdxT* idx_t = static_cast<const IdxT*>(idx);
   const float* s_unused = nullptr;

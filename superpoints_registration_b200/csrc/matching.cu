@@ -13,6 +13,8 @@
 //   row/column kept implicit (A = 0 there); each half-iteration is one pass over corr.
 #include "spr_common.cuh"
 
+#include <algorithm>
+
 namespace spr {
 namespace {
 
@@ -85,13 +87,14 @@ struct CorrElem {
   __device__ __forceinline__ float operator()(float c, int, int) const { return c; }
 };
 
-// Sinkhorn element: A_ij - u_i - v_j with A = -(max(c,0) - sp_alpha) / denom
+// Sinkhorn element: A_ij - u_i - v_j with A = -(max(c, lo) - sp_alpha) / denom.  The model path (qk_regtr_full.py:
+// 532-536) has lo = 0; a caller-supplied affinity matrix is the case lo = -inf, sp_alpha = 0, denom = -1 (A = c).
 struct SinkElem {
   const float* u;
   const float* v;
-  float sp_alpha, inv_denom;
+  float sp_alpha, inv_denom, lo;
   __device__ __forceinline__ float operator()(float c, int gi, int gj) const {
-    const float a = -(fmaxf(c, 0.f) - sp_alpha) * inv_denom;
+    const float a = -(fmaxf(c, lo) - sp_alpha) * inv_denom;
     return a - u[gi] - v[gj];
   }
 };
@@ -176,6 +179,14 @@ __device__ __forceinline__ float dual_softmax(float c, float rm, float rs, float
   return (expf(c - cm) / cs) * (expf(c - rm) / rs);
 }
 
+// torch.max semantics for the arg-max (qk_regtr_full.py:468,576): NaN is the maximum, ties and NaNs keep the FIRST
+// index, so the index is always in range (a row of NaNs must not leave a sentinel that a later gather dereferences).
+__device__ __forceinline__ bool better(float a, int ai, float b, int bi) {
+  const bool an = a != a, bn = b != b;
+  if (an || bn) return an && (!bn || ai < bi);
+  return a > b || (a == b && ai < bi);
+}
+
 // N <= M : val, ind = max(attn, dim=2): one warp per source row.
 __global__ void __launch_bounds__(256)
     k_match_rows(const float* __restrict__ corr, const int* __restrict__ so, const int* __restrict__ to,
@@ -190,11 +201,11 @@ __global__ void __launch_bounds__(256)
   for (int i = blockIdx.x * warps + (threadIdx.x >> 5); i < N; i += gridDim.x * warps) {
     const int gi = so[p] + i;
     const float rm = rmax[gi], rs = rsum[gi];
-    float best = -1.f;
+    float best = -INFINITY;
     int bj = 0x7fffffff;
     for (int j = lane; j < M; j += 32) {
       const float a = dual_softmax(C[(size_t)i * M + j], rm, rs, cmax[to[p] + j], csum[to[p] + j]);
-      if (a > best) {
+      if (better(a, j, best, bj)) {
         best = a;
         bj = j;
       }
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(256)
     for (int o = 16; o > 0; o >>= 1) {
       const float ob = __shfl_xor_sync(kFull, best, o);
       const int oj = __shfl_xor_sync(kFull, bj, o);
-      if (ob > best || (ob == best && oj < bj)) {
+      if (better(ob, oj, best, bj)) {
         best = ob;
         bj = oj;
       }
@@ -230,13 +241,13 @@ __global__ void __launch_bounds__(256)
   const float* C = corr + co[p];
   __shared__ float s_b[8][32];
   __shared__ int s_i[8][32];
-  float best = -1.f;
+  float best = -INFINITY;
   int bi = 0x7fffffff;
   if (j < M) {
     const float cm = cmax[to[p] + j], cs = csum[to[p] + j];
     for (int i = warp; i < N; i += warps) {
       const float a = dual_softmax(C[(size_t)i * M + j], rmax[so[p] + i], rsum[so[p] + i], cm, cs);
-      if (a > best) {
+      if (better(a, i, best, bi)) {
         best = a;
         bi = i;
       }
@@ -249,7 +260,7 @@ __global__ void __launch_bounds__(256)
     for (int w = 1; w < warps; ++w) {
       const float ob = s_b[w][threadIdx.x & 31];
       const int oi = s_i[w][threadIdx.x & 31];
-      if (ob > best || (ob == best && oi < bi)) {
+      if (better(ob, oi, best, bi)) {
         best = ob;
         bi = oi;
       }
@@ -314,11 +325,25 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-__global__ void k_gather_rows3(const float* __restrict__ src, const long long* __restrict__ ind,
+// log of the (near) doubly stochastic matrix, se3_torch.py:200: log_alpha_ij = A_ij - u_i - v_j
+__global__ void __launch_bounds__(256)
+    k_sink_log(const float* __restrict__ mat, const int* __restrict__ so, const int* __restrict__ to,
+               const long long* __restrict__ co, SinkElem f, float* __restrict__ out) {
+  const int p = blockIdx.y;
+  const int N = so[p + 1] - so[p], M = to[p + 1] - to[p];
+  const size_t total = (size_t)N * M;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / M), j = (int)(e % M);
+    out[co[p] + e] = f(mat[co[p] + e], so[p] + i, to[p] + j);
+  }
+}
+
+__global__ void k_gather_rows3(const float* __restrict__ src, int n_src, const long long* __restrict__ ind,
                                const int* __restrict__ base, int n, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const size_t r = (size_t)base[i] + (size_t)ind[i];
+  long long r = (long long)base[i] + ind[i];
+  r = r < 0 ? 0 : (r >= n_src ? n_src - 1 : r);  // never read outside src, whatever the index says
   out[3 * (size_t)i] = src[3 * r];
   out[3 * (size_t)i + 1] = src[3 * r + 1];
   out[3 * (size_t)i + 2] = src[3 * r + 2];
@@ -389,18 +414,17 @@ extern "C" size_t spr_sinkhorn_workspace_bytes(int total_src, int total_tgt, int
   return align_up((size_t)total_src * 12, 256) + align_up((size_t)total_tgt * 12, 256) + 512;
 }
 
-extern "C" int spr_sinkhorn_weighted_targets(const float* d_corr, const int64_t* d_corr_offsets,
-                                             const int32_t* d_src_offsets, const int32_t* d_tgt_offsets, int n_pairs,
-                                             int total_src, int total_tgt, int max_n, int max_m,
-                                             const float* d_tgt_xyz, float softplus_alpha, float exp_beta, int n_iters,
-                                             int slack, float* d_weighted_tgt, float* d_weights, void* d_workspace,
-                                             size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int sinkhorn_run(const float* d_mat, const int64_t* d_corr_offsets, const int32_t* d_src_offsets,
+                        const int32_t* d_tgt_offsets, int n_pairs, int total_src, int total_tgt, int max_n, int max_m,
+                        float sp_alpha, float inv_denom, float lo, int n_iters, const float* d_tgt_xyz,
+                        float* d_weighted_tgt, float* d_weights, float* d_log_perm, void* d_workspace,
+                        size_t workspace_bytes, cudaStream_t stream) {
   SPR_CHECK_ARG(n_pairs > 0 && total_src > 0 && total_tgt > 0 && max_n > 0 && max_m > 0, "sinkhorn: empty input");
   SPR_CHECK_ARG(n_iters >= 0, "sinkhorn: n_iters < 0");
-  SPR_CHECK_ARG(d_corr && d_corr_offsets && d_src_offsets && d_tgt_offsets && d_tgt_xyz && d_weighted_tgt && d_weights &&
-                    d_workspace,
-                "sinkhorn: null pointer");
+  SPR_CHECK_ARG(d_mat && d_corr_offsets && d_src_offsets && d_tgt_offsets && d_workspace, "sinkhorn: null pointer");
+  SPR_CHECK_ARG((d_weighted_tgt == nullptr) == (d_weights == nullptr) && (!d_weighted_tgt || d_tgt_xyz),
+                "sinkhorn: weighted targets need tgt_xyz, weighted_tgt and weights together");
+  SPR_CHECK_ARG(d_weighted_tgt || d_log_perm, "sinkhorn: no output requested");
   if (workspace_bytes < spr_sinkhorn_workspace_bytes(total_src, total_tgt, n_pairs)) {
     set_error("sinkhorn: workspace too small");
     return SPR_ENOSPACE;
@@ -418,38 +442,70 @@ extern "C" int spr_sinkhorn_weighted_targets(const float* d_corr, const int64_t*
   SinkElem f;
   f.u = u;
   f.v = v;
-  f.sp_alpha = softplus_alpha;
-  f.inv_denom = 1.0f / (exp_beta + 0.02f);
+  f.sp_alpha = sp_alpha;
+  f.inv_denom = inv_denom;
+  f.lo = lo;
   const int rb = min((max_n + 7) / 8, kNumSMs * 8);
   const int cb = (max_m + 31) / 32;
   // With slack (se3_torch.py:183-199): rows 0..N-1 are normalised over M+1 columns (the slack column holds
   // 0 - u_i - v_M with v_M never updated, i.e. -u_i); columns 0..M-1 over N+1 rows (slack row holds -v_j).
   // Without slack the reference still zero-pads (:182-184), so the implicit entries are identical.
-  (void)slack;
   for (int it = 0; it < n_iters; ++it) {
-    k_row_stats<SinkElem><<<dim3(rb, n_pairs), 256, 0, stream>>>(d_corr, d_src_offsets, d_tgt_offsets, co, f, rmx, rsm,
+    k_row_stats<SinkElem><<<dim3(rb, n_pairs), 256, 0, stream>>>(d_mat, d_src_offsets, d_tgt_offsets, co, f, rmx, rsm,
                                                                  0.f, u);
     SPR_LAUNCH_CHECK("k_row_stats<sink>");
     k_add_lse<<<(total_src + 255) / 256, 256, 0, stream>>>(u, rmx, rsm, total_src);
     SPR_LAUNCH_CHECK("k_add_lse");
-    k_col_stats<SinkElem><<<dim3(cb, n_pairs), 256, 0, stream>>>(d_corr, d_src_offsets, d_tgt_offsets, co, f, cmx, csm,
+    k_col_stats<SinkElem><<<dim3(cb, n_pairs), 256, 0, stream>>>(d_mat, d_src_offsets, d_tgt_offsets, co, f, cmx, csm,
                                                                  0.f, v);
     SPR_LAUNCH_CHECK("k_col_stats<sink>");
     k_add_lse<<<(total_tgt + 255) / 256, 256, 0, stream>>>(v, cmx, csm, total_tgt);
     SPR_LAUNCH_CHECK("k_add_lse");
   }
-  k_sink_finish<<<dim3(rb, n_pairs), 256, 0, stream>>>(d_corr, d_src_offsets, d_tgt_offsets, co, f, d_tgt_xyz,
-                                                       d_weighted_tgt, d_weights);
-  SPR_LAUNCH_CHECK("k_sink_finish");
+  if (d_log_perm) {
+    const long long per = (long long)max_n * max_m;
+    const int lb = (int)std::min<long long>((per + 255) / 256, (long long)kNumSMs * 8);
+    k_sink_log<<<dim3(lb, n_pairs), 256, 0, stream>>>(d_mat, d_src_offsets, d_tgt_offsets, co, f, d_log_perm);
+    SPR_LAUNCH_CHECK("k_sink_log");
+  }
+  if (d_weighted_tgt) {
+    k_sink_finish<<<dim3(rb, n_pairs), 256, 0, stream>>>(d_mat, d_src_offsets, d_tgt_offsets, co, f, d_tgt_xyz,
+                                                         d_weighted_tgt, d_weights);
+    SPR_LAUNCH_CHECK("k_sink_finish");
+  }
   return SPR_OK;
 }
 
-extern "C" int spr_gather_rows3(const float* d_src, const int64_t* d_ind, const int32_t* d_row_base, int n_rows,
-                                float* d_out, void* stream_) {
+extern "C" int spr_sinkhorn_weighted_targets(const float* d_corr, const int64_t* d_corr_offsets,
+                                             const int32_t* d_src_offsets, const int32_t* d_tgt_offsets, int n_pairs,
+                                             int total_src, int total_tgt, int max_n, int max_m,
+                                             const float* d_tgt_xyz, float softplus_alpha, float exp_beta, int n_iters,
+                                             int slack, float* d_weighted_tgt, float* d_weights, void* d_workspace,
+                                             size_t workspace_bytes, void* stream_) {
+  (void)slack;  // the reference zero-pads whether or not `slack` is set (se3_torch.py:182-184)
+  SPR_CHECK_ARG(d_tgt_xyz && d_weighted_tgt && d_weights, "sinkhorn: null pointer");
+  return sinkhorn_run(d_corr, d_corr_offsets, d_src_offsets, d_tgt_offsets, n_pairs, total_src, total_tgt, max_n, max_m,
+                      softplus_alpha, 1.0f / (exp_beta + 0.02f), 0.f, n_iters, d_tgt_xyz, d_weighted_tgt, d_weights,
+                      nullptr, d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int spr_sinkhorn_affinity(const float* d_affinity, const int64_t* d_mat_offsets, const int32_t* d_src_offsets,
+                                     const int32_t* d_tgt_offsets, int n_pairs, int total_src, int total_tgt, int max_n,
+                                     int max_m, int n_iters, int slack, float* d_log_perm, const float* d_tgt_xyz,
+                                     float* d_weighted_tgt, float* d_weights, void* d_workspace, size_t workspace_bytes,
+                                     void* stream_) {
+  (void)slack;
+  return sinkhorn_run(d_affinity, d_mat_offsets, d_src_offsets, d_tgt_offsets, n_pairs, total_src, total_tgt, max_n,
+                      max_m, 0.f, -1.0f, -INFINITY, n_iters, d_tgt_xyz, d_weighted_tgt, d_weights, d_log_perm,
+                      d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int spr_gather_rows3(const float* d_src, int n_src, const int64_t* d_ind, const int32_t* d_row_base,
+                                int n_rows, float* d_out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SPR_CHECK_ARG(n_rows > 0 && d_src && d_ind && d_row_base && d_out, "gather_rows3: bad argument");
-  k_gather_rows3<<<(n_rows + 255) / 256, 256, 0, stream>>>(d_src, reinterpret_cast<const long long*>(d_ind), d_row_base,
-                                                           n_rows, d_out);
+  SPR_CHECK_ARG(n_rows > 0 && n_src > 0 && d_src && d_ind && d_row_base && d_out, "gather_rows3: bad argument");
+  k_gather_rows3<<<(n_rows + 255) / 256, 256, 0, stream>>>(d_src, n_src, reinterpret_cast<const long long*>(d_ind),
+                                                           d_row_base, n_rows, d_out);
   SPR_LAUNCH_CHECK("k_gather_rows3");
   return SPR_OK;
 }

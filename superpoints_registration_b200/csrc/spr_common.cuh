@@ -47,6 +47,16 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
 
 constexpr int kNumSMs = 148;  // B200
 
+// cudaFuncSetAttribute(func, MaxDynamicSharedMemorySize, bytes), done once per (kernel, device) and safe to call
+// from several host threads (a process-wide `static bool` would leave the second GPU of a process unconfigured).
+cudaError_t ensure_max_dynamic_smem(const void* func, size_t bytes);
+
+// sticky numeric flags raised by kernels that write fp16 operand images (one word per translation unit, read and
+// combined by spr_numeric_flags)
+unsigned int gemm_numeric_flags(bool reset);
+unsigned int blocks_numeric_flags(bool reset);
+unsigned int attention_numeric_flags(bool reset);
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Bump allocator over a caller-provided workspace.

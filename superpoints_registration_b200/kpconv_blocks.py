@@ -10,8 +10,9 @@ Mirrors the operator surface of the reference's models/backbone_kpconv/kpconv_bl
   block_decider          :429-471
 Module / parameter names are the reference's, so a reference state_dict loads key for key
 (`KPConv.weights`, `KPConv.kernel_points`, `unary1.mlp.weight`, `unary2.mlp.weight`,
-`unary_shortcut.mlp.weight`).  The Linear layers of the unary blocks are plain fp32 GEMMs and go to cuBLAS
-through torch (TF32 disabled); everything else on the path is our own kernels.
+`unary_shortcut.mlp.weight`).  The Linear layers of the unary blocks run on the tcgen05 split-precision GEMM
+(ops.linear_tc / ops.gemm_tc: fp16 hi/lo operand pairs, fp32 accumulation, fp32-level accuracy); nothing on the
+path goes through cuBLAS.
 """
 from __future__ import annotations
 

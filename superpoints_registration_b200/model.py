@@ -334,6 +334,8 @@ class RegTR(nn.Module):
         pose, attn_list, val_list, ind_list, src_pts_list, tgt_pts_list = self._match_and_solve(
             src_packed, tgt_packed, pts_c, src_slens_c, tgt_slens_c, overlap_packed)
 
+        if cfg.get('check_numerics', False):
+            ops.check_numerics()  # one device synchronisation: fp16 operand range of the tensor-core GEMMs
         return {
             'pose': pose, 'attn': attn_list, 'src_feat': src_cond_list, 'tgt_feat': tgt_cond_list,
             'src_kp': src_xyz_c, 'tgt_kp': tgt_xyz_c, 'src_corr': src_pts_list, 'tgt_corr': tgt_pts_list,

@@ -398,6 +398,30 @@ def sinkhorn_weighted_targets(corr, pairs: PackedPairs, tgt_xyz, softplus_alpha:
     return wt, w
 
 
+def sinkhorn_affinity(affinity, pairs: PackedPairs, n_iters: int, slack: bool = True, tgt_xyz=None,
+                      want_log_perm: bool = True):
+    """Sinkhorn normalisation (se3_torch.py:166-202) of packed per-pair affinity matrices.
+    -> (log_perm packed or None, weighted_tgt f32[total_src,3] or None, weights f32[total_src] or None)."""
+    L = _lib.lib()
+    a = _f32c(affinity, "affinity").reshape(-1)
+    if a.numel() != pairs.total_corr:
+        raise RuntimeError("sinkhorn_affinity: affinity does not match the pair sizes")
+    dev = a.device
+    logp = torch.empty_like(a) if want_log_perm else None
+    txyz = wt = w = None
+    if tgt_xyz is not None:
+        txyz = _f32c(tgt_xyz, "tgt_xyz")
+        wt = torch.empty((pairs.total_src, 3), dtype=torch.float32, device=dev)
+        w = torch.empty(pairs.total_src, dtype=torch.float32, device=dev)
+    ws = _ws(L.spr_sinkhorn_workspace_bytes(pairs.total_src, pairs.total_tgt, pairs.P), dev)
+    rc = L.spr_sinkhorn_affinity(a.data_ptr(), pairs.co.data_ptr(), pairs.so.data_ptr(), pairs.to.data_ptr(), pairs.P,
+                                 pairs.total_src, pairs.total_tgt, pairs.max_n, pairs.max_m, int(n_iters),
+                                 1 if slack else 0, _ptr(logp), _ptr(txyz), _ptr(wt), _ptr(w), ws.data_ptr(), ws.numel(),
+                                 _stream())
+    _lib.check(rc, "spr_sinkhorn_affinity")
+    return logp, wt, w
+
+
 def weighted_procrustes(a, b, w, offsets: torch.Tensor) -> torch.Tensor:
     """Packed correspondences -> poses f32[P,3,4]."""
     L = _lib.lib()
@@ -418,7 +442,7 @@ def gather_rows3(src, ind, row_base) -> torch.Tensor:
     ii = ind.long().contiguous()
     rb = _i32c(row_base, "row_base")
     out = torch.empty((ii.shape[0], 3), dtype=torch.float32, device=s.device)
-    rc = L.spr_gather_rows3(s.data_ptr(), ii.data_ptr(), rb.data_ptr(), ii.shape[0], out.data_ptr(), _stream())
+    rc = L.spr_gather_rows3(s.data_ptr(), s.shape[0], ii.data_ptr(), rb.data_ptr(), ii.shape[0], out.data_ptr(), _stream())
     _lib.check(rc, "spr_gather_rows3")
     return out
 
@@ -535,8 +559,22 @@ def attention_varlen(hi: torch.Tensor, lo: torch.Tensor, tiles: torch.Tensor, n_
 
 
 # ---- tensor-core dense layers (gemm_tc.cu) ---------------------------------------------------------
-A_SCALE = 16.0          # power-of-two scale of activations inside the fp16 operand images
+# Power-of-two scale of activations inside the fp16 (hi, lo) operand images: values up to 65504 / 16 = 4094 are
+# representable.  Every activation on the path is normalised (InstanceNorm / LayerNorm outputs, soft-max averages,
+# ReLU of a LayerNorm-fed Linear), far below that; a value beyond it turns into NaN (never a silently wrong number)
+# and raises the sticky device flag that check_numerics() reports.
+A_SCALE = 16.0
 OUT_F32, OUT_PLANES, OUT_AIMG = 0, 1, 2
+
+
+def check_numerics(reset: bool = True) -> None:
+    """Raise if a kernel since the last check had to write an fp16 operand image outside its range (one device
+    synchronisation; RegTR.forward calls it when cfg.check_numerics is set)."""
+    flags = _lib.numeric_flags(reset)
+    if flags & _lib.FLAG_FP16_OVERFLOW:
+        raise FloatingPointError(
+            f"an activation exceeded the fp16 operand range of the tensor-core GEMMs (|x| > {65504.0 / A_SCALE:.0f}) "
+            "or was not finite: the affected outputs are NaN")
 
 
 def gemm_a_image(T: int, K: int, device) -> torch.Tensor:

@@ -2,7 +2,8 @@
 
 Mirrors utils/se3_torch.py of the reference:
   compute_rigid_transform(a, b, weights=None)              :109-163  -> spr_weighted_procrustes
-  compute_rigid_transform_with_sinkhorn(xyz_s, xyz_t, ...)  :204-239  -> spr_sinkhorn_weighted_targets + Procrustes
+  sinkhorn(log_alpha, n_iters, slack)                      :166-202  -> spr_sinkhorn_affinity
+  compute_rigid_transform_with_sinkhorn(xyz_s, xyz_t, ...)  :204-239  -> spr_sinkhorn_affinity + spr_weighted_procrustes
   se3_transform / se3_inv / se3_cat                         small torch helpers kept for callers
 """
 from __future__ import annotations
@@ -38,6 +39,37 @@ def compute_rigid_transform(a: torch.Tensor, b: torch.Tensor, weights: torch.Ten
     out = ops.weighted_procrustes(a.reshape(-1, 3), b.reshape(-1, 3), None if weights is None else weights.reshape(-1),
                                   offsets)
     return out.reshape(*lead, 3, 4)
+
+
+def _batched_pairs(B: int, J: int, K: int, device):
+    return ops.PackedPairs([J] * B, [K] * B, device)
+
+
+def sinkhorn(log_alpha: torch.Tensor, n_iters: int = 5, slack: bool = True) -> torch.Tensor:
+    """Sinkhorn iterations on log_alpha (B, J, K) -> log of the near doubly stochastic matrix (B, J, K)
+    (se3_torch.py:166-202: zero slack row and column, rows then columns normalised by log-sum-exp, n_iters times).
+    Like the reference, the zero padding is applied whether or not `slack` is set."""
+    if log_alpha.dim() != 3:
+        raise RuntimeError("sinkhorn: log_alpha must have shape (B, J, K)")
+    B, J, K = log_alpha.shape
+    pairs = _batched_pairs(B, J, K, log_alpha.device)
+    logp, _, _ = ops.sinkhorn_affinity(log_alpha.contiguous(), pairs, n_iters, slack)
+    return logp.view(B, J, K)
+
+
+def compute_rigid_transform_with_sinkhorn(xyz_s, xyz_t, affinity, slack, n_iters, mask=None):
+    """se3_torch.py:204-239: perm = exp(sinkhorn(affinity)); weighted_t = perm @ xyz_t / (rowsum + 1e-6); Procrustes of
+    xyz_s onto weighted_t with weights = rowsum.  xyz_s (B, J, 3), xyz_t (B, K, 3), affinity (B, J, K); returns
+    (B, 3, 4) squeezed on dim 0 like the reference (`mask` is unused there as well)."""
+    if xyz_s.dim() != 3 or xyz_t.dim() != 3 or affinity.dim() != 3:
+        raise RuntimeError("compute_rigid_transform_with_sinkhorn: batched (B, N, 3) / (B, J, K) inputs expected")
+    B, J, K = affinity.shape
+    assert xyz_s.shape == (B, J, 3) and xyz_t.shape == (B, K, 3)
+    pairs = _batched_pairs(B, J, K, affinity.device)
+    _, wt, w = ops.sinkhorn_affinity(affinity.contiguous(), pairs, n_iters, slack, tgt_xyz=xyz_t.reshape(-1, 3),
+                                     want_log_perm=False)
+    pose = ops.weighted_procrustes(xyz_s.reshape(-1, 3), wt, w, pairs.so)
+    return pose.squeeze(0)
 
 
 def se3_transform(pose, xyz):

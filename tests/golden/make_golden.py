@@ -22,7 +22,7 @@ sys.path.insert(0, HERE)
 import oracle  # noqa: E402
 from oracle import ref_torch  # noqa: E402
 from superpoints_registration_b200 import synthetic  # noqa: E402  (data generator only)
-from weights import filled_state  # noqa: E402
+from weights import damp_transformer, filled_state  # noqa: E402
 
 torch.set_num_threads(8)
 
@@ -289,6 +289,71 @@ def gen_forward(ref):
         save(f"forward_{tag}.npz", **arrays)
 
 
+def gen_sinkhorn(ref):
+    """utils/se3_torch.py `sinkhorn` and `compute_rigid_transform_with_sinkhorn` of the reference on random affinities."""
+    rng = np.random.default_rng(47)
+    B, J, K = 3, 37, 53
+    aff = (rng.normal(size=(B, J, K)) * 3.0).astype(np.float32)
+    xs = rng.normal(size=(B, J, 3)).astype(np.float32)
+    xt = rng.normal(size=(B, K, 3)).astype(np.float32)
+    arrays = {"affinity": aff, "xyz_s": xs, "xyz_t": xt}
+    with torch.no_grad():
+        for it in (1, 3, 5):
+            arrays[f"log_perm_{it}"] = t2n(ref.se3_torch.sinkhorn(torch.from_numpy(aff), n_iters=it, slack=True))
+        arrays["transform_3"] = t2n(ref.se3_torch.compute_rigid_transform_with_sinkhorn(
+            torch.from_numpy(xs), torch.from_numpy(xt), torch.from_numpy(aff), True, 3))
+        arrays["transform_single"] = t2n(ref.se3_torch.compute_rigid_transform_with_sinkhorn(
+            torch.from_numpy(xs[:1]), torch.from_numpy(xt[:1]), torch.from_numpy(aff[:1]), True, 3))
+    save("sinkhorn.npz", **arrays)
+
+
+WELLCOND_ARCH = ["simple", "resnetb", "resnetb_strided", "resnetb", "resnetb", "resnetb_strided", "resnetb", "resnetb",
+                 "resnetb_strided", "resnetb", "resnetb"]          # conf/qk_regtr_full_3dmatch.yaml:64-74 (4-stage)
+WELLCOND_DAMP = 0.3
+
+
+def gen_forward_wellcond(ref):
+    """A WELL-CONDITIONED end-to-end case on the 4-stage architecture BASELINE.json names: tgt is a translated copy of
+    src (translation = a multiple of the coarsest voxel, so both pyramids see the same geometry), and the residual
+    branches of the cross-encoder are damped (weights.damp_transformer) so that conditioned features stay close to the
+    translation-invariant KPConv descriptors.  Corresponding superpoints are then each other's best match and the
+    reference recovers the ground-truth pose; its fp32 result is insensitive to summation order, so the end-to-end
+    pose can be held to north_star's 1e-3 deg / 1e-5 m.  Two variants on the same clouds and weights:
+      argmax    use_sinkhorn=False (the KITTI / ModelNet matching route), target jittered by 1 mm
+      sinkhorn  the 3DMatch yaml's route, exact copy (the reference's affinity rewards LOW correlation, :535, so its
+                untrained Sinkhorn pose is far from the ground truth; it is recorded as is)
+    """
+    rng = np.random.default_rng(81)
+    trans = np.array([0.3, -0.2, 0.1])
+    data = synthetic.make_batch("3dmatch", 2, seed=81, n_points=4000)
+    srcs = data["src_xyz"]
+    arrays = {"weight_seed": np.asarray(1234), "damp": np.asarray(WELLCOND_DAMP, np.float32), "n_pairs": np.asarray(2),
+              "gt_pose": np.concatenate([np.eye(3), trans[:, None]], 1).astype(np.float32)}
+    for tag, jitter, overrides in (("argmax", 0.001, dict(use_sinkhorn=False)), ("sinkhorn", 0.0, {})):
+        tgts = [(s.astype(np.float64) + trans + rng.normal(0, jitter, s.shape)).astype(np.float32) for s in srcs]
+        cfg = ref_torch.load_cfg("qk_regtr_full_3dmatch.yaml", architecture=list(WELLCOND_ARCH), **overrides)
+        model = ref_torch.build_model(cfg, seed=0)
+        sd = model.state_dict()
+        vals = damp_transformer(filled_state({k: tuple(v.shape) for k, v in sd.items()}, 1234), WELLCOND_DAMP)
+        model.load_state_dict({k: (torch.from_numpy(vals[k]) if k in vals else v) for k, v in sd.items()})
+        batch = {"src_xyz": [torch.from_numpy(c) for c in srcs], "tgt_xyz": [torch.from_numpy(c) for c in tgts]}
+        with torch.no_grad():
+            out = model(batch)
+        for k, v in sd.items():
+            if k.endswith("kernel_points"):
+                arrays[f"kp::{k}"] = t2n(v)
+        for i in range(2):
+            arrays[f"src_{i}"] = srcs[i]
+            arrays[f"{tag}_tgt_{i}"] = tgts[i]
+            arrays[f"{tag}_ind_{i}"] = t2n(out["ind_list"][i])
+            arrays[f"{tag}_val_{i}"] = t2n(out["overlap_prob_list"][i])
+            arrays[f"{tag}_n_src_{i}"] = np.asarray(out["src_feat"][i].shape[1])
+            arrays[f"{tag}_n_tgt_{i}"] = np.asarray(out["tgt_feat"][i].shape[1])
+        arrays[f"{tag}_pose"] = t2n(out["pose"])
+        print(tag, "superpoints", [(int(arrays[f"{tag}_n_src_{i}"]), int(arrays[f"{tag}_n_tgt_{i}"])) for i in range(2)])
+    save("forward_wellcond.npz", **arrays)
+
+
 def main():
     oracle.build()
     ref = ref_torch.load()
@@ -298,7 +363,9 @@ def main():
     gen_pose(ref)
     gen_matching(ref)
     gen_refinements(ref)
+    gen_sinkhorn(ref)
     gen_forward(ref)
+    gen_forward_wellcond(ref)
 
 
 if __name__ == "__main__":

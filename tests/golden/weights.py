@@ -42,3 +42,16 @@ def reference_shapes(own_shapes: Mapping[str, Tuple[int, ...]], d_embed: int) ->
     shapes["feature_criterion.W"] = (d_embed, d_embed)
     shapes["feature_criterion_un.W"] = (d_embed, d_embed)
     return shapes
+
+
+def damp_transformer(values: Dict[str, np.ndarray], scale: float) -> Dict[str, np.ndarray]:
+    """Scale the residual branches of the cross-encoder (attention output projections and the second FFN layer) by
+    `scale`.  With scale < 1 the conditioned features stay close to the (translation-invariant) KPConv descriptors,
+    so corresponding superpoints of a moved copy of a cloud are each other's best match: the filler weights then
+    behave like a trained network on such a pair and the end-to-end pose is WELL-CONDITIONED (see
+    tests/golden/make_golden.py:gen_forward_wellcond)."""
+    out = dict(values)
+    for name, v in values.items():
+        if name.startswith("transformer_encoder.") and (".out_proj." in name or ".linear2." in name):
+            out[name] = (v * np.float32(scale)).astype(np.float32)
+    return out

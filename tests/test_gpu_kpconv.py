@@ -354,3 +354,48 @@ def test_kpconv_full_size_properties():
     rows = rng.choice(n, size=512, replace=False)
     exact = oracle.kpconv_forward(pts[rows], pts, idx[rows], x1, w, kp, ext)
     assert np.abs(y1[_t(rows)].cpu().numpy() - exact).max() <= FEAT_RTOL * np.abs(exact).max()
+
+
+@pytest.mark.parametrize("c", [64, 128, 256])
+def test_kpconv_tc_multi_tile_parity_and_determinism(c):
+    """The regime the bench runs: C >= 64 (several channel passes -> the influence-fragment cache
+    is live), >= 3 tiles per CTA (deferred epilogue, tile-parity double buffer, dispenser wrap-around), H = 40 rows
+    from the real searcher (shadow tails of every length), cell-order walk on and off.  Checked: mode 1 against the
+    fp32 SIMT anchor (mode 0) over ALL rows, 512 sampled rows against the fp64 oracle, and five repeated launches
+    bit-identical -- the race detector of this suite (compute-sanitizer is not usable on the pool)."""
+    from superpoints_registration_b200.kernel_points import load_kernels
+    rng = np.random.default_rng(1000 + c)
+    lens = np.array([14000, 9000, 11000, 8000], dtype=np.int32)
+    n, H, r = int(lens.sum()), 40, 0.09
+    pts = rng.uniform(0, 1, size=(n, 3)).astype(np.float32)
+    pts[:14000, 2] *= 0.3                                      # one dense cloud: full rows next to ragged ones
+    tp, tl = _t(pts), _t(lens)
+    grid = ops.CellGrid(tp, tl, r)
+    x = rng.normal(size=(n, c)).astype(np.float32) * 1.5 + 0.2
+    o = ops.instance_norm_lrelu_ex(_t(x), tl, slope=0.1, want_f32=True, kpconv_points=tp)
+    f32, prep = o["f32"], o["kpconv"]
+    w = _t((rng.normal(size=(15, c, c)) / np.sqrt(15 * c)).astype(np.float32))
+    kp = _t(load_kernels(r, 15))
+    ext = r * 2.0 / 2.5
+    for dtype in (torch.int64, torch.int32):
+        idx, mc = grid.query(tp, tl, H, index_dtype=dtype)
+        assert int(mc) > H                                      # the dense cloud truncates at the limit
+        valid = (idx < n).sum(1)
+        assert int(valid.min()) < 10 and int(valid.max()) == H  # shadow tails of many lengths
+        anchor = ops.kpconv_forward(tp, tp, idx, f32, w, kp, ext, mode=0)
+        scale = anchor.abs().max().item()
+        for order in (None, grid.order()):
+            outs = [ops.kpconv_forward_prepared(tp, idx, prep, w, kp, ext, order=order) for _ in range(5)]
+            for other in outs[1:]:
+                assert torch.equal(outs[0], other), (c, dtype, order is not None)
+            err = (outs[0] - anchor).abs().max().item()
+            assert err <= FEAT_RTOL * scale, (c, dtype, order is not None, err, scale)
+        alone = [ops.kpconv_forward(tp, tp, idx, f32, w, kp, ext, mode=1) for _ in range(5)]   # with its own pre-pass
+        for other in alone[1:]:
+            assert torch.equal(alone[0], other)
+        assert (alone[0] - anchor).abs().max().item() <= FEAT_RTOL * scale
+    rows = rng.choice(n, size=512, replace=False)
+    idx_h = idx.cpu().numpy().astype(np.int64)
+    exact = oracle.kpconv_forward(pts[rows], pts, idx_h[rows], f32.cpu().numpy(), w.cpu().numpy(), kp.cpu().numpy(), ext)
+    got = outs[0][_t(rows)].cpu().numpy()
+    assert np.abs(got - exact).max() <= FEAT_RTOL * np.abs(exact).max()

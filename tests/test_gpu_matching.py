@@ -201,6 +201,50 @@ def test_matching_matches_oracle_on_ragged_batch():
                 assert abs(x - y) <= 1e-5 * abs(y)
 
 
+def test_matching_with_non_finite_features_keeps_indices_in_range():
+    """torch.max semantics (qk_regtr_full.py:468,576): a row / column of NaN attention yields a NaN value and an
+    IN-RANGE index (the first NaN), so the gather that follows never leaves the cloud."""
+    rng = np.random.default_rng(8)
+    shapes = [(40, 60), (70, 30)]
+    S = [rng.normal(size=(n, 256)).astype(np.float32) for n, _ in shapes]
+    T = [rng.normal(size=(m, 256)).astype(np.float32) for _, m in shapes]
+    S[0][3] = np.nan                                   # N <= M: source row 3 is all NaN
+    T[1][5] = np.inf                                   # N > M: target column 5 has infinite correlations
+    pairs = ops.PackedPairs([n for n, _ in shapes], [m for _, m in shapes], DEV)
+    corr, attn, val, ind = ops.dual_softmax_match(_t(np.concatenate(S)), _t(np.concatenate(T)), pairs, want_attn=True)
+    ind_h, val_h = ind.cpu().numpy(), val.cpu().numpy()
+    for p, (n, m) in enumerate(shapes):
+        got = ind_h[pairs.h_oo[p]:pairs.h_oo[p + 1]]
+        assert got.min() >= 0 and got.max() < (m if n <= m else n), (p, got.min(), got.max())
+    assert np.isnan(val_h[3]) and ind_h[3] == 0        # first index, like torch.max
+    want = torch.max(attn[:40 * 60].view(40, 60), dim=1)
+    ok = ~torch.isnan(want.values)
+    assert torch.equal(ind[:40][ok], want.indices[ok])
+    pts = _t(rng.normal(size=(200, 3)).astype(np.float32))
+    base = torch.zeros(ind.shape[0], dtype=torch.int32, device=DEV)
+    out = ops.gather_rows3(pts, torch.full_like(ind, 2 ** 31 - 1), base)    # a sentinel index is clamped, not read
+    assert torch.equal(out, pts[-1].expand_as(out))
+
+
+def test_sinkhorn_surface_against_golden(golden_dir):
+    """The reference's callable surface utils/se3_torch.py:166-239 (`sinkhorn`, `compute_rigid_transform_with_sinkhorn`,
+    callers qk_regtr_full.py:536,647) on its own outputs."""
+    from superpoints_registration_b200 import compute_rigid_transform_with_sinkhorn, sinkhorn
+    g = np.load(os.path.join(golden_dir, "sinkhorn.npz"))
+    aff, xs, xt = _t(g["affinity"]), _t(g["xyz_s"]), _t(g["xyz_t"])
+    for it in (1, 3, 5):
+        got = sinkhorn(aff, n_iters=it, slack=True)
+        assert tuple(got.shape) == tuple(aff.shape)
+        assert np.allclose(got.cpu().numpy(), g[f"log_perm_{it}"], rtol=0, atol=2e-5)
+    T = compute_rigid_transform_with_sinkhorn(xs, xt, aff, True, 3)
+    rot, tr = pose_error(T.cpu().numpy(), g["transform_3"])
+    assert tuple(T.shape) == (3, 3, 4) and rot.max() < ROT_TOL_DEG and tr.max() < TRANS_TOL, (rot, tr)
+    T1 = compute_rigid_transform_with_sinkhorn(xs[:1], xt[:1], aff[:1], True, 3)
+    assert tuple(T1.shape) == (3, 4)                                   # squeezed like the reference (:231)
+    rot, tr = pose_error(T1.cpu().numpy(), g["transform_single"])
+    assert rot < ROT_TOL_DEG and tr < TRANS_TOL
+
+
 def _v64(corr, axis):
     a = numpy_ops._softmax(corr, 0) * numpy_ops._softmax(corr, 1)
     return a.max(axis=axis)
@@ -261,11 +305,50 @@ def test_full_forward_against_golden(golden_dir):
             assert key in out
         rot, tr = pose_error(out["pose"].cpu().numpy(), g["pose"])
         print(f"[{tag}] end-to-end pose difference vs reference: rot {rot.max():.2e} deg, trans {tr.max():.2e} m")
-        assert rot.max() < 0.05 and tr.max() < 1e-3, (tag, rot, tr)
+        if cfg.use_sinkhorn:
+            # ill-conditioned by construction of the fixture (see above): the reference's own fp32 evaluation is
+            # ~2e-3 deg from exact arithmetic here; the well-conditioned end-to-end case is
+            # test_full_forward_end_to_end_pose_on_the_well_conditioned_fixture
+            assert rot.max() < 0.05 and tr.max() < 1e-3, (tag, rot, tr)
+        else:
+            assert rot.max() < ROT_TOL_DEG and tr.max() < TRANS_TOL, (tag, rot, tr)
+
+
+@pytest.mark.parametrize("tag", ["argmax", "sinkhorn"])
+def test_full_forward_end_to_end_pose_on_the_well_conditioned_fixture(golden_dir, tag):
+    """END-TO-END pose parity at north_star's tolerance (1e-3 deg, 1e-5 m) against the unmodified reference, raw
+    clouds in, pose out, on the 4-stage architecture of the bench (tests/golden/make_golden.py:gen_forward_wellcond):
+    pyramid, 11 encoder blocks (tcgen05 KPConv and GEMMs), 6 cross-encoder layers, matching and pose solve all on
+    our kernels."""
+    from weights import damp_transformer
+    g = np.load(os.path.join(golden_dir, "forward_wellcond.npz"))
+    cfg = cfgs.threedmatch_4stage_config(use_sinkhorn=False) if tag == "argmax" else cfgs.threedmatch_4stage_config()
+    model = RegTR(cfg).to(DEV).eval()
+    own = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    vals = damp_transformer(filled_state(reference_shapes(own, cfg.d_embed), int(g["weight_seed"])), float(g["damp"]))
+    model.load_state_dict({k: (_t(g[f"kp::{k}"]) if k.endswith("kernel_points") else _t(vals[k])) for k in own})
+    B = int(g["n_pairs"])
+    batch = {"src_xyz": [_t(g[f"src_{i}"]) for i in range(B)], "tgt_xyz": [_t(g[f"{tag}_tgt_{i}"]) for i in range(B)]}
+    out = model(batch)
+    for i in range(B):
+        assert out["src_feat"][i].shape[1] == int(g[f"{tag}_n_src_{i}"])         # same superpoints
+        assert out["tgt_feat"][i].shape[1] == int(g[f"{tag}_n_tgt_{i}"])
+    rot, tr = pose_error(out["pose"].cpu().numpy(), g[f"{tag}_pose"])
+    print(f"[wellcond/{tag}] end-to-end pose vs reference: rot {rot.max():.2e} deg, trans {tr.max():.2e} m")
+    assert rot.max() < ROT_TOL_DEG and tr.max() < TRANS_TOL, (tag, rot, tr)
+    # and the plain route (fp32 SIMT KPConv, unfused blocks, padded nn.MultiheadAttention) agrees to the same bar
+    model.packed_transformer = False
+    for m in model.modules():
+        if m.__class__.__name__ == "KPConv":
+            m.mode = 0
+    plain = model(dict(batch))
+    rot, tr = pose_error(plain["pose"].cpu().numpy(), g[f"{tag}_pose"])
+    assert rot.max() < ROT_TOL_DEG and tr.max() < TRANS_TOL, (tag, "plain", rot, tr)
 
 
 @pytest.mark.parametrize("kind,cfg,kw", [("3dlomatch", cfgs.threedmatch_config(), dict(n_points=4000)),
-                                         ("kitti", cfgs.kitti_config(), dict(n_points=6000))])
+                                         ("kitti", cfgs.kitti_config(), dict(n_points=6000)),
+                                         ("3dmatch", cfgs.threedmatch_4stage_config(), dict(n_points=6000))])
 def test_forward_lomatch_and_kitti_shapes_against_oracle(kind, cfg, kw):
     """BASELINE configs[3] (low-overlap 3DLoMatch-shape pairs, Sinkhorn) and configs[4] (KITTI-shape scans, 4-stage,
     wide neighbourhoods, argmax + Procrustes) through the whole CUDA forward against the CPU restatement of the

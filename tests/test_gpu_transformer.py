@@ -152,13 +152,15 @@ def test_fused_encoder_matches_packed_torch_linears():
     assert err <= 2e-5 * ref.abs().max().item(), (err, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("kind", ["kitti", "modelnet", "3dmatch"])
+@pytest.mark.parametrize("kind", ["kitti", "modelnet", "3dmatch", "3dmatch_4stage"])
 def test_forward_fused_paths_agree_with_plain_paths(kind):
     """Whole forward on every shipped configuration: the fused route (format-aware encoder blocks, tensor-core KPConv,
     packed cross-encoder on our GEMM / attention kernels) against the plain route (fp32 SIMT KPConv, unfused blocks,
     padded nn.MultiheadAttention modules) with the same weights."""
     from superpoints_registration_b200 import synthetic
-    cfg = {"kitti": cfgs.kitti_config, "modelnet": cfgs.modelnet_config, "3dmatch": cfgs.threedmatch_config}[kind]()
+    cfg = {"kitti": cfgs.kitti_config, "modelnet": cfgs.modelnet_config, "3dmatch": cfgs.threedmatch_config,
+           "3dmatch_4stage": cfgs.threedmatch_4stage_config}[kind]()
+    kind = kind.split("_")[0]
     torch.manual_seed(3)
     np.random.seed(3)
     model = RegTR(cfg).to(DEV).eval()
@@ -205,3 +207,45 @@ def test_weight_image_cache_follows_the_tensor():
         ref = x.double() @ w2.double().t()
         assert (ops.linear_tc(x, w2).double() - ref).abs().max().item() <= 3e-6 * ref.abs().max().item()
         del w2
+
+
+@pytest.mark.parametrize("mag", [1e-4, 1e-2, 1.0, 60.0, 3000.0])
+def test_gemm_tc_accuracy_over_input_magnitudes(mag):
+    """The GEMM's activations travel as fp16 (hi, lo) pairs at a fixed power-of-two scale (ops.A_SCALE): fp32-level
+    accuracy must hold from 1e-4 up to the documented limit of ~4094, relative to the output scale."""
+    from superpoints_registration_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(int(mag * 1e4) % 9973)
+    x = torch.randn(300, 256, device=DEV, generator=g) * mag
+    w = torch.randn(192, 256, device=DEV, generator=g) / 16
+    b = torch.randn(192, device=DEV, generator=g)
+    _lib.numeric_flags(reset=True)
+    y = ops.linear_tc(x, w, b)
+    ref = x.double() @ w.double().t() + b.double()
+    assert (y.double() - ref).abs().max().item() <= 3e-6 * ref.abs().max().item()
+    assert _lib.numeric_flags() == 0
+
+
+def test_gemm_tc_operand_overflow_is_loud():
+    """Beyond the fp16 operand range the result is NaN (not a wrong finite number) and the sticky flag is raised."""
+    from superpoints_registration_b200 import _lib
+    x = torch.randn(128, 64, device=DEV)
+    x[5, 7] = 1.0e4                                   # 1e4 * 16 > 65504
+    w = torch.randn(32, 64, device=DEV) / 8
+    _lib.numeric_flags(reset=True)
+    y = ops.linear_tc(x, w)
+    assert torch.isnan(y[5]).all() and torch.isfinite(y[:5]).all() and torch.isfinite(y[6:]).all()
+    with pytest.raises(FloatingPointError):
+        ops.check_numerics()
+    ops.check_numerics()                              # the check cleared the flag
+    # every other producer of operand images raises it as well
+    lens = torch.tensor([128], dtype=torch.int32, device=DEV)
+    big = torch.randn(128, 64, device=DEV)
+    res = torch.zeros_like(big)
+    res[3, 3] = 1.0e4
+    ops.instance_norm_lrelu_ex(big, lens, residual=res, want_f32=False, want_image=True)
+    assert _lib.numeric_flags() & _lib.FLAG_FP16_OVERFLOW
+    t = torch.randn(64, 256, device=DEV)
+    t[0, 0] = float("nan")
+    ops.layernorm256_prepare(t, None, None, None, 1e-5, ops.gemm_a_image(64, 256, DEV))
+    assert _lib.numeric_flags() & _lib.FLAG_FP16_OVERFLOW
+    assert _lib.numeric_flags() == 0

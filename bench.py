@@ -5,9 +5,11 @@
     python bench.py --impl reference --steps K --warmup W     # the reference algorithm on the host CPU cores
 
 A step is one pass of the whole hot path (pyramid -> KPConv encoder -> transformer -> superpoint matching
--> pose) over one batch of `--pairs` synthetic 3DMatch-shape pairs per GPU.  Pairs are independent, so ranks
-shard them with no data-path collective; the only communication is the final all_gather of the poses.
-Rank 0 prints ONE JSON line.
+-> pose) over one batch of `--pairs` synthetic 3DMatch-shape pairs per GPU (BASELINE.json configs[2], the headline).
+Pairs are independent, so ranks shard them with no data-path collective; the only communication is the final
+all_gather of the poses.  Rank 0 prints ONE JSON line; its `configs` object carries the other BASELINE.json
+configurations (single-pair latency, ModelNet-shape, 3DLoMatch-shape, KITTI-shape) measured with the same rules at
+the same number of ranks.
 """
 from __future__ import annotations
 
@@ -39,10 +41,11 @@ def parse_args():
     ap.add_argument("--points", type=int, default=20000, help="nominal points per fragment")
     ap.add_argument("--arch", default="4stage", choices=["3stage", "4stage"],
                     help="4stage = the configuration BASELINE.json names; 3stage = the shipped yaml")
-    ap.add_argument("--no-alt", action="store_true", help="skip the short run of the other architecture")
+    ap.add_argument("--no-alt", action="store_true", help="skip the other BASELINE configurations (`configs` object)")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-pairs", type=int, default=8, help="pairs in the bounded CPU sample (about 5 s of host work)")
+    ap.add_argument("--cpu-workers", type=int, default=0,
+                    help="single-thread CPU worker processes of the CPU baseline / reference arm (0 = one per host core)")
     return ap.parse_args()
 
 
@@ -58,6 +61,15 @@ def workload_name(args):
             f"full forward + pose, Sinkhorn x3")
 
 
+def headline_config(args, world):
+    """The `config` object of the JSON line -- identical for both arms (the reference arm times a bounded sample of it)."""
+    return {"workload": workload_name(args), "pairs_per_gpu_per_step": args.pairs,
+            "parallelism": f"pairs sharded x{world}", "seed": args.seed,
+            "l2": "flushed between timed iterations (256 MiB write)",
+            "outputs": "pose, correspondences, weights, conditioned features; the N x M attention matrices "
+                       "(outputs['attn'], qk_regtr_full.py:295) are not materialised (return_attn=False)"}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -68,65 +80,117 @@ def peaks():
 
 # --------------------------------------------------------------------------------------------------------
 # the reference algorithm on the host CPU (oracle) -- cpu_baseline leg and --impl reference
+# the reference's C++ preprocessing is single-threaded, so the throughput number comes
+# from P = cpu_count independent single-thread worker processes over distinct pairs (aggregate pairs/s); the
+# latency number is one pair with all torch threads.
 # --------------------------------------------------------------------------------------------------------
 
-def cpu_forward_timing(args, n_pairs, repeats=1):
-    """Time the CPU restatement of the reference path on `n_pairs` pairs of the bench workload."""
+_W = {}
+
+
+def _worker_init(arch, points, seed, n_workers):
+    import torch
+    torch.set_num_threads(1)
+    import oracle
+    import superpoints_registration_b200 as spr
+    oracle.build()
+    cfg = make_cfg(arch)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = spr.RegTR(cfg)  # host-side module only used as a container of reference-named random-init weights
+    _W.update(cfg=cfg, sd={k: v.detach().clone() for k, v in model.state_dict().items()},
+              backend="reference" if oracle.have_ref() else "port", points=points, seed=seed, data={})
+
+
+def _worker_pair(index):
+    """One pair of the bench workload through the CPU restatement, single-threaded.  Returns seconds."""
+    from oracle import pipeline
+    from superpoints_registration_b200 import synthetic
+    if index not in _W["data"]:
+        _W["data"][index] = synthetic.threedmatch_pair((_W["seed"] * 100) * 1000 + index, n_points=_W["points"])
+    p = _W["data"][index]
+    t0 = time.perf_counter()
+    pipeline.forward(_W["sd"], _W["cfg"], [p["src"]], [p["tgt"]], backend=_W["backend"])
+    return time.perf_counter() - t0
+
+
+class CpuWorkers:
+    """P single-thread worker processes, each holding the weights and its own pair(s) of the bench workload."""
+
+    def __init__(self, args):
+        import multiprocessing as mp
+        self.n = args.cpu_workers if args.cpu_workers > 0 else (os.cpu_count() or 1)
+        self.pool = mp.get_context("spawn").Pool(self.n, initializer=_worker_init,
+                                                 initargs=(args.arch, args.points, args.seed, self.n))
+
+    def step(self):
+        """One pair per worker, concurrently.  -> (pairs, wall seconds, per-pair seconds)."""
+        t0 = time.perf_counter()
+        per_pair = self.pool.map(_worker_pair, range(self.n), chunksize=1)
+        return self.n, time.perf_counter() - t0, per_pair
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_latency_all_threads(args):
+    """One pair with every host core as a torch thread (the reference's own way of running one forward)."""
     import torch
 
     import oracle
     from oracle import pipeline
     import superpoints_registration_b200 as spr
     from superpoints_registration_b200 import synthetic
-
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg = make_cfg(args.arch)
     torch.manual_seed(0)
     np.random.seed(0)
-    model = spr.RegTR(cfg)  # host-side module only used as a container of reference-named random-init weights
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    data = synthetic.make_batch("3dmatch", n_pairs, seed=args.seed, n_points=args.points)
+    sd = {k: v.detach().clone() for k, v in spr.RegTR(cfg).state_dict().items()}
+    p = synthetic.threedmatch_pair((args.seed * 100) * 1000, n_points=args.points)
     backend = "reference" if oracle.have_ref() else "port"
-    best, stages = None, {}
-    for _ in range(repeats):
-        t = {}
-        t0 = time.perf_counter()
-        pipeline.forward(sd, cfg, data["src_xyz"], data["tgt_xyz"], backend=backend, timings=t)
-        dt = time.perf_counter() - t0
-        if best is None or dt < best:
-            best, stages = dt, t
-    kind = "port"
-    sample = (f"{n_pairs} pair(s) of the bench workload through oracle/pipeline.py:forward (torch-CPU fp32 restatement "
-              f"of the reference network, {cores} torch threads; preprocessing by "
-              f"{'the reference C++ core (oracle/_ref), single-threaded as in the reference' if backend == 'reference' else 'the C restatement'}); "
-              f"stage seconds: " + ", ".join(f"{k}={v:.2f}" for k, v in stages.items()))
-    return n_pairs / best, best, cores, kind, sample
+    stages = {}
+    t0 = time.perf_counter()
+    pipeline.forward(sd, cfg, [p["src"]], [p["tgt"]], backend=backend, timings=stages)
+    return time.perf_counter() - t0, cores, stages, backend
+
+
+def cpu_sample_text(n_workers, backend, extra=""):
+    return (f"{n_workers} single-thread worker processes, one pair of the bench workload each per step, through "
+            f"oracle/pipeline.py:forward (torch-CPU fp32 restatement of the reference network; preprocessing by "
+            f"{'the reference C++ core (oracle/_ref)' if backend == 'reference' else 'the C restatement'}, "
+            f"single-threaded as in the reference); value = aggregate pairs/s" + extra)
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # warm-up once (imports, thread pools), then K bounded steps
-    n = max(1, args.cpu_pairs)
-    for _ in range(min(args.warmup, 1)):
-        cpu_forward_timing(args, n)
-    times = []
-    info = None
+    import oracle
+    oracle.build()
+    backend = "reference" if oracle.have_ref() else "port"
+    workers = CpuWorkers(args)
+    for _ in range(max(args.warmup, 0)):
+        workers.step()
+    pairs, walls = 0, []
     for _ in range(max(1, args.steps)):
-        v, dt, cores, kind, sample = cpu_forward_timing(args, n)
-        times.append(dt)
-        info = (cores, kind, sample)
-    total = sum(times)
-    value = n * len(times) / total
-    cores, kind, sample = info
+        n, dt, _ = workers.step()
+        pairs += n
+        walls.append(dt)
+    workers.close()
+    total = sum(walls)
+    value = pairs / total
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "pairs_per_step": n, "host": "cpu"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(walls),
+        "warmup": max(args.warmup, 0), "ms_per_step": 1e3 * total / len(walls),
+        "ms_per_step_median": 1e3 * float(np.median(walls)), "ms_per_step_best": 1e3 * min(walls),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": headline_config(args, max(world, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers.n, "kind": "port",
+                         "sample": cpu_sample_text(workers.n, backend, f"; a step = {workers.n} pairs (bounded sample of "
+                                                   f"the {args.pairs}-pair batch), host only")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -150,7 +214,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
                  str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -196,12 +260,57 @@ def kpconv_algorithmic_bytes(nq, H, cin, cout, K=15):
     return nq * H * (4 * cin + 12 + 4) + nq * (12 + 4 * cout) + 4 * K * cin * cout + 12 * K
 
 
+def kpconv_compulsory_bytes(nq, ns, H, cin, cout, K=15):
+    """every support row and point read once, the index matrix, the output, the weights."""
+    return ns * (4 * cin + 12) + 4 * nq * H + nq * (12 + 4 * cout) + 4 * K * cin * cout + 12 * K
+
+
+class Runner:
+    """One configuration on this rank: model, device-resident batch, pinned host copy, step functions."""
+
+    def __init__(self, cfg, kind, B, seed, dev, world, gen_kw):
+        import torch
+        import superpoints_registration_b200 as spr
+        from superpoints_registration_b200 import synthetic
+        self.torch, self.dev, self.world, self.B = torch, dev, world, B
+        torch.manual_seed(0)
+        np.random.seed(0)
+        self.model = spr.RegTR(cfg).to(dev).eval()
+        self.model.return_attn = False  # see config["outputs"]
+        data = synthetic.make_batch(kind, B, seed=seed, **gen_kw)
+        host = [torch.from_numpy(c) for c in data["src_xyz"] + data["tgt_xyz"]]
+        self.cloud_lens = [c.shape[0] for c in host]
+        self.points_per_step = int(sum(self.cloud_lens))
+        # end-to-end staging: all fragments of the step in ONE pinned buffer -> one host-to-device copy per step
+        self.host_all = torch.cat(host, dim=0).pin_memory()
+        self.h2d_bytes = int(self.host_all.numel() * 4)
+        self.dev_batch = {"src_xyz": [c.to(dev) for c in host[:B]], "tgt_xyz": [c.to(dev) for c in host[B:]]}
+        self.gathered = torch.empty((world * B, 3, 4), device=dev) if world > 1 else None
+        self.host_pose = torch.empty((B, 3, 4)).pin_memory()
+
+    def step(self, batch):
+        import torch.distributed as dist
+        pose = self.model(dict(batch))["pose"]
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, pose.contiguous())
+        return pose
+
+    def step_resident(self):
+        return self.step(self.dev_batch)
+
+    def step_e2e(self):
+        clouds = self.torch.split(self.host_all.to(self.dev, non_blocking=True), self.cloud_lens)
+        pose = self.step({"src_xyz": list(clouds[:self.B]), "tgt_xyz": list(clouds[self.B:])})
+        self.host_pose.copy_(pose, non_blocking=True)
+        return pose
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     import superpoints_registration_b200 as spr
-    from superpoints_registration_b200 import _lib, ops, synthetic
+    from superpoints_registration_b200 import _lib, ops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -233,35 +342,58 @@ def run_ours(args):
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
 
-    cfg = make_cfg(args.arch)
-    torch.manual_seed(0)
-    np.random.seed(0)
-    model = spr.RegTR(cfg).to(dev).eval()
-    model.return_attn = False  # outputs['attn'] (N x M per pair) is training/analysis output; pose path needs corr only
-    B = args.pairs
-    data = synthetic.make_batch("3dmatch", B, seed=args.seed * 100 + rank, n_points=args.points)
-    host_src = [torch.from_numpy(c).pin_memory() for c in data["src_xyz"]]
-    host_tgt = [torch.from_numpy(c).pin_memory() for c in data["tgt_xyz"]]
-    dev_batch = {"src_xyz": [c.to(dev) for c in host_src], "tgt_xyz": [c.to(dev) for c in host_tgt]}
-    h2d_bytes = sum(c.numel() * 4 for c in host_src + host_tgt)
-    # end-to-end staging: all fragments of the step in ONE pinned buffer -> one host-to-device copy per step
-    cloud_lens = [c.shape[0] for c in host_src + host_tgt]
-    host_all = torch.cat(host_src + host_tgt, dim=0).pin_memory()
-    gathered = torch.empty((world * B, 3, 4), device=dev) if world > 1 else None
-    host_pose = torch.empty((B, 3, 4)).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def step(batch):
-        out = model(dict(batch))
-        pose = out["pose"]
+    def barrier():
         if world > 1:
-            dist.all_gather_into_tensor(gathered, pose.contiguous())
-        return pose
+            dist.barrier()
+        torch.cuda.synchronize()
 
-    # ---- KPConv instrumentation (CUDA events on the launching stream) ----
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize; CUDA events per step on the launching stream; L2 flushed
+        between steps (outside the timed intervals).  -> list of per-step milliseconds."""
+        evs = []
+        barrier()
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    def reduce_max(values):
+        t = torch.tensor(values, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def measure(runner, steps, warmup):
+        """-> dict(value, ms stats, e2e) with the max over ranks of the summed step times."""
+        for _ in range(warmup):
+            runner.step_resident()
+        ms = timed(runner.step_resident, steps)
+        for _ in range(2):
+            runner.step_e2e()
+        ms_e = timed(runner.step_e2e, steps)
+        tot, tot_e, med, best = reduce_max([sum(ms), sum(ms_e), float(np.median(ms)), min(ms)])
+        pairs = world * runner.B * steps
+        return {"value": pairs / (tot * 1e-3), "unit": UNIT, "pairs_per_gpu_per_step": runner.B, "steps": steps,
+                "ms_per_step": tot / steps, "ms_per_step_median": med, "ms_per_step_best": best,
+                "points_per_gpu_per_step": runner.points_per_step,
+                "e2e": {"value": pairs / (tot_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes,
+                        "d2h_bytes_per_step": int(runner.host_pose.numel() * 4), "ms_per_step": tot_e / steps}}
+
+    # ---- headline: BASELINE.json configs[2] ----
+    B = args.pairs
+    head = Runner(make_cfg(args.arch), "3dmatch", B, args.seed * 100 + rank, dev, world, dict(n_points=args.points))
+
+    # KPConv instrumentation (CUDA events on the launching stream)
     records = []
-    raw_kpconv = ops.kpconv_forward
     recording = {"on": False}
+    raw_kpconv, raw_prepared = ops.kpconv_forward, ops.kpconv_forward_prepared
 
     def timed_kpconv(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent, mode=0):
         if not recording["on"]:
@@ -270,14 +402,10 @@ def run_ours(args):
         e0.record()
         y = raw_kpconv(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent, mode)
         e1.record()
-        records.append((e0, e1, q_pts.shape[0], neighb_inds.shape[1], weights.shape[1], weights.shape[2]))
+        records.append((e0, e1, q_pts.shape[0], s_pts.shape[0], neighb_inds.shape[1], weights.shape[1], weights.shape[2]))
         return y
 
-    ops.kpconv_forward = timed_kpconv
-
     # the encoder blocks feed the tensor-core KPConv with operands written by the preceding normalisation kernel
-    raw_prepared = ops.kpconv_forward_prepared
-
     def timed_prepared(q_pts, neighb_inds, feats, weights, kernel_points, extent, **kw):
         if not recording["on"]:
             return raw_prepared(q_pts, neighb_inds, feats, weights, kernel_points, extent, **kw)
@@ -285,70 +413,39 @@ def run_ours(args):
         e0.record()
         y = raw_prepared(q_pts, neighb_inds, feats, weights, kernel_points, extent, **kw)
         e1.record()
-        records.append((e0, e1, q_pts.shape[0], neighb_inds.shape[1], weights.shape[1], weights.shape[2]))
+        records.append((e0, e1, q_pts.shape[0], feats.x16.shape[0], neighb_inds.shape[1], weights.shape[1],
+                        weights.shape[2]))
         return y
 
-    ops.kpconv_forward_prepared = timed_prepared
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    ops.kpconv_forward, ops.kpconv_forward_prepared = timed_kpconv, timed_prepared
 
     for _ in range(max(args.warmup, 3)):
-        step(dev_batch)
+        head.step_resident()
     barrier()
 
-    # ---- timed region 1: inputs resident in HBM ----
+    # timed region 1: inputs resident in HBM
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
     recording["on"] = True
-    evs = []
-    barrier()
-    for _ in range(args.steps):
-        flush.zero_()  # L2 flush between timed iterations (outside the timed interval)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step(dev_batch)
-        e1.record()
-        evs.append((e0, e1))
-    barrier()
+    ms = timed(head.step_resident, args.steps)
     recording["on"] = False
     launches = _lib.launch_count() - launches0
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # timed region 2: end to end through the public API with HOST buffers (H2D of the clouds, D2H of the poses)
+    ms_e = timed(head.step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    ops.kpconv_forward, ops.kpconv_forward_prepared = raw_kpconv, raw_prepared
+    total_ms, e2e_ms, med_ms, best_ms = reduce_max([sum(ms), sum(ms_e), float(np.median(ms)), min(ms)])
 
-    # ---- timed region 2: end to end through the public API with HOST buffers ----
-    e2e_evs = []
-    barrier()
-    for _ in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        clouds = torch.split(host_all.to(dev, non_blocking=True), cloud_lens)
-        batch = {"src_xyz": list(clouds[:B]), "tgt_xyz": list(clouds[B:])}
-        pose = step(batch)
-        host_pose.copy_(pose, non_blocking=True)
-        e1.record()
-        e2e_evs.append((e0, e1))
-    barrier()
-    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
-
-    t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
-
+    line = None
     if rank == 0:
         pairs_total = world * B * args.steps
-        value = pairs_total / (total_ms * 1e-3)
-        e2e_value = pairs_total / (e2e_ms * 1e-3)
         peak, peak_src = peaks()
-        k_bytes = sum(kpconv_algorithmic_bytes(nq, H, ci, co) for (_, _, nq, H, ci, co) in records)
+        k_bytes = sum(kpconv_algorithmic_bytes(nq, H, ci, co) for (_, _, nq, ns, H, ci, co) in records)
+        k_comp = sum(kpconv_compulsory_bytes(nq, ns, H, ci, co) for (_, _, nq, ns, H, ci, co) in records)
         k_ms = sum(a.elapsed_time(b) for (a, b, *_r) in records)
-        k_flops = sum(2.0 * nq * 15 * ci * co + 2.0 * nq * 15 * H * ci for (_, _, nq, H, ci, co) in records)
+        k_flops = sum(2.0 * nq * 15 * ci * co + 2.0 * nq * 15 * H * ci for (_, _, nq, ns, H, ci, co) in records)
         achieved = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "kpconv_traffic.json")
@@ -358,57 +455,76 @@ def run_ours(args):
             except Exception:
                 traffic = None
         per_layer = {}
-        for (a, b, nq, H, ci, co) in records:
-            key = f"Nq={nq},H={H},C={ci}->{co}"
-            d = per_layer.setdefault(key, {"ms": 0.0, "bytes": 0, "n": 0})
+        for (a, b, nq, ns, H, ci, co) in records:
+            d = per_layer.setdefault(f"Nq={nq},H={H},C={ci}->{co}", {"ms": 0.0, "bytes": 0})
             d["ms"] += a.elapsed_time(b)
             d["bytes"] += kpconv_algorithmic_bytes(nq, H, ci, co)
-            d["n"] += 1
+        n_rec = max(len(records), 1)
+        cfg_obj = headline_config(args, world)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "pairs_per_gpu_per_step": B, "parallelism": f"pairs sharded x{world}",
-                       "points_per_step": int(sum(c.shape[0] for c in host_src + host_tgt)),
-                       "l2": "flushed between timed iterations (256 MiB write)", "seed": args.seed},
+            "metric": METRIC, "value": pairs_total / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "ms_per_step_median": med_ms, "ms_per_step_best": best_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_obj,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": k_bytes / max(len(records), 1),
-                         "kernel_ms_per_launch": k_ms / max(len(records), 1), "kernel": "k_kpconv_tc (operands pre-split by the preceding norm kernel) + k_kpconv_cin1 stem: all KPConv layers of the step",
+                         "traffic": traffic, "algorithmic_bytes_per_launch": k_bytes / n_rec,
+                         "compulsory_bytes_per_launch": k_comp / n_rec, "kernel_ms_per_launch": k_ms / n_rec,
+                         "kernel": "k_kpconv_tc (operands pre-split by the preceding norm kernel) + k_kpconv_cin1 stem: "
+                                   "all KPConv layers of the step",
                          "peak_source": peak_src, "algorithmic_bytes_per_step": k_bytes / max(args.steps, 1),
+                         "compulsory_bytes_per_step": k_comp / max(args.steps, 1),
                          "kpconv_ms_per_step": k_ms / max(args.steps, 1),
                          "kpconv_tflops_fp32": k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0,
                          "per_layer_gbs": {k: v["bytes"] / (v["ms"] * 1e-3) / 1e9 for k, v in per_layer.items()}},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": int(host_pose.numel() * 4), "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(launches),
+            "e2e": {"value": pairs_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": head.h2d_bytes,
+                    "d2h_bytes_per_step": int(head.host_pose.numel() * 4), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches), "points_per_gpu_per_step": head.points_per_step,
             "clocks": clocks,
         }
-        if world == 1 and not args.no_alt:
-            # the other architecture of the same yaml, short run, same timing rules (reported beside, not the headline)
-            other = "3stage" if args.arch == "4stage" else "4stage"
-            torch.manual_seed(0)
-            alt_model = spr.RegTR(make_cfg(other)).to(dev).eval()
-            alt_model.return_attn = False
-            for _ in range(3):
-                alt_model(dict(dev_batch))
-            torch.cuda.synchronize()
-            alt_ms = 0.0
-            alt_steps = max(3, args.steps // 2)
-            for _ in range(alt_steps):
-                flush.zero_()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                alt_model(dict(dev_batch))
-                e1.record()
-                torch.cuda.synchronize()
-                alt_ms += e0.elapsed_time(e1)
-            line["alt"] = {"workload": workload_name(argparse.Namespace(**{**vars(args), "arch": other})),
-                           "value": B * alt_steps / (alt_ms * 1e-3), "unit": UNIT, "ms_per_step": alt_ms / alt_steps,
-                           "steps": alt_steps}
-            del alt_model
+    del head
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configurations, same timing rules, same number of ranks ----
+    if not args.no_alt:
+        alt_steps, alt_warm = max(5, args.steps // 2), 3
+        other_arch = "3stage" if args.arch == "4stage" else "4stage"
+        alts = [
+            ("configs[0] 3DMatch single pair latency (~5k pts, shipped 3-stage yaml, batch 1)",
+             spr.threedmatch_config(), "3dmatch", 1, dict(n_points=5000)),
+            ("configs[1] ModelNet40-shape pairs (717 pts, partial-to-partial), batch 64",
+             spr.modelnet_config(), "modelnet", 64, {}),
+            (f"configs[2] variant: the {other_arch} architecture of the same yaml, ~20k pts, batch {B}",
+             make_cfg(other_arch), "3dmatch", B, dict(n_points=args.points)),
+            (f"configs[3] 3DLoMatch-shape low-overlap pairs (10-30% overlap, ~20k pts, {args.arch}), batch {B}",
+             make_cfg(args.arch), "3dlomatch", B, dict(n_points=args.points)),
+            ("configs[4] KITTI-odometry-shape scans (~30k pts, voxel 0.3 m, 4-stage, argmax + Procrustes), batch 8 per GPU",
+             spr.kitti_config(first_subsampling_dl=0.3), "kitti", 8, dict(n_points=30000, voxel=0.3)),
+        ]
+        out = {}
+        for name, cfg, kind, b, kw in alts:
+            runner = Runner(cfg, kind, b, args.seed * 100 + 17 + rank, dev, world, kw)
+            res = measure(runner, alt_steps, alt_warm)
+            if b == 1:
+                res["latency_ms_median"] = res["ms_per_step_median"]
+            out[name] = res
+            del runner
+            torch.cuda.empty_cache()
+        if rank == 0:
+            line["configs"] = out
+
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            v, dt, cores, kind, sample = cpu_forward_timing(args, max(1, args.cpu_pairs), repeats=2)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+            workers = CpuWorkers(args)
+            workers.step()  # warm-up (imports, page-in)
+            n, dt, per_pair = workers.step()
+            workers.close()
+            lat, cores, stages, backend = cpu_latency_all_threads(args)
+            line["cpu_baseline"] = {
+                "value": n / dt, "unit": UNIT, "cores": workers.n, "kind": "port",
+                "sample": cpu_sample_text(workers.n, backend, f"; one step of {n} pairs ({dt:.1f} s wall, "
+                                          f"{float(np.mean(per_pair)):.1f} s per pair per worker)"),
+                "latency_all_threads_s": lat, "latency_threads": cores,
+                "latency_stage_seconds": {k: round(v, 3) for k, v in stages.items()}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

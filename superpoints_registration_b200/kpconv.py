@@ -10,6 +10,11 @@ Same names, argument meaning, output dict keys ('points', 'neighbors', 'pools', 
 'stack_lengths'), dtypes (int64 indices, shadow = number of support points, int32 lengths) and errors
 (RuntimeError from the native layer).  Everything runs on the device the inputs live on; there is no CPU
 round trip (the reference does `.cpu()` in, `.to(device)` out, kpconv.py:313-314,410-416) and no CPU fallback.
+
+Inside, the pyramid is int32 and lazy where nobody looks: the searcher writes 4-byte indices (half the bytes the
+search writes and the KPConv / max-pool kernels read back), the int64 tensors of the reference's dict are made
+when a caller reads an entry, and 'upsamples' -- which the reference computes (kpconv.py:384) but the encoder-only
+model never reads -- is searched on first access.  The contract is the key and its value, not eagerness.
 """
 from __future__ import annotations
 
@@ -85,16 +90,63 @@ def _split_levels(architecture: Sequence[str]):
     return levels
 
 
+class _IndexList:
+    """One list entry of the pyramid dict ('neighbors' / 'pools' / 'upsamples'): a sequence of index matrices that
+    hands out the reference's dtype (int64) on access while the kernels keep reading the int32 matrices the searcher
+    wrote (`raw(l)`).  Entries may be thunks: they are searched when first read."""
+
+    def __init__(self, n_levels: int, dtype: torch.dtype):
+        self._raw = [None] * n_levels       # int32 (or the requested index dtype) tensors, or callables producing them
+        self._out = [None] * n_levels
+        self._dtype = dtype
+
+    def set(self, level: int, value) -> None:
+        self._raw[level] = value
+        self._out[level] = None
+
+    def raw(self, level: int) -> torch.Tensor:
+        v = self._raw[level]
+        if callable(v):
+            v = v()
+            self._raw[level] = v
+        return v
+
+    def __len__(self):
+        return len(self._raw)
+
+    def __getitem__(self, level):
+        if isinstance(level, slice):
+            return [self[i] for i in range(*level.indices(len(self)))]
+        if level < 0:
+            level += len(self)
+        if self._out[level] is None:
+            r = self.raw(level)
+            self._out[level] = r if r.dtype == self._dtype else r.to(self._dtype)
+        return self._out[level]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def __repr__(self):
+        return f"_IndexList({[None if callable(r) or r is None else tuple(r.shape) for r in self._raw]})"
+
+
 class Preprocessor(nn.Module):
     """Computes the metadata used by the KPConv encoder (drop-in for kpconv.py:295-418)."""
 
-    def __init__(self, cfg, exact_width: bool = True, index_dtype: torch.dtype = torch.int64):
+    def __init__(self, cfg, exact_width: bool = True, index_dtype: torch.dtype = torch.int64,
+                 lazy_upsamples: bool = True):
         super().__init__()
         self.cfg = cfg
         # exact_width: trim each index matrix to min(batch max_count, limit) columns like the reference
         # (one extra host sync at the end).  False keeps `limit` columns; the extra columns are all-shadow.
         self.exact_width = exact_width
+        # index_dtype: what the dict entries hand out (the reference: int64, kpconv.py:396-398).  The searcher always
+        # writes int32; the wide copy of an entry is made when (and only if) a caller reads it.
         self.index_dtype = index_dtype
+        # lazy_upsamples: 'upsamples' (3 of the 10 searches of a 4-stage pyramid, never read by the encoder-only
+        # model) are searched on first access instead of up front
+        self.lazy_upsamples = lazy_upsamples
 
     @torch.no_grad()
     def forward(self, pts: List[torch.Tensor]) -> Dict[str, List[torch.Tensor]]:
@@ -106,18 +158,28 @@ class Preprocessor(nn.Module):
             raise RuntimeError("Preprocessor: inputs must be CUDA tensors (no CPU fallback on the B200 path)")
         limits = cfg.neighborhood_limits
         levels = _split_levels(cfg.architecture)
+        n_levels = len(levels)
 
         points = torch.cat([p.to(torch.float32) for p in pts], dim=0).contiguous()
         host_lengths = [int(p.shape[0]) for p in pts]
         lengths = ops.to_device_async(host_lengths, torch.int32, device)
         r = float(cfg.first_subsampling_dl) * float(cfg.conv_radius)
 
-        out_points, out_neighbors, out_pools, out_ups, out_lens = [], [], [], [], []
+        out_points, out_lens = [], []
+        out_neighbors, out_pools, out_ups = (_IndexList(n_levels, self.index_dtype) for _ in range(3))
         out_order = []  # per level: the points in cell order (private: processing order of the KPConv kernels)
         out_host_lens = []  # per level: stack_lengths as a host list (private: saves consumers a device read)
-        widths = []  # (list, position, max_count tensor)
+        widths = []  # (list, level, max_count tensor, limit)
         grid = ops.CellGrid(points, lengths, r)
-        empty_idx = lambda: torch.zeros((0, 1), dtype=torch.int64, device=device)
+        exact = self.exact_width
+        empty_idx = lambda: torch.zeros((0, 1), dtype=torch.int32, device=device)
+
+        def upsample_search(next_grid, q_pts, q_lens, limit):
+            up_i, mc = next_grid.query(q_pts, q_lens, limit, index_dtype=torch.int32)
+            if exact:
+                up_i = up_i[:, :min(int(mc.item()), limit)]
+            return up_i
+
         for li, (has_conv, strided) in enumerate(levels):
             limit = int(limits[li])
             pending = None
@@ -127,17 +189,20 @@ class Preprocessor(nn.Module):
                 dl = 2.0 * r / float(cfg.conv_radius)
                 pending = ops.grid_subsample_batch_async(points, lengths, dl)
             if has_conv:
-                conv_i, mc = grid.query(points, lengths, limit, index_dtype=self.index_dtype)
+                conv_i, mc = grid.query(points, lengths, limit, index_dtype=torch.int32)
                 widths.append((out_neighbors, li, mc, limit))
             else:
                 conv_i = empty_idx()
             if strided:
                 pool_p, pool_b, pool_host = pending.finish()
-                pool_i, mc = grid.query(pool_p, pool_b, limit, index_dtype=self.index_dtype)
+                pool_i, mc = grid.query(pool_p, pool_b, limit, index_dtype=torch.int32)
                 widths.append((out_pools, li, mc, limit))
                 next_grid = ops.CellGrid(pool_p, pool_b, 2.0 * r)
-                up_i, mc = next_grid.query(points, lengths, limit, index_dtype=self.index_dtype)
-                widths.append((out_ups, li, mc, limit))
+                if self.lazy_upsamples:
+                    up_i = (lambda g=next_grid, q=points, ql=lengths, lim=limit: upsample_search(g, q, ql, lim))
+                else:
+                    up_i, mc = next_grid.query(points, lengths, limit, index_dtype=torch.int32)
+                    widths.append((out_ups, li, mc, limit))
             else:
                 pool_i, up_i = empty_idx(), empty_idx()
                 pool_p = torch.zeros((0, 3), dtype=torch.float32, device=device)
@@ -145,19 +210,19 @@ class Preprocessor(nn.Module):
                 next_grid, pool_host = None, []
             out_points.append(points)
             out_order.append(grid.order() if grid is not None else None)
-            out_neighbors.append(conv_i)
-            out_pools.append(pool_i)
-            out_ups.append(up_i)
+            out_neighbors.set(li, conv_i)
+            out_pools.set(li, pool_i)
+            out_ups.set(li, up_i)
             out_lens.append(lengths)
             out_host_lens.append(host_lengths)
             points, lengths, grid, host_lengths = pool_p, pool_b, next_grid, pool_host
             r *= 2.0
 
-        if self.exact_width and widths:
+        if exact and widths:
             counts = torch.cat([w[2] for w in widths]).tolist()  # the single sync for all widths
             for (lst, li, _, limit), mc in zip(widths, counts):
                 w = min(int(mc), limit)
-                lst[li] = lst[li][:, :w]
+                lst.set(li, lst.raw(li)[:, :w])
         meta = Pyramid({"points": out_points, "neighbors": out_neighbors, "pools": out_pools, "upsamples": out_ups,
                         "stack_lengths": out_lens})
         meta.order, meta.host_lengths = out_order, out_host_lens
@@ -167,9 +232,15 @@ class Preprocessor(nn.Module):
 class Pyramid(dict):
     """The reference's collate dict (exactly its five keys) plus two by-products of building it, kept as attributes
     so that code iterating over the dict sees nothing new: `order[l]` = the level's points in cell order (the
-    KPConv kernels walk their queries in it), `host_lengths[l]` = stack_lengths[l] as a host list."""
+    KPConv kernels walk their queries in it), `host_lengths[l]` = stack_lengths[l] as a host list.
+    `index(key, l)` is what the kernels read: the int32 matrix behind entry l of 'neighbors' / 'pools' / 'upsamples'
+    (`meta[key][l]` is the same matrix in the reference's int64)."""
     order = None
     host_lengths = None
+
+    def index(self, key: str, level: int) -> torch.Tensor:
+        lst = self[key]
+        return lst.raw(level) if isinstance(lst, _IndexList) else lst[level]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -148,10 +148,13 @@ class UnaryBlock(nn.Module):
 
 
 def _level_io(batch, layer_ind: int, strided: bool):
+    # a Pyramid hands the kernels its int32 index matrices (batch.index); any other mapping with the reference's keys
+    # (e.g. a dict of int64 tensors built by a caller) is used as is
+    index = getattr(batch, 'index', None) or (lambda key, l: batch[key][l])
     if strided:
-        return (batch['points'][layer_ind + 1], batch['points'][layer_ind], batch['pools'][layer_ind],
+        return (batch['points'][layer_ind + 1], batch['points'][layer_ind], index('pools', layer_ind),
                 batch['stack_lengths'][layer_ind + 1])
-    return (batch['points'][layer_ind], batch['points'][layer_ind], batch['neighbors'][layer_ind],
+    return (batch['points'][layer_ind], batch['points'][layer_ind], index('neighbors', layer_ind),
             batch['stack_lengths'][layer_ind])
 
 

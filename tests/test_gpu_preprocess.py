@@ -241,3 +241,34 @@ def test_pyramid_full_size_properties():
             cnt = int((sqdist32(pts[rr][None], seg) < r2).sum())
             assert int(valid[list(rows).index(rr)].sum()) == min(cnt, idx.shape[1])
         r *= 2
+
+
+def test_pyramid_is_int32_inside_and_lazy_where_nobody_looks():
+    """The dict hands out the reference's int64 matrices; the kernels read the int32 ones behind them (Pyramid.index),
+    and 'upsamples' is searched on first access.  Same values whichever way the pyramid is built."""
+    from superpoints_registration_b200 import _lib
+    cfg = cfgs.threedmatch_4stage_config()
+    clouds = [_t(c) for c in _clouds("3dmatch", 2, 4, n_points=5000)]
+    n0 = _lib.launch_count()
+    meta = Preprocessor(cfg)(clouds)
+    lazy_launches = _lib.launch_count() - n0
+    n0 = _lib.launch_count()
+    eager = Preprocessor(cfg, lazy_upsamples=False)(clouds)
+    eager_launches = _lib.launch_count() - n0
+    assert lazy_launches < eager_launches                       # three searches were not run
+    assert set(meta.keys()) == {"points", "neighbors", "pools", "upsamples", "stack_lengths"}
+    n0 = _lib.launch_count()
+    for key in ("neighbors", "pools"):
+        for l in range(len(meta["points"])):
+            wide, raw = meta[key][l], meta.index(key, l)
+            assert wide.dtype == torch.int64 and raw.dtype == torch.int32 and wide.shape == raw.shape
+            assert torch.equal(wide, raw.long()) and torch.equal(wide, eager[key][l])
+            assert meta[key][l] is wide                          # converted once
+    assert _lib.launch_count() == n0                             # nothing searched so far
+    ups = list(meta["upsamples"])                                # first access runs the three searches
+    assert _lib.launch_count() > n0
+    assert len(ups) == len(meta["points"]) and tuple(ups[-1].shape) == (0, 1)
+    for l, u in enumerate(ups):
+        assert u.dtype == torch.int64 and torch.equal(u, eager["upsamples"][l])
+    m32 = Preprocessor(cfg, index_dtype=torch.int32)(clouds)
+    assert m32["neighbors"][0].dtype == torch.int32 and torch.equal(m32["neighbors"][0].long(), meta["neighbors"][0])

@@ -73,6 +73,19 @@ SPR_API size_t spr_grid_subsample_workspace_bytes(int n_points, int n_clouds);
 SPR_API int spr_grid_subsample_batch(const float* d_points, const int32_t* d_lengths, int n_points, int n_clouds,
                              float sample_dl, float* d_out_points, int32_t* d_out_lengths, int32_t* d_out_total,
                              void* d_workspace, size_t workspace_bytes, void* stream);
+/* Same binning with a choice of voxel lattice and representative:
+ *   SPR_SUBSAMPLE_REFERENCE  the CPU reference (spr_grid_subsample_batch): per-cloud origin, barycentre = sum * (1/count)
+ *   SPR_SUBSAMPLE_MEAN       voxel = floor(p / dl) on the global lattice, mean = sum / count: MinkowskiEngine's
+ *                            UNWEIGHTED_AVERAGE quantisation as the reference's PreprocessorGPU uses it (kpconv.py:221-243)
+ *   SPR_SUBSAMPLE_FIRST      same lattice, the first point (input order) of every voxel unchanged: the KITTI loader's
+ *                            down-sampler (data_loaders/kitti_pred.py:12-14,203-204)
+ * Voxels come out per cloud in first-occurrence order in every mode. */
+#define SPR_SUBSAMPLE_REFERENCE 0
+#define SPR_SUBSAMPLE_MEAN 1
+#define SPR_SUBSAMPLE_FIRST 2
+SPR_API int spr_grid_subsample_batch_ex(const float* d_points, const int32_t* d_lengths, int n_points, int n_clouds,
+                                float sample_dl, int mode, float* d_out_points, int32_t* d_out_lengths,
+                                int32_t* d_out_total, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Batched fixed-radius neighbour search.
@@ -99,6 +112,16 @@ SPR_API int spr_cell_grid_order(const void* d_grid_workspace, int n_supports, in
 SPR_API int spr_radius_query(const float* d_queries, const int32_t* d_q_lengths, int n_queries, int n_clouds,
                      const void* d_grid_workspace, int n_supports, float radius, int limit, void* d_out_idx,
                      int idx_is_64, int row_stride, int32_t* d_out_max_count, void* stream);
+/* Same search with a choice of which in-radius supports a row keeps when there are more than `limit`:
+ *   SPR_ORDER_NEAREST  the `limit` nearest, nearest first (the reference's CPU Preprocessor; what spr_radius_query does)
+ *   SPR_ORDER_INDEX    the first `limit` in support-index order (pytorch3d.ops.ball_query as the reference's
+ *                      PreprocessorGPU calls it, models/backbone_kpconv/kpconv.py:265-292; the matrix then keeps all
+ *                      `limit` columns) */
+#define SPR_ORDER_NEAREST 0
+#define SPR_ORDER_INDEX 1
+SPR_API int spr_radius_query_ex(const float* d_queries, const int32_t* d_q_lengths, int n_queries, int n_clouds,
+                        const void* d_grid_workspace, int n_supports, float radius, int limit, int order, void* d_out_idx,
+                        int idx_is_64, int row_stride, int32_t* d_out_max_count, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * KPConv layer forward (rigid kernel, linear influence, sum aggregation -- the only mode any shipped

@@ -176,3 +176,70 @@ def pose_error(pred, gt) -> Tuple[float, float]:
     rot = 2 * np.degrees(np.arcsin(np.clip(fro / (2 * np.sqrt(2)), 0, 1)))
     tr = np.linalg.norm(p[..., :3, 3] - g[..., :3, 3], axis=-1)
     return rot, tr
+
+
+# ------------------------------------------------------------------------------------------------
+# PreprocessorGPU-compatible mode (models/backbone_kpconv/kpconv.py:421-549) and the KITTI front end.
+# PARITY UNPINNED: the arithmetic lives in pytorch3d (ball_query), MinkowskiEngine (sparse quantisation) and kiss_icp
+# (voxel down-sampling), none of which is vendored, pinned or installed; the functions below restate their DOCUMENTED
+# behaviour as the reference calls them, and the CUDA path is tested against these restatements only.
+# ------------------------------------------------------------------------------------------------
+
+def ball_query_first_k(queries, supports, q_lens, s_lens, radius, K):
+    """kpconv.py:265-292 (batch_neighbors_kpconv_gpu): pytorch3d.ops.ball_query keeps, per query, the FIRST K supports of
+    the same cloud in index order with d2 < r2 (not the K nearest); the matrix is always K wide, missing entries are
+    Ns_total.  d2 with the same fp32 rounding sequence as the CPU path (three products, two sums)."""
+    q, s = np.asarray(queries, np.float32), np.asarray(supports, np.float32)
+    out = np.full((len(q), K), len(s), np.int64)
+    r2 = np.float32(radius) * np.float32(radius)
+    qo = so = 0
+    for nq, ns in zip(q_lens, s_lens):
+        sc = s[so:so + ns]
+        for i in range(qo, qo + nq):
+            d = q[i] - sc
+            d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+            hit = np.nonzero(d2 < r2)[0][:K]
+            out[i, :len(hit)] = hit + so
+        qo += nq
+        so += ns
+    return out
+
+
+def voxel_mean_me(points, lens, dl):
+    """kpconv.py:221-243 (batch_grid_subsampling_kpconv_gpu): MinkowskiEngine quantises coordinates floor(p / dl) (global
+    origin, per batch element) and averages the points of a voxel (UNWEIGHTED_AVERAGE).  ME's output order and
+    summation order are unspecified ("not deterministic", :219-220); here: voxels in first-occurrence order per cloud,
+    members summed in input order in fp32, divided by the count."""
+    pts = np.asarray(points, np.float32)
+    dl32 = np.float32(dl)
+    out, out_lens, o = [], [], 0
+    for n in lens:
+        seg = pts[o:o + n]
+        keys = np.floor(seg / dl32).astype(np.int64)
+        order, sums, counts = {}, [], []
+        for i, k in enumerate(map(tuple, keys)):
+            v = order.get(k)
+            if v is None:
+                order[k] = len(sums)
+                sums.append(seg[i].copy())
+                counts.append(1)
+            else:
+                sums[v] = sums[v] + seg[i]          # fp32, input order
+                counts[v] += 1
+        out.append(np.stack([sm / np.float32(c) for sm, c in zip(sums, counts)]) if sums else np.zeros((0, 3), np.float32))
+        out_lens.append(len(sums))
+        o += n
+    return np.concatenate(out, 0).astype(np.float32), np.asarray(out_lens, np.int32)
+
+
+def voxel_first_point(points, voxel):
+    """data_loaders/kitti_pred.py:12-14 (kiss_icp VoxelDownsample): the first point, in input order, of every voxel
+    floor(p / voxel); emitted here in input order (kiss_icp emits its hash map's order)."""
+    pts = np.asarray(points, np.float32)
+    keys = np.floor(pts / np.float32(voxel)).astype(np.int64)
+    seen, keep = set(), []
+    for i, k in enumerate(map(tuple, keys)):
+        if k not in seen:
+            seen.add(k)
+            keep.append(i)
+    return pts[np.asarray(keep, np.int64)]

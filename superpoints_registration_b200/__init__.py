@@ -5,14 +5,15 @@ operator surface.  Importing the package does not need a GPU; calling any operat
 when libspr_b200.so has not been built.
 """
 from .config import Config, load_config, threedmatch_config, threedmatch_4stage_config, kitti_config, modelnet_config
-from .kpconv import Preprocessor, KPFEncoder, batch_grid_subsampling_kpconv, batch_neighbors_kpconv
+from .kpconv import Preprocessor, PreprocessorGPU, KPFEncoder, batch_grid_subsampling_kpconv, batch_neighbors_kpconv
 from .kpconv_blocks import KPConv, UnaryBlock, SimpleBlock, ResnetBottleneckBlock, BatchNormBlock, max_pool, block_decider
 from .se3 import compute_rigid_transform, compute_rigid_transform_with_sinkhorn, sinkhorn, se3_transform, se3_inv, se3_cat, pose_error
 from .model import RegTR
+from . import frontends
 
 __all__ = [
     "Config", "load_config", "threedmatch_config", "threedmatch_4stage_config", "kitti_config", "modelnet_config",
-    "Preprocessor", "KPFEncoder", "batch_grid_subsampling_kpconv", "batch_neighbors_kpconv",
+    "Preprocessor", "PreprocessorGPU", "KPFEncoder", "batch_grid_subsampling_kpconv", "batch_neighbors_kpconv",
     "KPConv", "UnaryBlock", "SimpleBlock", "ResnetBottleneckBlock", "BatchNormBlock", "max_pool", "block_decider",
-    "compute_rigid_transform", "compute_rigid_transform_with_sinkhorn", "sinkhorn", "se3_transform", "se3_inv", "se3_cat", "pose_error", "RegTR",
+    "compute_rigid_transform", "compute_rigid_transform_with_sinkhorn", "sinkhorn", "se3_transform", "se3_inv", "se3_cat", "pose_error", "RegTR", "frontends",
 ]

@@ -24,11 +24,15 @@ _SIGNATURES = {
     "spr_numeric_flags": (ctypes.c_uint, [c_int]),
     "spr_grid_subsample_workspace_bytes": (c_size_t, [c_int, c_int]),
     "spr_grid_subsample_batch": (c_int, [c_fp, c_fp, c_int, c_int, c_float, c_fp, c_fp, c_fp, c_fp, c_size_t, c_void_p]),
+    "spr_grid_subsample_batch_ex": (c_int, [c_fp, c_fp, c_int, c_int, c_float, c_int, c_fp, c_fp, c_fp, c_fp, c_size_t,
+                                            c_void_p]),
     "spr_cell_grid_workspace_bytes": (c_size_t, [c_int, c_int]),
     "spr_cell_grid_build": (c_int, [c_fp, c_fp, c_int, c_int, c_float, c_fp, c_size_t, c_void_p]),
     "spr_cell_grid_order": (c_int, [c_fp, c_int, c_int, c_fp, c_void_p]),
     "spr_radius_query": (c_int, [c_fp, c_fp, c_int, c_int, c_fp, c_int, c_float, c_int, c_fp, c_int, c_int, c_fp,
                                  c_void_p]),
+    "spr_radius_query_ex": (c_int, [c_fp, c_fp, c_int, c_int, c_fp, c_int, c_float, c_int, c_int, c_fp, c_int, c_int, c_fp,
+                                    c_void_p]),
     "spr_kpconv_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "spr_kpconv_forward": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_fp, c_int, c_fp, c_int, c_fp, c_int,
                                    c_float, c_fp, c_int, c_int, c_int, c_fp, c_size_t, c_void_p]),

@@ -32,9 +32,28 @@ __device__ __forceinline__ unsigned long long f2u64(float v) {
 }
 
 
-__global__ void k_cloud_grid(const uint32_t* __restrict__ bb, int B, float dl, CloudGrid* __restrict__ g) {
+// mode SPR_SUBSAMPLE_REFERENCE: the CPU reference's per-cloud origin and (p - origin) / dl voxels.
+// other modes (MinkowskiEngine-style mean, first point): voxel = floor(p / dl) on a global lattice; (ox, oy, oz) then
+// hold the cloud's lowest voxel coordinate (an integer-valued float) so that the local key stays non-negative.
+__global__ void k_cloud_grid(const uint32_t* __restrict__ bb, int B, float dl, int mode, CloudGrid* __restrict__ g) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  if (mode != SPR_SUBSAMPLE_REFERENCE) {
+    CloudGrid cg;
+    float lo[3], hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = floorf(__fdiv_rn(ord2f(bb[3 * b + a]), dl));
+      hi[a] = floorf(__fdiv_rn(ord2f(bb[3 * (B + b) + a]), dl));
+    }
+    cg.ox = lo[0];
+    cg.oy = lo[1];
+    cg.oz = lo[2];
+    cg.nx = f2u64(__fsub_rn(hi[0], lo[0])) + 1ull;
+    cg.ny = f2u64(__fsub_rn(hi[1], lo[1])) + 1ull;
+    g[b] = cg;
+    return;
+  }
   // grid_subsampling.cpp:27  originCorner = floor(minCorner * (1/sampleDl)) * sampleDl   (all fp32)
   const float inv = __fdiv_rn(1.0f, dl);
   float o[3], mx[3];
@@ -64,7 +83,7 @@ __device__ __forceinline__ uint32_t hash_mix(unsigned long long key, int cloud) 
 
 // slot_rep: -1 = empty, otherwise the index of the point that claimed the slot.
 __global__ void __launch_bounds__(kThreads)
-    k_key_insert(const float* __restrict__ pts, const int* __restrict__ offs, int B, int n, float dl,
+    k_key_insert(const float* __restrict__ pts, const int* __restrict__ offs, int B, int n, float dl, int mode,
                  const CloudGrid* __restrict__ grids, unsigned long long* __restrict__ keys, int* __restrict__ slot_rep,
                  int* __restrict__ slot_min, int* __restrict__ slot_cnt, int* __restrict__ point_slot,
                  uint32_t table_mask) {
@@ -72,10 +91,18 @@ __global__ void __launch_bounds__(kThreads)
   if (i >= n) return;
   const int b = find_cloud(offs, B, i);
   const CloudGrid g = grids[b];
-  // grid_subsampling.cpp:53-56 (fp32 subtract, fp32 divide, floor)
-  unsigned long long ix = f2u64(floorf(__fdiv_rn(__fsub_rn(pts[3 * (size_t)i + 0], g.ox), dl)));
-  unsigned long long iy = f2u64(floorf(__fdiv_rn(__fsub_rn(pts[3 * (size_t)i + 1], g.oy), dl)));
-  unsigned long long iz = f2u64(floorf(__fdiv_rn(__fsub_rn(pts[3 * (size_t)i + 2], g.oz), dl)));
+  unsigned long long ix, iy, iz;
+  if (mode == SPR_SUBSAMPLE_REFERENCE) {
+    // grid_subsampling.cpp:53-56 (fp32 subtract, fp32 divide, floor)
+    ix = f2u64(floorf(__fdiv_rn(__fsub_rn(pts[3 * (size_t)i + 0], g.ox), dl)));
+    iy = f2u64(floorf(__fdiv_rn(__fsub_rn(pts[3 * (size_t)i + 1], g.oy), dl)));
+    iz = f2u64(floorf(__fdiv_rn(__fsub_rn(pts[3 * (size_t)i + 2], g.oz), dl)));
+  } else {
+    // floor(p / dl) on the global lattice, relative to the cloud's lowest voxel (integer-valued floats: exact)
+    ix = f2u64(__fsub_rn(floorf(__fdiv_rn(pts[3 * (size_t)i + 0], dl)), g.ox));
+    iy = f2u64(__fsub_rn(floorf(__fdiv_rn(pts[3 * (size_t)i + 1], dl)), g.oy));
+    iz = f2u64(__fsub_rn(floorf(__fdiv_rn(pts[3 * (size_t)i + 2], dl)), g.oz));
+  }
   const unsigned long long key = ix + g.nx * iy + g.nx * g.ny * iz;
   keys[i] = key;
   __threadfence();  // the key must be visible before this point can become a slot representative
@@ -143,7 +170,7 @@ __global__ void __launch_bounds__(kThreads)
 
 __global__ void __launch_bounds__(kThreads)
     k_barycentre(const float* __restrict__ pts, const int* __restrict__ members, const int* __restrict__ vox_off,
-                 const int* __restrict__ vox_cnt, const int* __restrict__ total, float* __restrict__ out) {
+                 const int* __restrict__ vox_cnt, const int* __restrict__ total, int mode, float* __restrict__ out) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= *total) return;
   const int beg = vox_off[v], cnt = vox_cnt[v];
@@ -188,11 +215,30 @@ __global__ void __launch_bounds__(kThreads)
       last = best;
     }
   }
-  // grid_subsampling.cpp:87 -- the double 1.0/count is narrowed to float by operator*(PointXYZ, float)
-  const float w = (float)(1.0 / (double)cnt);
-  out[3 * (size_t)v + 0] = __fmul_rn(sx, w);
-  out[3 * (size_t)v + 1] = __fmul_rn(sy, w);
-  out[3 * (size_t)v + 2] = __fmul_rn(sz, w);
+  if (mode == SPR_SUBSAMPLE_REFERENCE) {
+    // grid_subsampling.cpp:87 -- the double 1.0/count is narrowed to float by operator*(PointXYZ, float)
+    const float w = (float)(1.0 / (double)cnt);
+    out[3 * (size_t)v + 0] = __fmul_rn(sx, w);
+    out[3 * (size_t)v + 1] = __fmul_rn(sy, w);
+    out[3 * (size_t)v + 2] = __fmul_rn(sz, w);
+  } else {  // unweighted average: sum / count
+    const float c = (float)cnt;
+    out[3 * (size_t)v + 0] = __fdiv_rn(sx, c);
+    out[3 * (size_t)v + 1] = __fdiv_rn(sy, c);
+    out[3 * (size_t)v + 2] = __fdiv_rn(sz, c);
+  }
+}
+
+// first-point mode: a voxel is represented by its lowest-index member (its head), copied unchanged
+__global__ void __launch_bounds__(kThreads)
+    k_first_point(const float* __restrict__ pts, const int* __restrict__ point_slot, const int* __restrict__ slot_min,
+                  const int* __restrict__ head_scan, int n, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || slot_min[point_slot[i]] != i) return;
+  const int v = head_scan[i];
+  out[3 * (size_t)v + 0] = pts[3 * (size_t)i + 0];
+  out[3 * (size_t)v + 1] = pts[3 * (size_t)i + 1];
+  out[3 * (size_t)v + 2] = pts[3 * (size_t)i + 2];
 }
 
 uint32_t table_size_for(int n) {
@@ -229,7 +275,17 @@ extern "C" size_t spr_grid_subsample_workspace_bytes(int n_points, int n_clouds)
 extern "C" int spr_grid_subsample_batch(const float* d_points, const int32_t* d_lengths, int n_points, int n_clouds,
                                         float sample_dl, float* d_out_points, int32_t* d_out_lengths,
                                         int32_t* d_out_total, void* d_workspace, size_t workspace_bytes, void* stream_) {
+  return spr_grid_subsample_batch_ex(d_points, d_lengths, n_points, n_clouds, sample_dl, SPR_SUBSAMPLE_REFERENCE,
+                                     d_out_points, d_out_lengths, d_out_total, d_workspace, workspace_bytes, stream_);
+}
+
+extern "C" int spr_grid_subsample_batch_ex(const float* d_points, const int32_t* d_lengths, int n_points, int n_clouds,
+                                           float sample_dl, int mode, float* d_out_points, int32_t* d_out_lengths,
+                                           int32_t* d_out_total, void* d_workspace, size_t workspace_bytes,
+                                           void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPR_CHECK_ARG(mode == SPR_SUBSAMPLE_REFERENCE || mode == SPR_SUBSAMPLE_MEAN || mode == SPR_SUBSAMPLE_FIRST,
+                "grid_subsample: unknown mode %d", mode);
   SPR_CHECK_ARG(n_points > 0 && n_clouds > 0, "grid_subsample: empty input (n_points=%d, n_clouds=%d)", n_points,
                 n_clouds);
   SPR_CHECK_ARG(sample_dl > 0.f, "grid_subsample: sample_dl must be > 0");
@@ -267,13 +323,13 @@ extern "C" int spr_grid_subsample_batch(const float* d_points, const int32_t* d_
   if (rc) return rc;
   rc = cloud_bboxes(d_points, offs, B, n, bb, stream);
   if (rc) return rc;
-  k_cloud_grid<<<(B + 127) / 128, 128, 0, stream>>>(bb, B, sample_dl, grids);
+  k_cloud_grid<<<(B + 127) / 128, 128, 0, stream>>>(bb, B, sample_dl, mode, grids);
   SPR_LAUNCH_CHECK("k_cloud_grid");
   SPR_CUDA(cudaMemsetAsync(slot_rep, 0xff, (size_t)T * 4, stream));  // -1
   SPR_CUDA(cudaMemsetAsync(slot_min, 0x7f, (size_t)T * 4, stream));  // 0x7f7f7f7f > any index
   SPR_CUDA(cudaMemsetAsync(slot_cnt, 0, (size_t)T * 4, stream));
   SPR_CUDA(cudaMemsetAsync(vox_cnt, 0, (size_t)n * 4 * 3, stream));  // vox_cnt, vox_off, vox_fill
-  k_key_insert<<<gp, kThreads, 0, stream>>>(d_points, offs, B, n, sample_dl, grids, keys, slot_rep, slot_min, slot_cnt,
+  k_key_insert<<<gp, kThreads, 0, stream>>>(d_points, offs, B, n, sample_dl, mode, grids, keys, slot_rep, slot_min, slot_cnt,
                                             point_slot, T - 1);
   SPR_LAUNCH_CHECK("k_key_insert");
   k_heads<<<gp, kThreads, 0, stream>>>(point_slot, slot_min, n, head);
@@ -284,11 +340,16 @@ extern "C" int spr_grid_subsample_batch(const float* d_points, const int32_t* d_
   SPR_LAUNCH_CHECK("k_vox_counts");
   k_out_lengths<<<(B + 127) / 128, 128, 0, stream>>>(head, offs, B, n, d_out_total, d_out_lengths);
   SPR_LAUNCH_CHECK("k_out_lengths");
+  if (mode == SPR_SUBSAMPLE_FIRST) {
+    k_first_point<<<gp, kThreads, 0, stream>>>(d_points, point_slot, slot_min, head, n, d_out_points);
+    SPR_LAUNCH_CHECK("k_first_point");
+    return SPR_OK;
+  }
   rc = exclusive_scan_i32(vox_cnt, vox_off, (size_t)n, nullptr, scan_tmp, stream);  // entries >= M are zero
   if (rc) return rc;
   k_scatter_members<<<gp, kThreads, 0, stream>>>(point_slot, slot_vox, vox_off, vox_fill, n, members);
   SPR_LAUNCH_CHECK("k_scatter_members");
-  k_barycentre<<<gp, kThreads, 0, stream>>>(d_points, members, vox_off, vox_cnt, d_out_total, d_out_points);
+  k_barycentre<<<gp, kThreads, 0, stream>>>(d_points, members, vox_off, vox_cnt, d_out_total, mode, d_out_points);
   SPR_LAUNCH_CHECK("k_barycentre");
   return SPR_OK;
 }

@@ -170,7 +170,10 @@ __device__ __forceinline__ int compact_stage(unsigned long long* __restrict__ sk
   return min(cnt, limit);
 }
 
-template <typename IdxT>
+// BY_INDEX: rows hold the first `limit` in-radius supports in INDEX order (pytorch3d ball_query as the reference's
+// PreprocessorGPU calls it, kpconv.py:280-286) instead of the `limit` nearest in distance order: the same staging
+// and ranking with the distance word of the key left at zero.
+template <typename IdxT, bool BY_INDEX>
 __global__ void __launch_bounds__(kThreads, 4)
     k_radius_query(const float* __restrict__ q, const int* __restrict__ q_offs, int B, int nq,
                    const CellGrid* __restrict__ grids, const int* __restrict__ cell_start,
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 4)
         const float4 c = __ldg(sorted + s_beg[warp][r] + t);
         const float d2 = sqdist_exact(px, py, pz, c.x, c.y, c.z);
         hit = d2 < r2;
-        key = make_key(d2, __float_as_int(c.w));
+        key = BY_INDEX ? (unsigned long long)(unsigned int)__float_as_int(c.w) : make_key(d2, __float_as_int(c.w));
       }
       const unsigned hm = __ballot_sync(kFull, hit);
       in_radius += __popc(hm);
@@ -405,9 +408,10 @@ extern "C" int spr_cell_grid_build(const float* d_supports, const int32_t* d_s_l
   return SPR_OK;
 }
 
-extern "C" int spr_radius_query(const float* d_queries, const int32_t* d_q_lengths, int n_queries, int n_clouds,
-                                const void* d_grid_workspace, int n_supports, float radius, int limit, void* d_out_idx,
-                                int idx_is_64, int row_stride, int32_t* d_out_max_count, void* stream_) {
+extern "C" int spr_radius_query_ex(const float* d_queries, const int32_t* d_q_lengths, int n_queries, int n_clouds,
+                                   const void* d_grid_workspace, int n_supports, float radius, int limit, int order,
+                                   void* d_out_idx, int idx_is_64, int row_stride, int32_t* d_out_max_count,
+                                   void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SPR_CHECK_ARG(n_queries > 0 && n_clouds > 0 && n_supports > 0, "radius_query: empty input (nq=%d, ns=%d, B=%d)",
                 n_queries, n_supports, n_clouds);
@@ -415,6 +419,7 @@ extern "C" int spr_radius_query(const float* d_queries, const int32_t* d_q_lengt
                 SPR_MAX_NEIGHBOR_LIMIT);
   SPR_CHECK_ARG(row_stride >= limit, "radius_query: row_stride < limit");
   SPR_CHECK_ARG(radius > 0.f, "radius_query: radius must be > 0");
+  SPR_CHECK_ARG(order == SPR_ORDER_NEAREST || order == SPR_ORDER_INDEX, "radius_query: unknown row order %d", order);
   SPR_CHECK_ARG(d_queries && d_q_lengths && d_grid_workspace && d_out_idx && d_out_max_count, "radius_query: null pointer");
   GridLayout L = carve_grid(const_cast<void*>(d_grid_workspace), (size_t)-1, n_supports, n_clouds);
   int* q_offs = L.q_offs;
@@ -425,15 +430,23 @@ extern "C" int spr_radius_query(const float* d_queries, const int32_t* d_q_lengt
   int blocks = (n_queries + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int max_blocks = kNumSMs * 8 * 4;
   if (blocks > max_blocks) blocks = max_blocks;
-  if (idx_is_64)
-    k_radius_query<long long><<<blocks, kThreads, 0, stream>>>(d_queries, q_offs, n_clouds, n_queries, L.grids,
-                                                               L.cell_start, L.sorted, n_supports, r2, limit,
-                                                               static_cast<long long*>(d_out_idx), row_stride,
-                                                               d_out_max_count);
-  else
-    k_radius_query<int><<<blocks, kThreads, 0, stream>>>(d_queries, q_offs, n_clouds, n_queries, L.grids, L.cell_start,
-                                                         L.sorted, n_supports, r2, limit, static_cast<int*>(d_out_idx),
-                                                         row_stride, d_out_max_count);
+#define SPR_RQ(T, BYI)                                                                                               \
+  k_radius_query<T, BYI><<<blocks, kThreads, 0, stream>>>(d_queries, q_offs, n_clouds, n_queries, L.grids, L.cell_start, \
+                                                          L.sorted, n_supports, r2, limit, static_cast<T*>(d_out_idx),   \
+                                                          row_stride, d_out_max_count)
+  if (order == SPR_ORDER_INDEX) {
+    if (idx_is_64) SPR_RQ(long long, true); else SPR_RQ(int, true);
+  } else {
+    if (idx_is_64) SPR_RQ(long long, false); else SPR_RQ(int, false);
+  }
+#undef SPR_RQ
   SPR_LAUNCH_CHECK("k_radius_query");
   return SPR_OK;
+}
+
+extern "C" int spr_radius_query(const float* d_queries, const int32_t* d_q_lengths, int n_queries, int n_clouds,
+                                const void* d_grid_workspace, int n_supports, float radius, int limit, void* d_out_idx,
+                                int idx_is_64, int row_stride, int32_t* d_out_max_count, void* stream_) {
+  return spr_radius_query_ex(d_queries, d_q_lengths, n_queries, n_clouds, d_grid_workspace, n_supports, radius, limit,
+                             SPR_ORDER_NEAREST, d_out_idx, idx_is_64, row_stride, d_out_max_count, stream_);
 }

@@ -135,9 +135,20 @@ class Preprocessor(nn.Module):
     """Computes the metadata used by the KPConv encoder (drop-in for kpconv.py:295-418)."""
 
     def __init__(self, cfg, exact_width: bool = True, index_dtype: torch.dtype = torch.int64,
-                 lazy_upsamples: bool = True):
+                 lazy_upsamples: bool = True, mode: str = "reference"):
         super().__init__()
         self.cfg = cfg
+        # mode: "reference" = the CPU Preprocessor (kpconv.py:295-418), the oracle north_star names: the `limit` NEAREST
+        # neighbours, barycentres on per-cloud lattices, matrices trimmed to the batch-wide max count.
+        # "gpu_compat" = the PreprocessorGPU the reference's model instantiates (kpconv.py:421-549,
+        # qk_regtr_full.py:40): the FIRST `limit` neighbours in index order (pytorch3d ball_query), voxel means on the
+        # global lattice floor(p / dl) (MinkowskiEngine quantisation), `limit` columns always, int64 stack_lengths.
+        # PARITY UNPINNED for gpu_compat: pytorch3d / MinkowskiEngine are neither vendored nor installed and the
+        # reference calls its own result "not deterministic" (kpconv.py:219-220,422-424); tests compare against a
+        # NumPy restatement of the documented behaviour (oracle/numpy_ops.py).
+        if mode not in ("reference", "gpu_compat"):
+            raise ValueError(f"Preprocessor mode '{mode}': expected 'reference' or 'gpu_compat'")
+        self.mode = mode
         # exact_width: trim each index matrix to min(batch max_count, limit) columns like the reference
         # (one extra host sync at the end).  False keeps `limit` columns; the extra columns are all-shadow.
         self.exact_width = exact_width
@@ -171,11 +182,13 @@ class Preprocessor(nn.Module):
         out_host_lens = []  # per level: stack_lengths as a host list (private: saves consumers a device read)
         widths = []  # (list, level, max_count tensor, limit)
         grid = ops.CellGrid(points, lengths, r)
-        exact = self.exact_width
+        compat = self.mode == "gpu_compat"
+        exact = self.exact_width and not compat          # ball_query matrices are always `limit` wide
+        sub_mode = "mean" if compat else "reference"
         empty_idx = lambda: torch.zeros((0, 1), dtype=torch.int32, device=device)
 
         def upsample_search(next_grid, q_pts, q_lens, limit):
-            up_i, mc = next_grid.query(q_pts, q_lens, limit, index_dtype=torch.int32)
+            up_i, mc = next_grid.query(q_pts, q_lens, limit, index_dtype=torch.int32, by_index=compat)
             if exact:
                 up_i = up_i[:, :min(int(mc.item()), limit)]
             return up_i
@@ -187,21 +200,21 @@ class Preprocessor(nn.Module):
                 # the subsampling goes first and its sizes travel to the host while the convolution neighbours
                 # (independent of them) are searched: the device is never idle waiting for the host to learn M
                 dl = 2.0 * r / float(cfg.conv_radius)
-                pending = ops.grid_subsample_batch_async(points, lengths, dl)
+                pending = ops.grid_subsample_batch_async(points, lengths, dl, sub_mode)
             if has_conv:
-                conv_i, mc = grid.query(points, lengths, limit, index_dtype=torch.int32)
+                conv_i, mc = grid.query(points, lengths, limit, index_dtype=torch.int32, by_index=compat)
                 widths.append((out_neighbors, li, mc, limit))
             else:
                 conv_i = empty_idx()
             if strided:
                 pool_p, pool_b, pool_host = pending.finish()
-                pool_i, mc = grid.query(pool_p, pool_b, limit, index_dtype=torch.int32)
+                pool_i, mc = grid.query(pool_p, pool_b, limit, index_dtype=torch.int32, by_index=compat)
                 widths.append((out_pools, li, mc, limit))
                 next_grid = ops.CellGrid(pool_p, pool_b, 2.0 * r)
                 if self.lazy_upsamples:
                     up_i = (lambda g=next_grid, q=points, ql=lengths, lim=limit: upsample_search(g, q, ql, lim))
                 else:
-                    up_i, mc = next_grid.query(points, lengths, limit, index_dtype=torch.int32)
+                    up_i, mc = next_grid.query(points, lengths, limit, index_dtype=torch.int32, by_index=compat)
                     widths.append((out_ups, li, mc, limit))
             else:
                 pool_i, up_i = empty_idx(), empty_idx()
@@ -223,10 +236,21 @@ class Preprocessor(nn.Module):
             for (lst, li, _, limit), mc in zip(widths, counts):
                 w = min(int(mc), limit)
                 lst.set(li, lst.raw(li)[:, :w])
+        lens32 = out_lens
+        if compat:   # batched_lengths are int64 in PreprocessorGPU (kpconv.py:453,235-243); the kernels keep the int32 ones
+            out_lens = [l.to(torch.int64) for l in out_lens]
         meta = Pyramid({"points": out_points, "neighbors": out_neighbors, "pools": out_pools, "upsamples": out_ups,
                         "stack_lengths": out_lens})
-        meta.order, meta.host_lengths = out_order, out_host_lens
+        meta.order, meta.host_lengths, meta.lengths32 = out_order, out_host_lens, lens32
         return meta
+
+
+class PreprocessorGPU(Preprocessor):
+    """Drop-in for the reference's PreprocessorGPU (kpconv.py:421-549): Preprocessor(cfg, mode="gpu_compat")."""
+
+    def __init__(self, cfg, **kw):
+        kw.setdefault("mode", "gpu_compat")
+        super().__init__(cfg, **kw)
 
 
 class Pyramid(dict):
@@ -237,6 +261,7 @@ class Pyramid(dict):
     (`meta[key][l]` is the same matrix in the reference's int64)."""
     order = None
     host_lengths = None
+    lengths32 = None
 
     def index(self, key: str, level: int) -> torch.Tensor:
         lst = self[key]

@@ -151,11 +151,10 @@ def _level_io(batch, layer_ind: int, strided: bool):
     # a Pyramid hands the kernels its int32 index matrices (batch.index); any other mapping with the reference's keys
     # (e.g. a dict of int64 tensors built by a caller) is used as is
     index = getattr(batch, 'index', None) or (lambda key, l: batch[key][l])
+    lens = getattr(batch, 'lengths32', None) or batch['stack_lengths']
     if strided:
-        return (batch['points'][layer_ind + 1], batch['points'][layer_ind], index('pools', layer_ind),
-                batch['stack_lengths'][layer_ind + 1])
-    return (batch['points'][layer_ind], batch['points'][layer_ind], index('neighbors', layer_ind),
-            batch['stack_lengths'][layer_ind])
+        return (batch['points'][layer_ind + 1], batch['points'][layer_ind], index('pools', layer_ind), lens[layer_ind + 1])
+    return (batch['points'][layer_ind], batch['points'][layer_ind], index('neighbors', layer_ind), lens[layer_ind])
 
 
 class SimpleBlock(nn.Module):
@@ -220,7 +219,7 @@ class ResnetBottleneckBlock(nn.Module):
         reads: unary1's normalised output as pre-split KPConv rows, the KPConv norm as the operand image of unary2,
         the block output as rows + operand image of the next block's unary GEMMs."""
         strided = 'strided' in self.block_name
-        pre_lengths = batch['stack_lengths'][self.layer_ind]
+        pre_lengths = (getattr(batch, 'lengths32', None) or batch['stack_lengths'])[self.layer_ind]
         q_pts, s_pts, inds, post_lengths = _level_io(batch, self.layer_ind, strided)
         n_in = features.shape[0]
         stash = batch.get('_operand_image')
@@ -253,7 +252,7 @@ class ResnetBottleneckBlock(nn.Module):
             return self._forward_fused(features, batch)
         batch['_operand_image'] = None  # this route writes plain rows only
         strided = 'strided' in self.block_name
-        pre_lengths = batch['stack_lengths'][self.layer_ind]
+        pre_lengths = (getattr(batch, 'lengths32', None) or batch['stack_lengths'])[self.layer_ind]
         q_pts, s_pts, inds, post_lengths = _level_io(batch, self.layer_ind, strided)
 
         x = self.unary1(features, pre_lengths) if isinstance(self.unary1, UnaryBlock) else features

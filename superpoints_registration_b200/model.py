@@ -246,7 +246,9 @@ class RegTR(nn.Module):
         if cfg.get('use_overlap_as_weights', False) and cfg.get('remove_points_from_val', False):
             raise NotImplementedError("use_overlap_as_weights with remove_points_from_val: weights and points differ "
                                       "in length in the reference (:497-500, :546)")
-        self.preprocessor = Preprocessor(cfg)
+        # cfg.preprocessor = 'gpu_compat' selects the PreprocessorGPU-compatible pyramid (what the reference's model
+        # instantiates, qk_regtr_full.py:40); the default is the CPU Preprocessor north_star names as the oracle
+        self.preprocessor = Preprocessor(cfg, mode=cfg.get('preprocessor', 'reference'))
         self.kpf_encoder = KPFEncoder(cfg, cfg.d_embed)
         self.feat_proj = nn.Linear(self.kpf_encoder.encoder_skip_dims[-1], cfg.d_embed, bias=True)
         if cfg.get('pos_emb_type', 'sine') != 'sine':

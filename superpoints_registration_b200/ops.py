@@ -78,9 +78,14 @@ class PendingSubsample:
         return self._out[:host[self._b]], self._meta[:self._b], host[:self._b]
 
 
-def grid_subsample_batch_async(points: torch.Tensor, lengths: torch.Tensor, sample_dl: float) -> PendingSubsample:
+SUBSAMPLE_MODES = {"reference": 0, "mean": 1, "first_point": 2}   # SPR_SUBSAMPLE_* of include/spr_b200.h
+
+
+def grid_subsample_batch_async(points: torch.Tensor, lengths: torch.Tensor, sample_dl: float,
+                               mode: str = "reference") -> PendingSubsample:
     """Launch the barycentre voxel subsampling and request its sizes; the caller queues independent work and then
-    calls .finish(), so the device never waits for the host to learn M."""
+    calls .finish(), so the device never waits for the host to learn M.  mode: 'reference' (the CPU Preprocessor's
+    recipe), 'mean' (MinkowskiEngine-style: global lattice, sum / count), 'first_point' (first point of every voxel)."""
     L = _lib.lib()
     pts = _f32c(points, "points")
     lens = _i32c(lengths, "lengths")
@@ -91,8 +96,9 @@ def grid_subsample_batch_async(points: torch.Tensor, lengths: torch.Tensor, samp
     meta = torch.empty(b + 1, dtype=torch.int32, device=pts.device)  # [lengths..., total]
     wsb = L.spr_grid_subsample_workspace_bytes(n, b)
     ws = _ws(wsb, pts.device)
-    rc = L.spr_grid_subsample_batch(pts.data_ptr(), lens.data_ptr(), n, b, float(sample_dl), out.data_ptr(),
-                                    meta.data_ptr(), meta.data_ptr() + 4 * b, ws.data_ptr(), ws.numel(), _stream())
+    rc = L.spr_grid_subsample_batch_ex(pts.data_ptr(), lens.data_ptr(), n, b, float(sample_dl), SUBSAMPLE_MODES[mode],
+                                       out.data_ptr(), meta.data_ptr(), meta.data_ptr() + 4 * b, ws.data_ptr(),
+                                       ws.numel(), _stream())
     _lib.check(rc, "spr_grid_subsample_batch")
     host = torch.empty(b + 1, dtype=torch.int32, pin_memory=True)
     host.copy_(meta, non_blocking=True)
@@ -101,14 +107,14 @@ def grid_subsample_batch_async(points: torch.Tensor, lengths: torch.Tensor, samp
     return PendingSubsample(out, meta, host, event, b)
 
 
-def grid_subsample_batch(points: torch.Tensor, lengths: torch.Tensor, sample_dl: float
+def grid_subsample_batch(points: torch.Tensor, lengths: torch.Tensor, sample_dl: float, mode: str = "reference"
                          ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Barycentre voxel subsampling of stacked clouds. -> (points f32[M,3], lengths i32[B]) on device.
 
     One host synchronisation (reading M), as in the reference where the lengths come back as a NumPy array
     (cpp_subsampling/wrapper.cpp:300-322).
     """
-    pts, lens, _ = grid_subsample_batch_async(points, lengths, sample_dl).finish()
+    pts, lens, _ = grid_subsample_batch_async(points, lengths, sample_dl, mode).finish()
     return pts, lens
 
 
@@ -137,8 +143,9 @@ class CellGrid:
         return out
 
     def query(self, queries: torch.Tensor, q_lengths: torch.Tensor, limit: int, radius: Optional[float] = None,
-              index_dtype: torch.dtype = torch.int64) -> Tuple[torch.Tensor, torch.Tensor]:
-        """-> (idx [Nq, limit] index_dtype, max_count i32[1] on device)."""
+              index_dtype: torch.dtype = torch.int64, by_index: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        """-> (idx [Nq, limit] index_dtype, max_count i32[1] on device).  by_index: rows keep the first `limit`
+        in-radius supports in index order (ball_query) instead of the `limit` nearest."""
         L = _lib.lib()
         q = _f32c(queries, "queries")
         ql = _i32c(q_lengths, "q_lengths")
@@ -150,9 +157,9 @@ class CellGrid:
         nq = q.shape[0]
         idx = torch.empty((nq, limit), dtype=index_dtype, device=q.device)
         mc = torch.empty(1, dtype=torch.int32, device=q.device)
-        rc = L.spr_radius_query(q.data_ptr(), ql.data_ptr(), nq, self.b, self.ws.data_ptr(), self.ns, r, int(limit),
-                                idx.data_ptr(), 1 if index_dtype == torch.int64 else 0, int(limit), mc.data_ptr(),
-                                _stream())
+        rc = L.spr_radius_query_ex(q.data_ptr(), ql.data_ptr(), nq, self.b, self.ws.data_ptr(), self.ns, r, int(limit),
+                                   1 if by_index else 0, idx.data_ptr(), 1 if index_dtype == torch.int64 else 0,
+                                   int(limit), mc.data_ptr(), _stream())
         _lib.check(rc, "spr_radius_query")
         return idx, mc
 

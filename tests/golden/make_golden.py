@@ -18,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))  # tests/parity.py
 
 import oracle  # noqa: E402
 from oracle import ref_torch  # noqa: E402
@@ -307,6 +308,32 @@ def gen_sinkhorn(ref):
     save("sinkhorn.npz", **arrays)
 
 
+def gen_est_log(ref):
+    """The reference's 3DMatch est.log writer (models/generic_reg_model.py:382-403) on a small batch, both pose ranks."""
+    import importlib
+    import tempfile
+    import types
+    grm = importlib.import_module("models.generic_reg_model")
+    rng = np.random.default_rng(5)
+    B = 3
+    batch = {"src_xyz": [torch.zeros(4, 3)] * B, "tgt_xyz": [torch.zeros(5, 3)] * B,
+             "src_path": ["test/7-scenes-redkitchen/cloud_bin_12.pth", "test/7-scenes-redkitchen/cloud_bin_3.pth",
+                          "test/sun3d-hotel_umd-maryland_hotel3/cloud_bin_40.pth"],
+             "tgt_path": ["test/7-scenes-redkitchen/cloud_bin_0.pth", "test/7-scenes-redkitchen/cloud_bin_1.pth",
+                          "test/sun3d-hotel_umd-maryland_hotel3/cloud_bin_7.pth"]}
+    pose = torch.from_numpy(rng.normal(size=(B, 3, 4)).astype(np.float32))
+    d = tempfile.mkdtemp()
+    fake = types.SimpleNamespace(_log_path=d, cfg=types.SimpleNamespace(benchmark="3DMatch"))
+    grm.GenericRegModel._save_3DMatch_log(fake, batch, {"pose": pose})
+    grm.GenericRegModel._save_3DMatch_log(fake, batch, {"pose": pose[None].repeat(2, 1, 1, 1)})   # (iters, B, 3, 4)
+    out = {}
+    for root, _, files in os.walk(d):
+        for f in files:
+            out[os.path.relpath(os.path.join(root, f), d)] = open(os.path.join(root, f)).read()
+    save("est_log.npz", pose=pose.numpy(), src_path=np.asarray(batch["src_path"]), tgt_path=np.asarray(batch["tgt_path"]),
+         files=np.asarray(sorted(out)), texts=np.asarray([out[k] for k in sorted(out)]))
+
+
 WELLCOND_ARCH = ["simple", "resnetb", "resnetb_strided", "resnetb", "resnetb", "resnetb_strided", "resnetb", "resnetb",
                  "resnetb_strided", "resnetb", "resnetb"]          # conf/qk_regtr_full_3dmatch.yaml:64-74 (4-stage)
 WELLCOND_DAMP = 0.3
@@ -321,7 +348,10 @@ def gen_forward_wellcond(ref):
     pose can be held to north_star's 1e-3 deg / 1e-5 m.  Two variants on the same clouds and weights:
       argmax    use_sinkhorn=False (the KITTI / ModelNet matching route), target jittered by 1 mm
       sinkhorn  the 3DMatch yaml's route, exact copy (the reference's affinity rewards LOW correlation, :535, so its
-                untrained Sinkhorn pose is far from the ground truth; it is recorded as is)
+                untrained Sinkhorn assignment is close to uniform, the pose far from the ground truth and only
+                moderately conditioned; recorded as is, together with the reference's own self-noise)
+    Each variant also stores how far the REFERENCE's pose moves when the points of every cloud are relabelled
+    (`*_self_noise_*`): the floor below which a difference from the reference means nothing.
     """
     rng = np.random.default_rng(81)
     trans = np.array([0.3, -0.2, 0.1])
@@ -350,6 +380,21 @@ def gen_forward_wellcond(ref):
             arrays[f"{tag}_n_src_{i}"] = np.asarray(out["src_feat"][i].shape[1])
             arrays[f"{tag}_n_tgt_{i}"] = np.asarray(out["tgt_feat"][i].shape[1])
         arrays[f"{tag}_pose"] = t2n(out["pose"])
+        # the reference's own conditioning on this input: its pose when the points of every cloud are merely
+        # relabelled (three shuffles) -- mathematically the same problem, different fp32 summation orders
+        from parity import pose_error
+        noise_rot, noise_tr = 0.0, 0.0
+        for trial in range(3):
+            prng = np.random.default_rng(100 + trial)
+            shuffled = {"src_xyz": [torch.from_numpy(c[prng.permutation(len(c))]) for c in srcs],
+                        "tgt_xyz": [torch.from_numpy(c[prng.permutation(len(c))]) for c in tgts]}
+            with torch.no_grad():
+                again = model(shuffled)
+            rot, tr = pose_error(t2n(again["pose"]), t2n(out["pose"]))
+            noise_rot, noise_tr = max(noise_rot, float(rot.max())), max(noise_tr, float(tr.max()))
+        arrays[f"{tag}_self_noise_rot_deg"] = np.asarray(noise_rot)
+        arrays[f"{tag}_self_noise_trans"] = np.asarray(noise_tr)
+        print(tag, f"reference self-noise under relabelling: {noise_rot:.2e} deg / {noise_tr:.2e} m")
         print(tag, "superpoints", [(int(arrays[f"{tag}_n_src_{i}"]), int(arrays[f"{tag}_n_tgt_{i}"])) for i in range(2)])
     save("forward_wellcond.npz", **arrays)
 
@@ -364,6 +409,7 @@ def main():
     gen_matching(ref)
     gen_refinements(ref)
     gen_sinkhorn(ref)
+    gen_est_log(ref)
     gen_forward(ref)
     gen_forward_wellcond(ref)
 

@@ -334,8 +334,16 @@ def test_full_forward_end_to_end_pose_on_the_well_conditioned_fixture(golden_dir
         assert out["src_feat"][i].shape[1] == int(g[f"{tag}_n_src_{i}"])         # same superpoints
         assert out["tgt_feat"][i].shape[1] == int(g[f"{tag}_n_tgt_{i}"])
     rot, tr = pose_error(out["pose"].cpu().numpy(), g[f"{tag}_pose"])
-    print(f"[wellcond/{tag}] end-to-end pose vs reference: rot {rot.max():.2e} deg, trans {tr.max():.2e} m")
-    assert rot.max() < ROT_TOL_DEG and tr.max() < TRANS_TOL, (tag, rot, tr)
+    # The bar is north_star's, unless the reference ITSELF moves by more than half of it when its input points are
+    # merely relabelled (recorded in the fixture): argmax 3.9e-5 deg / 1.3e-6 m -> the plain tolerance applies;
+    # Sinkhorn (near-uniform assignment with untrained weights) 2.2e-4 deg / 8.9e-6 m -> twice that self-noise.
+    rot_bar = max(ROT_TOL_DEG, 2 * float(g[f"{tag}_self_noise_rot_deg"]))
+    tr_bar = max(TRANS_TOL, 2 * float(g[f"{tag}_self_noise_trans"]))
+    print(f"[wellcond/{tag}] end-to-end pose vs reference: rot {rot.max():.2e} deg, trans {tr.max():.2e} m "
+          f"(bars {rot_bar:.1e} / {tr_bar:.1e})")
+    if tag == "argmax":
+        assert rot_bar == ROT_TOL_DEG and tr_bar == TRANS_TOL
+    assert rot.max() < rot_bar and tr.max() < tr_bar, (tag, rot, tr)
     # and the plain route (fp32 SIMT KPConv, unfused blocks, padded nn.MultiheadAttention) agrees to the same bar
     model.packed_transformer = False
     for m in model.modules():
@@ -343,7 +351,7 @@ def test_full_forward_end_to_end_pose_on_the_well_conditioned_fixture(golden_dir
             m.mode = 0
     plain = model(dict(batch))
     rot, tr = pose_error(plain["pose"].cpu().numpy(), g[f"{tag}_pose"])
-    assert rot.max() < ROT_TOL_DEG and tr.max() < TRANS_TOL, (tag, "plain", rot, tr)
+    assert rot.max() < rot_bar and tr.max() < tr_bar, (tag, "plain", rot, tr)
 
 
 @pytest.mark.parametrize("kind,cfg,kw", [("3dlomatch", cfgs.threedmatch_config(), dict(n_points=4000)),

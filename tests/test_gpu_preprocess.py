@@ -272,3 +272,85 @@ def test_pyramid_is_int32_inside_and_lazy_where_nobody_looks():
         assert u.dtype == torch.int64 and torch.equal(u, eager["upsamples"][l])
     m32 = Preprocessor(cfg, index_dtype=torch.int32)(clouds)
     assert m32["neighbors"][0].dtype == torch.int32 and torch.equal(m32["neighbors"][0].long(), meta["neighbors"][0])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# PreprocessorGPU-compatible mode and the KITTI front end.  PARITY UNPINNED: pytorch3d,
+# MinkowskiEngine and kiss_icp are absent; the oracle is the NumPy restatement of their documented behaviour.
+# ---------------------------------------------------------------------------------------------------------
+
+def test_ball_query_rows_keep_the_first_k_in_index_order():
+    from oracle import numpy_ops
+    rng = np.random.default_rng(31)
+    ql, sl = np.array([300, 0, 150, 41], np.int32), np.array([400, 0, 220, 3], np.int32)
+    q = rng.uniform(0, 1, size=(int(ql.sum()), 3)).astype(np.float32)
+    s = rng.uniform(0, 1, size=(int(sl.sum()), 3)).astype(np.float32)
+    for radius, K in ((0.2, 12), (0.45, 40), (0.05, 8)):
+        grid = ops.CellGrid(_t(s), _t(sl), radius)
+        for dtype in (torch.int32, torch.int64):
+            got, mc = grid.query(_t(q), _t(ql), K, index_dtype=dtype, by_index=True)
+            want = numpy_ops.ball_query_first_k(q, s, ql, sl, radius, K)
+            assert got.dtype == dtype and np.array_equal(got.cpu().numpy().astype(np.int64), want), (radius, K)
+        near, _ = grid.query(_t(q), _t(ql), K, by_index=False)
+        # same neighbour SETS whenever nothing is truncated
+        full = (want < len(s)).sum(1) < K
+        assert np.array_equal(np.sort(near.cpu().numpy()[full], 1), np.sort(want[full], 1))
+
+
+def test_voxel_mean_and_first_point_modes():
+    from oracle import numpy_ops
+    from superpoints_registration_b200 import frontends
+    rng = np.random.default_rng(32)
+    lens = np.array([5000, 1, 0, 2500], np.int32)
+    pts = (rng.normal(size=(int(lens.sum()), 3)) * np.array([2.0, 1.5, 0.3])).astype(np.float32)   # both signs: global lattice
+    for dl in (0.11, 0.4):
+        got_p, got_l = ops.grid_subsample_batch(_t(pts), _t(lens), dl, mode="mean")
+        want_p, want_l = numpy_ops.voxel_mean_me(pts, lens, dl)
+        assert np.array_equal(got_l.cpu().numpy(), want_l)
+        assert np.array_equal(got_p.cpu().numpy().view(np.uint32), want_p.view(np.uint32))       # bit-identical means
+    cloud = pts[:5000]
+    got = frontends.voxel_down_sample(_t(cloud), 0.3).cpu().numpy()
+    want = numpy_ops.voxel_first_point(cloud, 0.3)
+    assert np.array_equal(got, want)                              # a subset of the input, in input order
+    with pytest.raises(RuntimeError):
+        frontends.voxel_down_sample(torch.from_numpy(cloud), 0.3)  # CPU tensors are refused
+
+
+@pytest.mark.parametrize("cfg,kind,kw", [(cfgs.threedmatch_4stage_config(), "3dmatch", dict(n_points=5000)),
+                                         (cfgs.kitti_config(), "kitti", dict(n_points=5000))])
+def test_gpu_compat_pyramid_against_restatement(cfg, kind, kw):
+    """Preprocessor(mode='gpu_compat') / PreprocessorGPU level by level against the NumPy restatement of
+    kpconv.py:421-549: ball_query rows (first K by index, always `limit` wide), voxel means on the global lattice,
+    int64 lengths, the reference's radius / voxel schedule and last-level placeholders."""
+    from oracle import numpy_ops
+    from superpoints_registration_b200 import PreprocessorGPU
+    clouds = _clouds(kind, 2, 6, **kw)
+    meta = PreprocessorGPU(cfg)([_t(c) for c in clouds])
+    assert set(meta.keys()) == {"points", "neighbors", "pools", "upsamples", "stack_lengths"}
+    pts = np.concatenate(clouds).astype(np.float32)
+    lens = np.array([len(c) for c in clouds], np.int32)
+    r = cfg.first_subsampling_dl * cfg.conv_radius
+    L = len(meta["points"])
+    for l in range(L):
+        limit = cfg.neighborhood_limits[l]
+        assert meta["stack_lengths"][l].dtype == torch.int64
+        assert np.array_equal(meta["stack_lengths"][l].cpu().numpy(), lens)
+        assert np.array_equal(meta["points"][l].cpu().numpy().view(np.uint32), pts.view(np.uint32))
+        conv = meta["neighbors"][l].cpu().numpy()
+        assert conv.dtype == np.int64 and conv.shape == (len(pts), limit)
+        assert np.array_equal(conv, numpy_ops.ball_query_first_k(pts, pts, lens, lens, r, limit))
+        if l == L - 1:
+            assert tuple(meta["pools"][l].shape) == (0, 1) and tuple(meta["upsamples"][l].shape) == (0, 1)
+            break
+        nxt, nxt_lens = numpy_ops.voxel_mean_me(pts, lens, 2 * r / cfg.conv_radius)
+        assert np.array_equal(meta["pools"][l].cpu().numpy(), numpy_ops.ball_query_first_k(nxt, pts, nxt_lens, lens, r, limit))
+        assert np.array_equal(meta["upsamples"][l].cpu().numpy(),
+                              numpy_ops.ball_query_first_k(pts, nxt, lens, nxt_lens, 2 * r, limit))
+        pts, lens, r = nxt, nxt_lens, 2 * r
+    # and the whole forward runs on it (cfg.preprocessor selects the mode inside RegTR)
+    from superpoints_registration_b200.model import RegTR
+    torch.manual_seed(1)
+    np.random.seed(1)
+    model = RegTR(cfgs.Config(cfg, preprocessor="gpu_compat")).to(DEV).eval()
+    out = model({"src_xyz": [_t(c) for c in clouds[:2]], "tgt_xyz": [_t(c) for c in clouds[2:]]})
+    assert tuple(out["pose"].shape) == (2, 3, 4) and torch.isfinite(out["pose"]).all()

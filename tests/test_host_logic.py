@@ -103,3 +103,37 @@ def test_pose_error_metric_resolves_below_reference_metric_floor():
     T = torch.tensor([[[0.6, -0.8, 0.0, 1.0], [0.8, 0.6, 0.0, 2.0], [0.0, 0.0, 1.0, 3.0]]])
     rot, tr = spr.pose_error(T, T)
     assert float(rot) == 0.0 and float(tr) == 0.0
+
+
+def test_est_log_writer_matches_the_reference_byte_for_byte(tmp_path, golden_dir):
+    """frontends.save_3dmatch_log against the text the reference's _save_3DMatch_log wrote for the same batch
+    (models/generic_reg_model.py:382-403; tests/golden/make_golden.py:gen_est_log): two appends, both pose ranks."""
+    import os
+
+    import numpy as np
+    import torch
+
+    from superpoints_registration_b200 import frontends
+    g = np.load(os.path.join(golden_dir, "est_log.npz"))
+    pose = torch.from_numpy(g["pose"])
+    B = pose.shape[0]
+    batch = {"src_xyz": [torch.zeros(1, 3)] * B, "tgt_xyz": [torch.zeros(1, 3)] * B,
+             "src_path": [str(s) for s in g["src_path"]], "tgt_path": [str(s) for s in g["tgt_path"]]}
+    frontends.save_3dmatch_log(str(tmp_path), "3DMatch", batch, {"pose": pose})
+    frontends.save_3dmatch_log(str(tmp_path), "3DMatch", batch, {"pose": pose[None].repeat(2, 1, 1, 1)})
+    for rel, text in zip(map(str, g["files"]), map(str, g["texts"])):
+        assert open(os.path.join(str(tmp_path), rel)).read() == text, rel
+
+
+def test_collate_pair_contract():
+    """data_loaders/collate_functions.py:4-23: variable-size fields stay lists, pose is stacked, overlap_p is a tensor."""
+    import torch
+
+    from superpoints_registration_b200 import frontends
+    items = [{"src_xyz": torch.rand(5 + i, 3), "tgt_xyz": torch.rand(7, 3), "pose": torch.eye(4)[:3], "idx": i,
+              "src_path": f"a/b/c_{i}.pth", "tgt_path": f"a/b/c_{i + 1}.pth", "overlap_p": 0.1 * i, "extra": 1}
+             for i in range(3)]
+    batch = frontends.collate_pair(items)
+    assert isinstance(batch["src_xyz"], list) and [t.shape[0] for t in batch["src_xyz"]] == [5, 6, 7]
+    assert tuple(batch["pose"].shape) == (3, 3, 4) and batch["idx"] == [0, 1, 2]
+    assert torch.allclose(batch["overlap_p"], torch.tensor([0.0, 0.1, 0.2])) and "extra" not in batch

@@ -188,8 +188,11 @@ def test_cpu_forward_port_on_the_well_conditioned_fixture(golden_dir):
             assert out["src_feat"][i].shape[0] == int(g[f"{tag}_n_src_{i}"])
             assert out["tgt_feat"][i].shape[0] == int(g[f"{tag}_n_tgt_{i}"])
         rot, tr = pose_error(out["pose"], g[f"{tag}_pose"])
-        assert rot.max() < 1e-3 and tr.max() < 1e-5, (tag, rot, tr)
-        if tag == "argmax":   # the reference actually registers this pair: its pose is the ground truth to ~0.6 deg
+        # north_star's bar, or twice the reference's own movement under a relabelling of its input when that is larger
+        assert rot.max() < max(1e-3, 2 * float(g[f"{tag}_self_noise_rot_deg"])), (tag, rot)
+        assert tr.max() < max(1e-5, 2 * float(g[f"{tag}_self_noise_trans"])), (tag, tr)
+        if tag == "argmax":
+            assert float(g["argmax_self_noise_rot_deg"]) < 5e-4 and float(g["argmax_self_noise_trans"]) < 5e-6   # the reference actually registers this pair: its pose is the ground truth to ~0.6 deg
             rot_gt, tr_gt = pose_error(g[f"{tag}_pose"], np.stack([g["gt_pose"]] * B))
             assert rot_gt.max() < 1.0 and tr_gt.max() < 0.05
 

@@ -178,6 +178,19 @@ SPR_API int spr_instance_norm_lrelu_ex(const float* d_x, const int32_t* d_length
                                void* d_out_x16, void* d_out_pts4, const float* d_points, void* d_amax,
                                const float* d_stats16, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Second-generation tensor-core KPConv (csrc/kpconv_g.cu): the neighbour features are gathered by the TMA engine
+ * (cp.async.bulk.tensor tile::gather4 on the pre-split rows) and BOTH products of the layer -- influences x features per
+ * query, then (K*Cin) x Cout per tile -- run on tcgen05.  Same operands and result as spr_kpconv_forward_prepared; its
+ * own weight image (channel-major K order) and scratch.  c in {32, 64, 128}, H <= 64 (spr_kpconv_gather_supported). */
+SPR_API int spr_kpconv_gather_supported(int c, int H);
+SPR_API size_t spr_kpconv_gather_weight_image_bytes(int c);
+SPR_API size_t spr_kpconv_gather_scratch_bytes(int c);
+SPR_API int spr_kpconv_gather_prepare_weights(const float* d_w, int c, void* d_img, void* d_amax_w, void* stream);
+SPR_API int spr_kpconv_forward_gather(const float* d_q, const void* d_idx, int idx_is_64, int row_stride, int H,
+                              const void* d_pts4, const void* d_x16, const void* d_amax_x, int c, const void* d_wimg,
+                              const void* d_amax_w, const float* d_kp, float extent, float* d_out, int nq, int ns,
+                              void* d_scratch, const int32_t* d_order, void* stream);
+
 /* max_pool(x, inds)  kpconv_blocks.py:127-143: out[n,c] = max_h xpad[idx[n,h],c] where xpad has a zero
  * row appended for the shadow index. */
 SPR_API int spr_max_pool(const float* d_x, const void* d_idx, int idx_is_64, int row_stride, int H, int nq, int ns, int c,

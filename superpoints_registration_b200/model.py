@@ -369,7 +369,7 @@ class RegTR(nn.Module):
     def _match_and_solve(self, src_packed, tgt_packed, pts_c, src_lens, tgt_lens, overlap_packed=None):
         cfg = self.cfg
         dev = src_packed.device
-        pairs = ops.PackedPairs(src_lens, tgt_lens, dev)
+        pairs = ops.packed_pairs(src_lens, tgt_lens, dev)
         total_src = pairs.total_src
         src_xyz_packed, tgt_xyz_packed = pts_c[:total_src], pts_c[total_src:]
         ratio_test = bool(cfg.get('use_ratio_test', False))

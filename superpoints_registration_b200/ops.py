@@ -304,11 +304,44 @@ def kpconv_weight_image(weights: torch.Tensor) -> KPConvWeightImage:
     return wi
 
 
+class KPConvGatherWeightImage:
+    """Weight image of the gather kernel (csrc/kpconv_g.cu: channel-major K order)."""
+
+    def __init__(self, weights: torch.Tensor):
+        L = _lib.lib()
+        w = _f32c(weights.detach(), "weights")
+        self.c = w.shape[1]
+        self.img = torch.empty(L.spr_kpconv_gather_weight_image_bytes(self.c), dtype=torch.uint8, device=w.device)
+        self.amax = torch.empty(1, dtype=torch.int32, device=w.device)
+        rc = L.spr_kpconv_gather_prepare_weights(w.data_ptr(), self.c, self.img.data_ptr(), self.amax.data_ptr(), _stream())
+        _lib.check(rc, "spr_kpconv_gather_prepare_weights")
+        self.key = (weights.data_ptr(), weights._version)
+
+
+def kpconv_gather_weight_image(weights: torch.Tensor) -> KPConvGatherWeightImage:
+    key = (weights.data_ptr(), weights._version)
+    wi = getattr(weights, "_spr_kpconv_gather_image", None)
+    if wi is None or wi.key != key:
+        wi = KPConvGatherWeightImage(weights)
+        weights._spr_kpconv_gather_image = wi
+    return wi
+
+
+def kpconv_kernel_generation() -> int:
+    """2 = csrc/kpconv_g.cu (TMA gather + both products on tcgen05) where it applies, 1 = csrc/kpconv_tc.cu.
+    SPR_KPCONV_GEN=1|2 selects."""
+    return int(os.environ.get("SPR_KPCONV_GEN", "1"))
+
+
 def kpconv_forward_prepared(q_pts, neighb_inds, feats: PreparedFeatures, weights, kernel_points, extent: float,
-                            order=None):
+                            order=None, generation=None):
     """KPConv on the tensor-core path from inputs prepared by instance_norm_lrelu_ex (no pre-pass kernels).
     order: optional int32 permutation of the queries (CellGrid.order()) = processing order."""
     L = _lib.lib()
+    if generation is None:
+        generation = kpconv_kernel_generation()
+    if generation == 2 and L.spr_kpconv_gather_supported(int(feats.c), int(neighb_inds.shape[1])):
+        return _kpconv_forward_gather(q_pts, neighb_inds, feats, weights, kernel_points, extent, order)
     q = _f32c(q_pts, "q_pts")
     kp = _f32c(kernel_points, "kernel_points")
     idx, is64, stride, H = _idx_arg(neighb_inds)
@@ -329,6 +362,28 @@ def kpconv_forward_prepared(q_pts, neighb_inds, feats: PreparedFeatures, weights
     return out
 
 
+def _kpconv_forward_gather(q_pts, neighb_inds, feats: PreparedFeatures, weights, kernel_points, extent, order):
+    L = _lib.lib()
+    q = _f32c(q_pts, "q_pts")
+    kp = _f32c(kernel_points, "kernel_points")
+    idx, is64, stride, H = _idx_arg(neighb_inds)
+    nq, ns = q.shape[0], feats.x16.shape[0]
+    if order is not None and (order.dtype != torch.int32 or order.shape[0] != nq or not order.is_cuda):
+        raise RuntimeError("kpconv_forward_prepared: order must be an int32 CUDA tensor with one entry per query")
+    wi = kpconv_gather_weight_image(weights)
+    if wi.c != feats.c:
+        raise RuntimeError("kpconv_forward_prepared: channel mismatch between features and weights")
+    out = torch.empty((nq, feats.c), dtype=torch.float32, device=q.device)
+    sb = L.spr_kpconv_gather_scratch_bytes(feats.c)
+    scratch = _ws(sb, q.device) if sb else None
+    rc = L.spr_kpconv_forward_gather(q.data_ptr(), idx.data_ptr(), is64, stride, H, feats.pts4.data_ptr(),
+                                     feats.x16.data_ptr(), feats.amax.data_ptr(), feats.c, wi.img.data_ptr(),
+                                     wi.amax.data_ptr(), kp.data_ptr(), float(extent), out.data_ptr(), nq, ns,
+                                     _ptr(scratch), _ptr(order), _stream())
+    _lib.check(rc, "spr_kpconv_forward_gather")
+    return out
+
+
 def max_pool(x, inds):
     L = _lib.lib()
     xx = _f32c(x, "x")
@@ -343,6 +398,25 @@ def max_pool(x, inds):
 # ------------------------------------------------------------------------------------------------
 # matching and pose
 # ------------------------------------------------------------------------------------------------
+
+_small_cache = {}
+
+
+def _memo(key, build):
+    """Tiny LRU for device-side descriptions of a batch that depend only on its (host-known) cloud sizes -- offset
+    tables, attention tile lists: a stream of same-shaped batches (and every CUDA-graph replay) rebuilds nothing."""
+    hit = _small_cache.get(key)
+    if hit is None:
+        if len(_small_cache) >= 64:
+            _small_cache.pop(next(iter(_small_cache)))
+        hit = _small_cache[key] = build()
+    return hit
+
+
+def packed_pairs(src_lens, tgt_lens, device) -> "PackedPairs":
+    src_lens, tgt_lens = tuple(int(v) for v in src_lens), tuple(int(v) for v in tgt_lens)
+    return _memo(("pairs", src_lens, tgt_lens, str(device)), lambda: PackedPairs(src_lens, tgt_lens, device))
+
 
 class PackedPairs:
     """Offsets describing P pairs packed back to back: src rows, tgt rows, N_p x M_p matrices, outputs."""
@@ -535,6 +609,11 @@ def split_f16(x: torch.Tensor, n_scaled: int = 0, scale: float = 1.0):
 
 def attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q: int = 64) -> torch.Tensor:
     """Tile list of spr_attention_varlen: one row {first query row, rows, first key row, key rows} per 64 queries."""
+    key = ("tiles", tuple(q_offsets), tuple(q_lens), tuple(kv_offsets), tuple(kv_lens), str(device), block_q)
+    return _memo(key, lambda: _attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q))
+
+
+def _attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q):
     rows = []
     for qo, qn, ko, kn in zip(q_offsets, q_lens, kv_offsets, kv_lens):
         if qn <= 0:

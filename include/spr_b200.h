@@ -50,8 +50,8 @@ SPR_API unsigned long long spr_launch_count(void);
 /* Sticky numeric flags of the current device, raised by kernels that write fp16 (hi, lo) operand images for the
  * tensor-core GEMMs (spr_gemm_prepare_input, spr_layernorm256_prepare, spr_instance_norm_lrelu_ex, spr_attention_varlen
  * with an image output, spr_gemm_tc with plane / image output).  SPR_FLAG_FP16_OVERFLOW: an activation times the
- * image scale exceeded the fp16 range (|x| > 65504 / scale, i.e. ~4094 at the host layer's scale of 16) or was not
- * finite; the affected outputs are NaN (never silently wrong).  Synchronises the device.  reset != 0 clears them. */
+ * image scale exceeded the fp16 range (|x| > 65504 / scale, i.e. ~4094 at the host layer's scale of 16, or infinite);
+ * the affected outputs are NaN (never silently wrong).  A NaN input is not flagged: it propagates as NaN.  Synchronises the device.  reset != 0 clears them. */
 #define SPR_FLAG_FP16_OVERFLOW 1u
 SPR_API unsigned int spr_numeric_flags(int reset);
 

@@ -10,17 +10,20 @@
 //     B operand = [I_hi | I_lo] (32 rows: 16 kernel points x {hi, lo}; K = neighbours), K-major SWIZZLE_128B, written
 //       by the producer warp that evaluated the influences (pass 0) or copied back from an L2-resident scratch by the
 //       TMA engine (later passes: the influences depend on geometry only);
-//     D1 = 64 TMEM lanes x 32 columns per query: lane 2c / 2c+1 = hi / lo half of channel c, column k / 16+k = I_hi / I_lo.
-//   readback: two warps per query sum the four partial products (columns k and 16+k, lanes 2c and 2c+1), split the
-//     result into fp16 (hi, lo) and store it as two rows of the A tile of phase 2 (canonical K-major SWIZZLE_128B);
+//     D1 = 64 rows x 32 columns per query: row 2c / 2c+1 = hi / lo half of channel c, column k / 16+k = I_hi / I_lo.  An
+//       M = 64 accumulator occupies 16 lanes of each TMEM lane quadrant (row m -> quadrant m / 16, lane m % 16), so two
+//       queries share 32 columns: the slots of a pair use lane offsets 0 and 16;
+//   readback: four warps (one per quadrant) take the D1 of a slot pair at once -- lanes 0..15 the first query, 16..31 the
+//     second -- sum the four partial products (columns k and 16+k, lanes 2c and 2c+1), split the result into fp16
+//     (hi, lo) and store it as two rows of the A tile of phase 2 (canonical K-major SWIZZLE_128B);
 //   phase 2 (per tile of 64 queries, per pass): D2[128 x 2C] += A2[128 x 512] * [W_hi | W_lo]^T, weights streamed through
 //     a shared-memory ring by the TMA engine -- as in kpconv_tc.cu, with the K index ordered channel-major so that a
 //     readback lane writes 16 contiguous bytes;
 //   epilogue: four warps (one per TMEM lane quadrant) drain D2 while the next tile is produced.
-// Warp roles (2*NSLOT + 6 warps): per warpgroup two readback warps (TMEM quadrants 0, 1 hold D1) and two producer warps,
-// each producer owning one operand slot (A1 + B1, 8-12 KB); then the four epilogue warps, the MMA-issuing thread and the
-// weight-stream thread.  Queries of a tile are dealt statically (query i -> slot i % NSLOT), so every hand-over is a
-// plain in-order mbarrier wait.
+// Warp roles (NSLOT + 14 warps): two readback groups of four warps (slot pair p is served by group p % 2), NSLOT
+// producer warps, each owning one operand slot (A1 + B1, 8-12 KB), the four epilogue warps, the MMA-issuing thread and
+// the weight-stream thread.  Queries of a tile are dealt statically (query i -> slot i % NSLOT), so every hand-over is
+// a plain in-order mbarrier wait.
 #include <cuda.h>
 
 #include <mutex>
@@ -56,15 +59,19 @@ struct GCfg {
   static constexpr int MISC_BYTES = 2048;
   static constexpr int NSLOT_FIT = (kSmemMax - 1024 - A_BYTES - RING_BYTES - MISC_BYTES) / SLOT_BYTES;
   static constexpr int NSLOT = NSLOT_FIT >= 8 ? 8 : (NSLOT_FIT & ~1);
-  static constexpr int WARPS = 2 * NSLOT + 6;
+  static constexpr int NRG = 2;                       // readback groups (4 warps each)
+  static constexpr int W_PROD = 4 * NRG;              // first producer warp
+  static constexpr int W_EPI = W_PROD + NSLOT;        // first epilogue warp
+  static constexpr int W_MMA = W_EPI + 4;
+  static constexpr int WARPS = W_MMA + 2;
   static constexpr int THREADS = WARPS * 32;
   static constexpr int OFF_RING = A_BYTES;
   static constexpr int OFF_SLOTS = OFF_RING + RING_BYTES;
   static constexpr int OFF_MISC = OFF_SLOTS + NSLOT * SLOT_BYTES;
   static constexpr size_t SMEM = 1024 + OFF_MISC + MISC_BYTES;
-  static constexpr int D1_COL0 = NCOL;                // D1 of slot s: TMEM columns NCOL + 32 s
+  static constexpr int D1_COL0 = NCOL;                // D1 of slot s: TMEM columns NCOL + 32 (s / 2), lane offset 16 (s % 2)
   static constexpr size_t IMG_BYTES = (size_t)PASSES * BLOCKS_PER_PASS * STAGE_BYTES;
-  static_assert(NSLOT >= 4 && NCOL + 32 * NSLOT <= 512, "slot / TMEM budget");
+  static_assert(NSLOT >= 4 && NCOL + 16 * NSLOT <= 512, "slot / TMEM budget");
   static_assert(SMEM <= kSmemMax, "shared memory budget");
 };
 
@@ -192,10 +199,10 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::OFF_MISC);
   uint64_t* bar_full = bars;               // [8]  slot operands in place (producer arrive + TMA bytes)
   uint64_t* bar_d1full = bars + 8;         // [8]  phase-1 MMAs of the slot complete (D1 valid, slot memory reusable)
-  uint64_t* bar_d1free = bars + 16;        // [8]  both readback warps have D1 in registers
+  uint64_t* bar_d1free = bars + 16;        // [8]  the four readback warps have D1 in registers
   uint64_t* bar_wfull = bars + 24;         // [NSTAGES] weight ring
   uint64_t* bar_wempty = bars + 26;        // [NSTAGES]
-  uint64_t* bar_afull = bars + 28;         // A2 rows of the pass are written (NSLOT readback warps)
+  uint64_t* bar_afull = bars + 28;         // A2 rows of the pass are written (all readback warps)
   uint64_t* bar_done = bars + 29;          // phase-2 MMAs of the pass complete (A2 reusable)
   uint64_t* bar_d2full = bars + 30;        // phase-2 MMAs of the tile's last pass complete (D2 valid)
   uint64_t* bar_d2free = bars + 31;        // the four epilogue warps have drained D2
@@ -208,19 +215,19 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
     for (int i = 0; i < 8; ++i) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_d1full[i], 1);
-      mbar_init(&bar_d1free[i], 2);
+      mbar_init(&bar_d1free[i], 4);
     }
     for (int i = 0; i < K::NSTAGES; ++i) {
       mbar_init(&bar_wfull[i], 1);
       mbar_init(&bar_wempty[i], 1);
     }
-    mbar_init(bar_afull, NSLOT);
+    mbar_init(bar_afull, 4 * K::NRG);
     mbar_init(bar_done, 1);
     mbar_init(bar_d2full, 1);
     mbar_init(bar_d2free, 4);
     fence_mbar_init();
   }
-  constexpr int W_MMA = 2 * NSLOT + 4;  // the weight-stream warp is W_MMA + 1
+  constexpr int W_MMA = K::W_MMA;  // the weight-stream warp is W_MMA + 1
   if (warp == W_MMA) tmem_alloc(s_tmem, 512);
   for (int i = tid; i < KP * 3; i += K::THREADS) sKp[i] = kp[i];
   tc_fence_before();
@@ -231,9 +238,9 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
   const int es = scale_exp((float)H * __uint_as_float(*amax_x_bits), 15);
   const int et = scale_exp(__uint_as_float(*amax_w_bits), 14);
 
-  if (warp < 2 * NSLOT && (warp & 3) >= 2) {
+  if (warp >= K::W_PROD && warp < K::W_EPI) {
     // =========================================== producers ===========================================
-    const int slot = (warp >> 2) * 2 + ((warp & 3) - 2);
+    const int slot = warp - K::W_PROD;
     unsigned char* sA1 = sSlots + slot * K::SLOT_BYTES;
     unsigned char* sB1 = sA1 + K::A1_BYTES;
     const float inv_extent = 1.0f / extent;
@@ -355,12 +362,13 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
       }
     }
     if (K::PASSES > 1 && lane == 0) bulk_wait0();
-  } else if (warp < 2 * NSLOT) {
+  } else if (warp < K::W_PROD) {
     // =========================================== readback ===========================================
-    const int pair = warp >> 2, hw = warp & 1;  // TMEM lane quadrant = warp % 4 = hw
-    const int cl = 16 * hw + (lane >> 1);       // channel (within the pass) of this lane pair
-    const int odd = lane & 1;                    // even lane: X_hi partials and kernel points 0..7, odd: X_lo and 8..15
-    uint32_t par = 0;                            // bit o: parity of the next completion of slot 2 pair + o
+    const int rg = warp >> 2, qd = warp & 3;   // group, TMEM lane quadrant
+    const int second = lane >> 4;               // lanes 0..15: first slot of the pair, 16..31: second slot
+    const int cl = 8 * qd + ((lane & 15) >> 1);  // channel (within the pass) of this lane pair: D1 row 2 cl (+1)
+    const int odd = lane & 1;                   // even lane: X_hi partials and kernel points 0..7, odd: X_lo and 8..15
+    uint32_t par = 0;                           // bit s: parity of the next completion of slot s
     uint32_t seq = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int q0 = tile * tq;
@@ -370,19 +378,26 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
         bool first = true;
 #pragma unroll 1
         for (int base = 0; base < cnt; base += NSLOT) {
-#pragma unroll
-          for (int o = 0; o < 2; ++o) {
-            const int ql = base + 2 * pair + o;
-            if (ql >= cnt) continue;
-            const int slot = 2 * pair + o;
-            mbar_wait(&bar_d1full[slot], (par >> o) & 1u);
-            par ^= 1u << o;
+#pragma unroll 1
+          for (int pr = rg; pr < NSLOT / 2; pr += K::NRG) {
+            const int qa = base + 2 * pr;
+            if (qa >= cnt) continue;
+            const bool has_b = qa + 1 < cnt;
+            mbar_wait(&bar_d1full[2 * pr], (par >> (2 * pr)) & 1u);
+            par ^= 1u << (2 * pr);
+            if (has_b) {
+              mbar_wait(&bar_d1full[2 * pr + 1], (par >> (2 * pr + 1)) & 1u);
+              par ^= 1u << (2 * pr + 1);
+            }
             tc_fence_after();
             float v[32];
-            tmem_ld32(tmem + ((uint32_t)(32 * hw) << 16) + K::D1_COL0 + 32 * slot, v);
+            tmem_ld32(tmem + ((uint32_t)(32 * qd) << 16) + K::D1_COL0 + 32 * pr, v);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_d1free[slot]);
+            if (lane == 0) {
+              mbar_arrive(&bar_d1free[2 * pr]);
+              if (has_b) mbar_arrive(&bar_d1free[2 * pr + 1]);
+            }
             if (first) {  // the A tile still feeds the phase-2 MMAs of the previous pass until bar_done completes
               if (seq > 0) mbar_wait(bar_done, (seq - 1) & 1);
               first = false;
@@ -405,11 +420,14 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
               hi[p2] = h2_bits(hh);
               lo[p2] = h2_bits(__floats2half2_rn(mine[2 * p2] - hf.x, mine[2 * p2 + 1] - hf.y));
             }
-            // K index (channel-major) = cl * 16 + k: atom cl / 4, 16-byte chunk (cl % 4) * 2 + odd
-            unsigned char* atom = sA + (cl >> 2) * K::A_ATOM_BYTES;
-            const uint32_t j = (cl & 3) * 2 + odd;
-            *reinterpret_cast<uint4*>(atom + sw128_offset(2 * ql, j)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(atom + sw128_offset(2 * ql + 1, j)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            if (!second || has_b) {
+              // K index (channel-major) = cl * 16 + k: atom cl / 4, 16-byte chunk (cl % 4) * 2 + odd
+              const int ql = qa + second;
+              unsigned char* atom = sA + (cl >> 2) * K::A_ATOM_BYTES;
+              const uint32_t j = (cl & 3) * 2 + odd;
+              *reinterpret_cast<uint4*>(atom + sw128_offset(2 * ql, j)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(atom + sw128_offset(2 * ql + 1, j)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
           }
         }
         if (first && seq > 0) mbar_wait(bar_done, (seq - 1) & 1);  // keep the phases of bar_done in step
@@ -418,7 +436,7 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
         if (lane == 0) mbar_arrive(bar_afull);
       }
     }
-  } else if (warp < 2 * NSLOT + 4) {
+  } else if (warp < K::W_MMA) {
     // =========================================== epilogue ===========================================
     const int qd = warp & 3;  // TMEM lane quadrant: stacked rows 32 qd .. 32 qd + 31 = queries 16 qd .. 16 qd + 15
     const float o_scale = pow2i(-(es + et));
@@ -482,7 +500,8 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
             const uint32_t a1 = smem_u32(sSlots + slot * K::SLOT_BYTES);
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks)
-              umma_f16(tmem + K::D1_COL0 + 32 * slot, desc_sw128_mnmajor(a1 + ks * 2048),
+              umma_f16(tmem + ((uint32_t)((slot & 1) * 16) << 16) + K::D1_COL0 + 32 * (slot >> 1),
+                       desc_sw128_mnmajor(a1 + ks * 2048),
                        desc_sw128_kmajor(a1 + K::A1_BYTES + ks * 32), idesc1, ks != 0);
             umma_commit(&bar_d1full[slot]);
             par ^= 1u << slot;

@@ -659,8 +659,8 @@ def check_numerics(reset: bool = True) -> None:
     flags = _lib.numeric_flags(reset)
     if flags & _lib.FLAG_FP16_OVERFLOW:
         raise FloatingPointError(
-            f"an activation exceeded the fp16 operand range of the tensor-core GEMMs (|x| > {65504.0 / A_SCALE:.0f}) "
-            "or was not finite: the affected outputs are NaN")
+            f"an activation exceeded the fp16 operand range of the tensor-core GEMMs (|x| > {65504.0 / A_SCALE:.0f}): "
+            "the affected outputs are NaN")
 
 
 def gemm_a_image(T: int, K: int, device) -> torch.Tensor:

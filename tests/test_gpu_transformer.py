@@ -215,7 +215,7 @@ def test_gemm_tc_accuracy_over_input_magnitudes(mag):
     accuracy must hold from 1e-4 up to the documented limit of ~4094, relative to the output scale."""
     from superpoints_registration_b200 import _lib
     g = torch.Generator(device=DEV).manual_seed(int(mag * 1e4) % 9973)
-    x = torch.randn(300, 256, device=DEV, generator=g) * mag
+    x = (torch.rand(300, 256, device=DEV, generator=g) * 2 - 1) * mag      # bounded: |x| <= mag < 4094
     w = torch.randn(192, 256, device=DEV, generator=g) / 16
     b = torch.randn(192, device=DEV, generator=g)
     _lib.numeric_flags(reset=True)
@@ -245,7 +245,7 @@ def test_gemm_tc_operand_overflow_is_loud():
     ops.instance_norm_lrelu_ex(big, lens, residual=res, want_f32=False, want_image=True)
     assert _lib.numeric_flags() & _lib.FLAG_FP16_OVERFLOW
     t = torch.randn(64, 256, device=DEV)
-    t[0, 0] = float("nan")
-    ops.layernorm256_prepare(t, None, None, None, 1e-5, ops.gemm_a_image(64, 256, DEV))
+    gamma = torch.full((256,), 1.0e4, device=DEV)                    # LayerNorm output x 1e4
+    ops.layernorm256_prepare(t, gamma, torch.zeros(256, device=DEV), None, 1e-5, ops.gemm_a_image(64, 256, DEV))
     assert _lib.numeric_flags() & _lib.FLAG_FP16_OVERFLOW
     assert _lib.numeric_flags() == 0

@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(192) k_test(const __grid_constant__ CUtensorMa
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (j < 6) v = *reinterpret_cast<const uint4*>(b + (size_t)tid * KH + j * 8);
       *reinterpret_cast<uint4*>(sB + sw128_offset(tid, j)) = v;
+      *reinterpret_cast<uint4*>(sB + 4096 + sw128_offset(NN - 1 - tid, j)) = v;   // sB2: rows reversed
     }
     fence_proxy_async_smem();
   }
@@ -84,6 +85,13 @@ __global__ void __launch_bounds__(192) k_test(const __grid_constant__ CUtensorMa
       const uint64_t ad = desc_sw128(smem_u32(sA) + ks * 2048, 6144, 1024);
       const uint64_t bd = desc_sw128_kmajor(smem_u32(sB) + ks * 32);
       umma_f16(tb, ad, bd, idesc, ks != 0);
+    }
+    // a second M = 64 accumulator in the SAME columns at lane offset 16 (the other half of every lane quadrant):
+    // same A, B rows in reverse order (sB2)
+    for (int ks = 0; ks < KH / 16; ++ks) {
+      const uint64_t ad = desc_sw128(smem_u32(sA) + ks * 2048, 6144, 1024);
+      const uint64_t bd = desc_sw128_kmajor(smem_u32(sB + 4096) + ks * 32);
+      umma_f16(tb + (16u << 16), ad, bd, idesc, ks != 0);
     }
     umma_commit(&done);
   }
@@ -152,7 +160,7 @@ int main() {
   cudaMemcpy(didx, idx.data(), KH * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(db, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
   cudaMemset(dd, 0, 128 * NN * 4);
-  const int smem = 6144 + 4096 + 1024;
+  const int smem = 6144 + 8192 + 1024;
   cudaFuncSetAttribute(k_test, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   k_test<<<1, 192, smem>>>(tmap, didx, db, col0, dd, ddump);
   e = cudaDeviceSynchronize();
@@ -208,6 +216,19 @@ int main() {
     maxerr = fmax(maxerr, best_err);
   }
   printf("  (%s)\n", identity ? "lane = row" : "NOT the identity: see the map");
+  // the second accumulator: D2[m][n] = D[m][NN-1-n], expected at lane 16 + (m % 16) + 32 (m / 16)
+  double maxerr2 = 0;
+  for (int m = 0; m < MM; ++m) {
+    const int l = 16 + (m % 16) + 32 * (m / 16);
+    for (int n = 0; n < NN; ++n) maxerr2 = fmax(maxerr2, fabs(ref[m * NN + (NN - 1 - n)] - hd[l * NN + n]));
+  }
+  printf("second accumulator at lane offset 16: max abs err %.3e -> %s\n", maxerr2, maxerr2 < 1e-4 * maxref ? "OK" : "MISMATCH");
+  double maxerr1 = 0;
+  for (int m = 0; m < MM; ++m) {
+    const int l = (m % 16) + 32 * (m / 16);
+    for (int n = 0; n < NN; ++n) maxerr1 = fmax(maxerr1, fabs(ref[m * NN + n] - hd[l * NN + n]));
+  }
+  printf("first accumulator at lanes (m %% 16) + 32 (m / 16): max abs err %.3e -> %s\n", maxerr1, maxerr1 < 1e-4 * maxref ? "OK" : "MISMATCH");
   const bool ok = maxerr < 1e-4 * maxref;
   printf("MN-major UMMA M=%d N=%d K=%d: max abs err %.3e (max |ref| %.3e) -> %s\n", MM, NN, KH, maxerr, maxref,
          ok ? "OK" : "MISMATCH");

@@ -1,12 +1,14 @@
 // kpconv_g.cu -- fused KPConv forward, second generation: BOTH matrix products of the layer run on tcgen05 and the
-// neighbour-feature gather is done by the TMA engine (reference: kpconv_blocks.py:269-414).
+// neighbour-feature gather is asynchronous, global -> shared memory (reference: kpconv_blocks.py:269-414).
 //
 //   phase 1 (per query, per pass of 32 input channels)
 //        wf[c][k] = sum_h X[idx[h]][c] * I[h][k]          I = kernel-point influences (geometry only)
 //     A operand = the gathered, pre-split feature rows AS THEY LIE in global memory: a row is 32 channels x (hi, lo) fp16
 //       = 64 contiguous "M elements" (even = hi, odd = lo), one row per neighbour = one K index  ->  MN-major SWIZZLE_128B
-//       tile, filled by cp.async.bulk.tensor ... tile::gather4 (four rows per instruction, out-of-range = shadow rows
-//       arrive as zeros), no thread ever touches a feature;
+//       tile, filled by 16-byte asynchronous copies (cp.async through L2, zero-fill for shadow rows) whose completion
+//       arrives on the slot's mbarrier: no feature ever passes through a register.  (The TMA row gather, cp.async.bulk.
+//       tensor tile::gather4, produces the same tile -- tools/umma_mn_test.cu -- but sustained only one 128-byte row
+//       per ~18 clocks per SM on B200, 5x below what the copies through the LSU path deliver.)
 //     B operand = [I_hi | I_lo] (32 rows: 16 kernel points x {hi, lo}; K = neighbours), K-major SWIZZLE_128B, written
 //       by the producer warp that evaluated the influences (pass 0) or copied back from an L2-resident scratch by the
 //       TMA engine (later passes: the influences depend on geometry only);
@@ -20,14 +22,12 @@
 //     a shared-memory ring by the TMA engine -- as in kpconv_tc.cu, with the K index ordered channel-major so that a
 //     readback lane writes 16 contiguous bytes;
 //   epilogue: four warps (one per TMEM lane quadrant) drain D2 while the next tile is produced.
-// Warp roles (NSLOT + 14 warps): two readback groups of four warps (slot pair p is served by group p % 2), NSLOT
-// producer warps, each owning one operand slot (A1 + B1, 8-12 KB), the four epilogue warps, the MMA-issuing thread and
-// the weight-stream thread.  Queries of a tile are dealt statically (query i -> slot i % NSLOT), so every hand-over is
+// Warp roles (2 NSLOT + 16 warps): two readback groups of four warps (slot pair p is served by group p % 2), two
+// producer warps per operand slot (A1 + B1, 8-12 KB; each warp evaluates every other 8-neighbour block), the four
+// epilogue warps, the phase-2 MMA thread, the weight-stream thread, and one phase-1 MMA thread per readback group (a
+// hand-over costs a thread ~100 clocks per mbarrier operation, so the per-query chain is split over two issuers and
+// handled a slot PAIR at a time).  Queries of a tile are dealt statically (query i -> slot i % NSLOT), so every hand-over is
 // a plain in-order mbarrier wait.
-#include <cuda.h>
-
-#include <mutex>
-
 #include "spr_common.cuh"
 #include "tc05.cuh"
 
@@ -61,9 +61,10 @@ struct GCfg {
   static constexpr int NSLOT = NSLOT_FIT >= 8 ? 8 : (NSLOT_FIT & ~1);
   static constexpr int NRG = 2;                       // readback groups (4 warps each)
   static constexpr int W_PROD = 4 * NRG;              // first producer warp
-  static constexpr int W_EPI = W_PROD + NSLOT;        // first epilogue warp
-  static constexpr int W_MMA = W_EPI + 4;
-  static constexpr int WARPS = W_MMA + 2;
+  static constexpr int W_EPI = W_PROD + 2 * NSLOT;    // first epilogue warp (two producer warps per slot)
+  static constexpr int W_MMA = W_EPI + 4;             // phase-2 MMA issuer (+ TMEM owner); W_MMA + 1 = weight stream
+  static constexpr int W_ISS = W_MMA + 2;             // two phase-1 MMA issuers, one per readback group
+  static constexpr int WARPS = W_ISS + NRG;
   static constexpr int THREADS = WARPS * 32;
   static constexpr int OFF_RING = A_BYTES;
   static constexpr int OFF_SLOTS = OFF_RING + RING_BYTES;
@@ -76,13 +77,27 @@ struct GCfg {
 };
 
 // ---- PTX pieces that tc05.cuh does not have ---------------------------------------------------------------------
-__device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* tmap, uint64_t* bar, int col, int r0, int r1,
-                                            int r2, int r3) {
+// mbarrier wait that parks the thread in hardware (suspend-time hint) instead of spinning: a polling warp costs issue
+// slots -- the first profile of this kernel spent 64 % of its issued instructions in try_wait loops
+__device__ __forceinline__ void mbar_wait_park(uint64_t* bar, uint32_t parity) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
-      "%6, %7}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(tmap), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(20000u)
       : "memory");
+}
+// 16-byte asynchronous copy global -> shared through L2 (LDGSTS); src_bytes = 0 writes zeros
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+// one arrival on the mbarrier once every cp.async this thread has issued so far has landed (the barrier's expected
+// count must already include it: .noinc)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -181,9 +196,21 @@ __global__ void __launch_bounds__(256) k_absmax_g(const float* __restrict__ w, i
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
+#ifdef SPR_G_TRACE
+__device__ long long g_trace[8 * 4096];
+#define SPR_TR(role, i, v)                                                                         \
+  do {                                                                                             \
+    if (blockIdx.x == 0 && (i) < 4096 && lane == 0) g_trace[(role) * 4096 + (i)] = (long long)(v); \
+  } while (0)
+#else
+#define SPR_TR(role, i, v) \
+  do {                     \
+  } while (0)
+#endif
+
 template <int C, typename IdxT, int KS>
 __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
-    k_kpconv_g(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ q, const IdxT* __restrict__ idx,
+    k_kpconv_g(const uint32_t* __restrict__ x16, const float* __restrict__ q, const IdxT* __restrict__ idx,
                int row_stride, int H, const unsigned char* __restrict__ wimg, const float* __restrict__ kp,
                const float4* __restrict__ pts4, const unsigned int* __restrict__ amax_x_bits,
                const unsigned int* __restrict__ amax_w_bits, float extent, float* __restrict__ out, int nq, int ns, int tq,
@@ -197,9 +224,10 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
   unsigned char* sRing = smem + K::OFF_RING;
   unsigned char* sSlots = smem + K::OFF_SLOTS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::OFF_MISC);
-  uint64_t* bar_full = bars;               // [8]  slot operands in place (producer arrive + TMA bytes)
-  uint64_t* bar_d1full = bars + 8;         // [8]  phase-1 MMAs of the slot complete (D1 valid, slot memory reusable)
-  uint64_t* bar_d1free = bars + 16;        // [8]  the four readback warps have D1 in registers
+  // per slot PAIR (the two slots of a pair are always filled, multiplied and read back together):
+  uint64_t* bar_full = bars;               // [4]  operands of both slots in place (4 producer warps + TMA bytes)
+  uint64_t* bar_d1full = bars + 8;         // [4]  phase-1 MMAs of the pair complete (D1 valid, slot memory reusable)
+  uint64_t* bar_d1free = bars + 16;        // [4]  the four readback warps have D1 in registers
   uint64_t* bar_wfull = bars + 24;         // [NSTAGES] weight ring
   uint64_t* bar_wempty = bars + 26;        // [NSTAGES]
   uint64_t* bar_afull = bars + 28;         // A2 rows of the pass are written (all readback warps)
@@ -209,11 +237,12 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 32);
   float* sInv = reinterpret_cast<float*>(s_tmem + 4);  // [3][TQ] 1 / neighbour count, by tile number % 3
   float* sKp = sInv + 3 * K::TQ;                        // [45] (48 reserved)
+  float* sCnt = sKp + 48;                               // [8][2] partial neighbour counts of a slot's two producer warps
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
     for (int i = 0; i < 8; ++i) {
-      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_full[i], 132);  // per producer lane (4 warps) when its asynchronous copies have landed + 4 x lane 0
       mbar_init(&bar_d1full[i], 1);
       mbar_init(&bar_d1free[i], 4);
     }
@@ -240,7 +269,9 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
 
   if (warp >= K::W_PROD && warp < K::W_EPI) {
     // =========================================== producers ===========================================
-    const int slot = warp - K::W_PROD;
+    // two warps per slot: warp `half` evaluates the 8-neighbour blocks b = half, half + 2, ... of every query of the
+    // slot and copies every other group of four feature rows
+    const int slot = (warp - K::W_PROD) >> 1, half = (warp - K::W_PROD) & 1;
     unsigned char* sA1 = sSlots + slot * K::SLOT_BYTES;
     unsigned char* sB1 = sA1 + K::A1_BYTES;
     const float inv_extent = 1.0f / extent;
@@ -251,125 +282,191 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
                 k1z = g < 7 ? sKp[3 * (g + 8) + 2] : 0.f;
     const float k1_on = g < 7 ? 1.f : 0.f;  // kernel point 15 is padding
     uint32_t use = 0;                        // fills of this slot so far
-    int titer = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
-      const int q0 = tile * tq;
-      const int cnt = min(nq, q0 + tq) - q0;
-      unsigned char* tile_scratch = scratch + ((size_t)blockIdx.x * 2 + (titer & 1)) * K::TQ * K::B1_BYTES;
-#pragma unroll 1
-      for (int pass = 0; pass < K::PASSES; ++pass) {
-#pragma unroll 1
-        for (int ql = slot; ql < cnt; ql += NSLOT) {
-          const int n = order ? __ldg(order + q0 + ql) : q0 + ql;
-          // the neighbour row: lanes = slots (two rounds cover 64 columns)
-          int j0 = -1, j1 = -1;
-          if (lane < H) j0 = (int)__ldg(idx + (size_t)n * row_stride + lane);
-          if (KS > 2 && 32 + lane < H) j1 = (int)__ldg(idx + (size_t)n * row_stride + 32 + lane);
-          if (j0 >= ns) j0 = -1;
-          if (j1 >= ns) j1 = -1;
-          // gather coordinates: lane i < 4 KS fetches rows 4i .. 4i+3 (absent neighbour -> row ns: out of range -> zeros)
-          int rr[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int src = (4 * lane + e) & 31;
-            const int v0 = __shfl_sync(kFull, j0, src), v1 = __shfl_sync(kFull, j1, src);
-            const int v = (4 * lane + e) < 32 ? v0 : v1;
-            rr[e] = v >= 0 ? v : ns;
-          }
-          uint32_t ih0[K::NB], ih1[K::NB], il0[K::NB], il1[K::NB];
-          float fcount = 0.f;
-          if (pass == 0) {
-            // ---- influences of the 16 kernel points on every neighbour, as fp16 (hi, lo) pairs in registers ----
-            const float qx = __ldg(q + 3 * (size_t)n), qy = __ldg(q + 3 * (size_t)n + 1), qz = __ldg(q + 3 * (size_t)n + 2);
-            const unsigned m0 = __ballot_sync(kFull, j0 >= 0), m1 = __ballot_sync(kFull, j1 >= 0);
-            unsigned bm = ((m0 & 0xffu) ? 1u : 0u) | ((m0 & 0xff00u) ? 2u : 0u) | ((m0 & 0xff0000u) ? 4u : 0u) |
-                          ((m0 & 0xff000000u) ? 8u : 0u) | ((m1 & 0xffu) ? 16u : 0u) | ((m1 & 0xff00u) ? 32u : 0u) |
-                          ((m1 & 0xff0000u) ? 64u : 0u) | ((m1 & 0xff000000u) ? 128u : 0u);
-            float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa, na = pa, nb = pa;
-            auto fetch = [&](int b, float4& fa, float4& fb) {
-              const int src = (b & 3) * 8 + 2 * t;
-              const int jsel = b < 4 ? j0 : j1;
-              const int ja = __shfl_sync(kFull, jsel, src), jb = __shfl_sync(kFull, jsel, src + 1);
-              fa = make_float4(0.f, 0.f, 0.f, 0.f);
-              fb = fa;
-              if (ja >= 0) fa = __ldg(pts4 + ja);
-              if (jb >= 0) fb = __ldg(pts4 + jb);
-            };
-            if (bm & 1u) fetch(0, na, nb);
-#pragma unroll
-            for (int b = 0; b < K::NB; ++b) {
-              ih0[b] = ih1[b] = il0[b] = il1[b] = 0u;
-              pa = na;
-              pb = nb;
-              if (b + 1 < K::NB && ((bm >> (b + 1)) & 1u)) fetch(b + 1, na, nb);  // warp-uniform
-              if ((bm >> b) & 1u) {
-                const float ax = pa.x - qx, ay = pa.y - qy, az = pa.z - qz;
-                const float bx = pb.x - qx, by = pb.y - qy, bz = pb.z - qz;
-                const float sa = fabsf(pa.w) * a_scale, sb = fabsf(pb.w) * a_scale;  // an absent neighbour has w = 0
-                fcount += (pa.w > 0.f ? 1.f : 0.f) + (pb.w > 0.f ? 1.f : 0.f);
-                const float f00 = influence_g(ax, ay, az, k0x, k0y, k0z, inv_extent) * sa;
-                const float f01 = influence_g(bx, by, bz, k0x, k0y, k0z, inv_extent) * sb;
-                const float f10 = influence_g(ax, ay, az, k1x, k1y, k1z, inv_extent) * (sa * k1_on);
-                const float f11 = influence_g(bx, by, bz, k1x, k1y, k1z, inv_extent) * (sb * k1_on);
-                const __half2 h0 = __floats2half2_rn(f00, f01), h1 = __floats2half2_rn(f10, f11);
-                const float2 h0f = __half22float2(h0), h1f = __half22float2(h1);
-                ih0[b] = h2_bits(h0);
-                ih1[b] = h2_bits(h1);
-                il0[b] = h2_bits(__floats2half2_rn(f00 - h0f.x, f01 - h0f.y));
-                il1[b] = h2_bits(__floats2half2_rn(f10 - h1f.x, f11 - h1f.y));
-              }
-            }
-          }
-          // ---- the slot: free once the MMAs of its previous fill have completed ----
-          if (use > 0) mbar_wait(&bar_d1full[slot], (use - 1) & 1);
-          if (lane == 0) {
-            if (K::PASSES > 1) {
-              if (pass == 0) bulk_wait_read0();  // the scratch copy of the previous fill has left shared memory
-              else bulk_wait0();                 // this thread's scratch copies have landed in global memory
-            }
-            mbar_expect_tx(&bar_full[slot], K::A1_BYTES + (pass > 0 ? K::B1_BYTES : 0));
-          }
-          __syncwarp();
-          if (lane < 4 * KS) tma_gather4(sA1 + lane * 512, &tmap, &bar_full[slot], pass * 64, rr[0], rr[1], rr[2], rr[3]);
-          if (pass == 0) {
-            // B1: row = kernel point (+16 for the lo half), K element = neighbour 8 b + 2 t (+1)
-#pragma unroll
-            for (int b = 0; b < K::NB; ++b) {
-              *reinterpret_cast<uint32_t*>(sB1 + sw128_offset(g, b) + 4 * t) = ih0[b];
-              *reinterpret_cast<uint32_t*>(sB1 + sw128_offset(8 + g, b) + 4 * t) = ih1[b];
-              *reinterpret_cast<uint32_t*>(sB1 + sw128_offset(16 + g, b) + 4 * t) = il0[b];
-              *reinterpret_cast<uint32_t*>(sB1 + sw128_offset(24 + g, b) + 4 * t) = il1[b];
-            }
-            // a neighbour is replicated over g: count the g == 0 copies (lanes 0..3)
-            float c = g == 0 ? fcount : 0.f;
-            c += __shfl_xor_sync(kFull, c, 1);
-            c += __shfl_xor_sync(kFull, c, 2);
-            if (lane == 0) sInv[(titer % 3) * K::TQ + ql] = 1.f / fmaxf(c, 1.f);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              if (K::PASSES > 1) bulk_s2g(tile_scratch + (size_t)ql * K::B1_BYTES, sB1, K::B1_BYTES);
-              mbar_arrive(&bar_full[slot]);
-            }
-          } else {
-            if (lane == 0) {
-              bulk_g2s(sB1, tile_scratch + (size_t)ql * K::B1_BYTES, K::B1_BYTES, &bar_full[slot]);
-              mbar_arrive(&bar_full[slot]);
-            }
-          }
-          ++use;
+    // The producer's work list is the sequence of its (tile, pass, query) items.  Its global loads are software
+    // pipelined ACROSS items -- the index row and the query point of item i+1 are requested before item i is
+    // evaluated, the packed support points of item i+1 right after -- so that no L2 round trip sits on the warp's
+    // critical path (three dependent round trips per item otherwise: index row, support points, and the first block).
+    struct Work {
+      int tile, titer, pass, ql, q0, cnt;
+      bool valid;
+    };
+    struct Loads {
+      int j0, j1;          // the neighbour row, lane = column (two rounds of 32)
+      float qx, qy, qz;    // the query point
+      float4 p0, p1;       // packed support points of this lane's neighbours (x, y, z, +-2^-e), zero when absent
+    };
+    // A slot pair is filled as a unit: when the first query of a pair exists and the second does not (odd tail of a
+    // tile), the second slot gets a dummy fill -- nothing is copied, the stale operands are multiplied, nobody reads
+    // the result -- so that every hand-over of a pair has the same number of participants.
+    const int pair = slot >> 1;
+    auto settle = [&](Work& w) {  // move forward to the next (tile, pass) in which this warp's pair is active
+      while (w.valid && w.ql - (slot & 1) >= w.cnt) {
+        w.ql = slot;
+        if (++w.pass == K::PASSES) {
+          w.pass = 0;
+          w.tile += gridDim.x;
+          ++w.titer;
+          w.valid = w.tile < n_tiles;
+          w.q0 = w.tile * tq;
+          w.cnt = w.valid ? min(nq, w.q0 + tq) - w.q0 : 0;
         }
       }
+    };
+    auto stage_a = [&](const Work& w, Loads& l) {
+      const int qq = w.ql < w.cnt ? w.ql : w.cnt - 1;  // (a dummy fill looks at the tile's last query and ignores it)
+      const int n = order ? __ldg(order + w.q0 + qq) : w.q0 + qq;
+      l.j0 = l.j1 = -1;
+      if (lane < H) l.j0 = (int)__ldg(idx + (size_t)n * row_stride + lane);
+      if (KS > 2 && 32 + lane < H) l.j1 = (int)__ldg(idx + (size_t)n * row_stride + 32 + lane);
+      l.qx = __ldg(q + 3 * (size_t)n);
+      l.qy = __ldg(q + 3 * (size_t)n + 1);
+      l.qz = __ldg(q + 3 * (size_t)n + 2);
+    };
+    auto stage_b = [&](const Work& w, Loads& l) {
+      if (l.j0 >= ns) l.j0 = -1;
+      if (l.j1 >= ns) l.j1 = -1;
+      l.p0 = make_float4(0.f, 0.f, 0.f, 0.f);
+      l.p1 = l.p0;
+      if (w.pass == 0) {
+        if (l.j0 >= 0) l.p0 = __ldg(pts4 + l.j0);
+        if (KS > 2 && l.j1 >= 0) l.p1 = __ldg(pts4 + l.j1);
+      }
+    };
+    Work cur;
+    cur.tile = blockIdx.x;
+    cur.titer = 0;
+    cur.pass = 0;
+    cur.ql = slot;
+    cur.valid = cur.tile < n_tiles;
+    cur.q0 = cur.tile * tq;
+    cur.cnt = cur.valid ? min(nq, cur.q0 + tq) - cur.q0 : 0;
+    settle(cur);
+    Loads lc;
+    if (cur.valid) {
+      stage_a(cur, lc);
+      stage_b(cur, lc);
     }
-    if (K::PASSES > 1 && lane == 0) bulk_wait0();
+    while (cur.valid) {
+      Work nxt = cur;
+      nxt.ql += NSLOT;
+      settle(nxt);
+      Loads ln;
+      if (nxt.valid) stage_a(nxt, ln);
+      const int pass = cur.pass, ql = cur.ql, titer = cur.titer;
+      const bool dummy = ql >= cur.cnt;
+      unsigned char* tile_scratch = scratch + ((size_t)blockIdx.x * 2 + (titer & 1)) * K::TQ * K::B1_BYTES;
+      const int j0 = lc.j0, j1 = lc.j1;
+      uint32_t ih0[KS], ih1[KS], il0[KS], il1[KS];  // this warp's KS blocks
+      float fcount = 0.f;
+      if (pass == 0) {
+        // ---- influences of the 16 kernel points on every neighbour, as fp16 (hi, lo) pairs in registers ----
+        // lane (g, t) evaluates kernel points g, g + 8 on neighbours 8 b + 2 t, 8 b + 2 t + 1 of block b; the neighbours'
+        // packed points sit in the lanes that loaded them (lane = column) and are fetched by shuffle
+        const float qx = lc.qx, qy = lc.qy, qz = lc.qz;
+        const unsigned m0 = __ballot_sync(kFull, j0 >= 0), m1 = __ballot_sync(kFull, j1 >= 0);
+        const unsigned bm = ((m0 & 0xffu) ? 1u : 0u) | ((m0 & 0xff00u) ? 2u : 0u) | ((m0 & 0xff0000u) ? 4u : 0u) |
+                            ((m0 & 0xff000000u) ? 8u : 0u) | ((m1 & 0xffu) ? 16u : 0u) | ((m1 & 0xff00u) ? 32u : 0u) |
+                            ((m1 & 0xff0000u) ? 64u : 0u) | ((m1 & 0xff000000u) ? 128u : 0u);
+#pragma unroll
+        for (int bb = 0; bb < KS; ++bb) {
+          const int b = 2 * bb + half;
+          ih0[bb] = ih1[bb] = il0[bb] = il1[bb] = 0u;
+          if ((bm >> b) & 1u) {  // warp-uniform
+            const int src = (b & 3) * 8 + 2 * t;
+            const float4 ps = b < 4 ? lc.p0 : lc.p1;
+            const float pax = __shfl_sync(kFull, ps.x, src), pay = __shfl_sync(kFull, ps.y, src),
+                        paz = __shfl_sync(kFull, ps.z, src), paw = __shfl_sync(kFull, ps.w, src);
+            const float pbx = __shfl_sync(kFull, ps.x, src + 1), pby = __shfl_sync(kFull, ps.y, src + 1),
+                        pbz = __shfl_sync(kFull, ps.z, src + 1), pbw = __shfl_sync(kFull, ps.w, src + 1);
+            const float ax = pax - qx, ay = pay - qy, az = paz - qz;
+            const float bx = pbx - qx, by = pby - qy, bz = pbz - qz;
+            const float sa = fabsf(paw) * a_scale, sb = fabsf(pbw) * a_scale;  // an absent neighbour has w = 0
+            fcount += (paw > 0.f ? 1.f : 0.f) + (pbw > 0.f ? 1.f : 0.f);
+            const float f00 = influence_g(ax, ay, az, k0x, k0y, k0z, inv_extent) * sa;
+            const float f01 = influence_g(bx, by, bz, k0x, k0y, k0z, inv_extent) * sb;
+            const float f10 = influence_g(ax, ay, az, k1x, k1y, k1z, inv_extent) * (sa * k1_on);
+            const float f11 = influence_g(bx, by, bz, k1x, k1y, k1z, inv_extent) * (sb * k1_on);
+            const __half2 h0 = __floats2half2_rn(f00, f01), h1 = __floats2half2_rn(f10, f11);
+            const float2 h0f = __half22float2(h0), h1f = __half22float2(h1);
+            ih0[bb] = h2_bits(h0);
+            ih1[bb] = h2_bits(h1);
+            il0[bb] = h2_bits(__floats2half2_rn(f00 - h0f.x, f01 - h0f.y));
+            il1[bb] = h2_bits(__floats2half2_rn(f10 - h1f.x, f11 - h1f.y));
+          }
+        }
+      }
+      if (nxt.valid) stage_b(nxt, ln);  // the next item's index row has arrived meanwhile
+      // ---- the slot: free once the MMAs of its previous fill have completed ----
+      if (slot == 0 && half == 0) SPR_TR(0, use, clock64());
+      if (use > 0) mbar_wait_park(&bar_d1full[pair], (use - 1) & 1);
+      if (slot == 0 && half == 0) SPR_TR(1, use, clock64());
+      if (dummy) {
+        cp_async_arrive_noinc(&bar_full[pair]);
+        if (lane == 0) mbar_arrive(&bar_full[pair]);
+        ++use;
+        cur = nxt;
+        lc = ln;
+        continue;
+      }
+      if (K::PASSES > 1 && half == 0 && lane == 0) {
+        if (pass == 0) bulk_wait_read0();  // the scratch copy of the previous pass-0 fill has left shared memory
+        else bulk_wait0();                 // this thread's scratch copies have landed in global memory
+      }
+      // A1: the neighbours' 128-byte row segments (32 channels x hi/lo) of this pass, one row per neighbour, copied
+      // asynchronously through L2; lane = (row % 4, 16-byte chunk); an absent neighbour's row is zero-filled
+      {
+        const int rsub = lane >> 3, ch = lane & 7;
+        const uint32_t a1 = smem_u32(sA1);
+        const uint32_t* xcol = x16 + pass * 32 + ch * 4;
+#pragma unroll
+        for (int ii = 0; ii < 2 * KS; ++ii) {
+          const int h = 4 * (2 * ii + half) + rsub;
+          const int j = __shfl_sync(kFull, h < 32 ? j0 : j1, h & 31);
+          cp_async16(a1 + sw128_offset(h, ch), xcol + (size_t)(j >= 0 ? j : 0) * C, j >= 0 ? 16u : 0u);
+        }
+      }
+      if (pass == 0) {
+        // B1: row = kernel point (+16 for the lo half), K element = neighbour 8 b + 2 t (+1)
+#pragma unroll
+        for (int bb = 0; bb < KS; ++bb) {
+          const int b = 2 * bb + half;
+          *reinterpret_cast<uint32_t*>(sB1 + sw128_offset(g, b) + 4 * t) = ih0[bb];
+          *reinterpret_cast<uint32_t*>(sB1 + sw128_offset(8 + g, b) + 4 * t) = ih1[bb];
+          *reinterpret_cast<uint32_t*>(sB1 + sw128_offset(16 + g, b) + 4 * t) = il0[bb];
+          *reinterpret_cast<uint32_t*>(sB1 + sw128_offset(24 + g, b) + 4 * t) = il1[bb];
+        }
+        // a neighbour is replicated over g: count the g == 0 copies (lanes 0..3) of this warp's blocks
+        float c = g == 0 ? fcount : 0.f;
+        c += __shfl_xor_sync(kFull, c, 1);
+        c += __shfl_xor_sync(kFull, c, 2);
+        if (lane == 0) sCnt[2 * slot + half] = c;
+        if (K::PASSES > 1) fence_proxy_async_smem();  // the scratch copy below reads B1 through the async proxy
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");  // both warps of the slot have written B1 / sCnt
+        if (half == 0 && lane == 0) {
+          sInv[(titer % 3) * K::TQ + ql] = 1.f / fmaxf(sCnt[2 * slot] + sCnt[2 * slot + 1], 1.f);
+          if (K::PASSES > 1) bulk_s2g(tile_scratch + (size_t)ql * K::B1_BYTES, sB1, K::B1_BYTES);
+        }
+      } else if (half == 0 && lane == 0) {
+        mbar_expect_tx(&bar_full[pair], K::B1_BYTES);
+        bulk_g2s(sB1, tile_scratch + (size_t)ql * K::B1_BYTES, K::B1_BYTES, &bar_full[pair]);
+      }
+      cp_async_arrive_noinc(&bar_full[pair]);
+      if (lane == 0) mbar_arrive(&bar_full[pair]);  // release: this warp's shared-memory stores, in program order
+      if (slot == 0 && half == 0) SPR_TR(2, use, clock64());
+      ++use;
+      cur = nxt;
+      lc = ln;
+    }
+    if (K::PASSES > 1 && half == 0 && lane == 0) bulk_wait0();
   } else if (warp < K::W_PROD) {
     // =========================================== readback ===========================================
     const int rg = warp >> 2, qd = warp & 3;   // group, TMEM lane quadrant
     const int second = lane >> 4;               // lanes 0..15: first slot of the pair, 16..31: second slot
     const int cl = 8 * qd + ((lane & 15) >> 1);  // channel (within the pass) of this lane pair: D1 row 2 cl (+1)
     const int odd = lane & 1;                   // even lane: X_hi partials and kernel points 0..7, odd: X_lo and 8..15
-    uint32_t par = 0;                           // bit s: parity of the next completion of slot s
+    uint32_t par = 0;                           // bit p: parity of the next completion of slot pair p
     uint32_t seq = 0;
+    int rtr = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int q0 = tile * tq;
       const int cnt = min(nq, q0 + tq) - q0;
@@ -383,23 +480,19 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
             const int qa = base + 2 * pr;
             if (qa >= cnt) continue;
             const bool has_b = qa + 1 < cnt;
-            mbar_wait(&bar_d1full[2 * pr], (par >> (2 * pr)) & 1u);
-            par ^= 1u << (2 * pr);
-            if (has_b) {
-              mbar_wait(&bar_d1full[2 * pr + 1], (par >> (2 * pr + 1)) & 1u);
-              par ^= 1u << (2 * pr + 1);
-            }
+            mbar_wait_park(&bar_d1full[pr], (par >> pr) & 1u);
+            par ^= 1u << pr;
             tc_fence_after();
+            if (warp == 0) SPR_TR(6, rtr, clock64());
             float v[32];
             tmem_ld32(tmem + ((uint32_t)(32 * qd) << 16) + K::D1_COL0 + 32 * pr, v);
+            if (warp == 0) SPR_TR(7, rtr, clock64());
+            ++rtr;
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(&bar_d1free[2 * pr]);
-              if (has_b) mbar_arrive(&bar_d1free[2 * pr + 1]);
-            }
+            if (lane == 0) mbar_arrive(&bar_d1free[pr]);
             if (first) {  // the A tile still feeds the phase-2 MMAs of the previous pass until bar_done completes
-              if (seq > 0) mbar_wait(bar_done, (seq - 1) & 1);
+              if (seq > 0) mbar_wait_park(bar_done, (seq - 1) & 1);
               first = false;
             }
             // columns k and 16 + k (I_hi, I_lo), lanes 2c and 2c + 1 (X_hi, X_lo): the even lane finishes kernel points
@@ -430,7 +523,7 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
             }
           }
         }
-        if (first && seq > 0) mbar_wait(bar_done, (seq - 1) & 1);  // keep the phases of bar_done in step
+        if (first && seq > 0) mbar_wait_park(bar_done, (seq - 1) & 1);  // keep the phases of bar_done in step
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_afull);
@@ -444,7 +537,7 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
       const int q0 = tile * tq;
       const int cnt = min(nq, q0 + tq) - q0;
-      mbar_wait_sleep(bar_d2full, titer & 1);
+      mbar_wait_park(bar_d2full, titer & 1);
       tc_fence_after();
       const int ql = qd * 16 + (lane >> 1);
       const bool ok = ql < cnt;
@@ -475,14 +568,12 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
       if (lane == 0) mbar_arrive(bar_d2free);
     }
   } else if (warp == W_MMA) {
-    // =========================================== MMA issuer ===========================================
+    // ===================================== phase-2 MMA issuer =====================================
     if (lane == 0) {
-      constexpr uint32_t idesc1 = idesc_f16_amn(64, 32);
       constexpr uint32_t idesc2 = idesc_f16_f32(128, K::NS);
       const uint64_t adesc0 = desc_sw128_kmajor(smem_u32(sA));
       const uint64_t bdesc0 = desc_sw128_kmajor(smem_u32(sRing));
       uint32_t seq = 0;
-      uint32_t par = 0, used = 0;  // per slot: parity of the next fill, slot filled before
       int stage = 0;
       uint32_t phase = 0;
       int titer = 0;
@@ -490,30 +581,13 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
         const int q0 = tile * tq;
         const int cnt = min(nq, q0 + tq) - q0;
         for (int pass = 0; pass < K::PASSES; ++pass, ++seq) {
-          // ---- phase 1: one group of KS MMAs per query, in query order (query i lives in slot i % NSLOT) ----
-          for (int i = 0; i < cnt; ++i) {
-            const int slot = i % NSLOT;
-            const uint32_t p = (par >> slot) & 1u;
-            mbar_wait(&bar_full[slot], p);
-            if ((used >> slot) & 1u) mbar_wait(&bar_d1free[slot], p ^ 1u);  // readback of the previous fill has D1
-            tc_fence_after();
-            const uint32_t a1 = smem_u32(sSlots + slot * K::SLOT_BYTES);
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks)
-              umma_f16(tmem + ((uint32_t)((slot & 1) * 16) << 16) + K::D1_COL0 + 32 * (slot >> 1),
-                       desc_sw128_mnmajor(a1 + ks * 2048),
-                       desc_sw128_kmajor(a1 + K::A1_BYTES + ks * 32), idesc1, ks != 0);
-            umma_commit(&bar_d1full[slot]);
-            par ^= 1u << slot;
-            used |= 1u << slot;
-          }
           // ---- phase 2: D2 += A2 * [W_hi | W_lo]^T for this pass ----
-          mbar_wait(bar_afull, seq & 1);
-          if (pass == 0 && titer > 0) mbar_wait(bar_d2free, (titer - 1) & 1);
+          mbar_wait_park(bar_afull, seq & 1);
+          if (pass == 0 && titer > 0) mbar_wait_park(bar_d2free, (titer - 1) & 1);
           tc_fence_after();
           for (int a = 0; a < 8; ++a) {
             for (int sub = 0; sub < K::NSUB; ++sub) {
-              mbar_wait(&bar_wfull[stage], phase);
+              mbar_wait_park(&bar_wfull[stage], phase);
               tc_fence_after();
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
@@ -534,6 +608,49 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
       }
     }
     __syncwarp();
+  } else if (warp >= K::W_ISS) {
+    // ===================================== phase-1 MMA issuers =====================================
+    // issuer g serves the slot pairs p = g, g + 2, ... (the pairs of readback group g), in the order the queries were
+    // dealt: per pair one wait for the operands, one for the previous readback, 2 KS MMAs, one commit
+    if (lane == 0) {
+      const int rg = warp - K::W_ISS;
+      constexpr uint32_t idesc1 = idesc_f16_amn(64, 32);
+      uint32_t par = 0, used = 0;  // per pair: parity of the next fill, pair filled before
+      int trq = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int q0 = tile * tq;
+        const int cnt = min(nq, q0 + tq) - q0;
+        for (int pass = 0; pass < K::PASSES; ++pass) {
+          for (int base = 0; base < cnt; base += NSLOT) {
+#pragma unroll
+            for (int pr = 0; pr < NSLOT / 2; ++pr) {
+              if ((pr % K::NRG) != rg || base + 2 * pr >= cnt) continue;
+              const uint32_t p = (par >> pr) & 1u;
+              mbar_wait_park(&bar_full[pr], p);
+              if (rg == 0) SPR_TR(3, trq, clock64());
+              if ((used >> pr) & 1u) mbar_wait_park(&bar_d1free[pr], p ^ 1u);  // readback of the previous fill has D1
+              if (rg == 0) SPR_TR(4, trq, clock64());
+              fence_proxy_async_smem();  // the operands were written through the generic proxy (cp.async, st.shared)
+              tc_fence_after();
+#pragma unroll
+              for (int o = 0; o < 2; ++o) {
+                const uint32_t a1 = smem_u32(sSlots + (2 * pr + o) * K::SLOT_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+                  umma_f16(tmem + ((uint32_t)(o * 16) << 16) + K::D1_COL0 + 32 * pr, desc_sw128_mnmajor(a1 + ks * 2048),
+                           desc_sw128_kmajor(a1 + K::A1_BYTES + ks * 32), idesc1, ks != 0);
+              }
+              umma_commit(&bar_d1full[pr]);
+              if (rg == 0) SPR_TR(5, trq, clock64());
+              ++trq;
+              par ^= 1u << pr;
+              used |= 1u << pr;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // =========================================== weight stream ===========================================
     if (lane == 0) {
@@ -541,7 +658,7 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int blk = 0; blk < K::PASSES * K::BLOCKS_PER_PASS; ++blk) {
-          mbar_wait_sleep(&bar_wempty[stage], phase ^ 1);
+          mbar_wait_park(&bar_wempty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bar_wfull[stage], K::STAGE_BYTES);
           bulk_g2s(sRing + stage * K::STAGE_BYTES, wimg + (size_t)blk * K::STAGE_BYTES, K::STAGE_BYTES,
                    &bar_wfull[stage]);
@@ -560,41 +677,12 @@ __global__ void __launch_bounds__(GCfg<C, KS>::THREADS, 1)
 }
 
 // ---- host ----------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled() {
-  static std::once_flag once;
-  static EncodeTiledFn fn = nullptr;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
 template <int C, typename IdxT>
 int launch_g(const float* q, const void* idx, int row_stride, int H, const uint32_t* x16, const unsigned char* img,
              const float* kp, const float4* pts4, const unsigned int* amax_x_bits, const unsigned int* amax_w_bits,
              float extent, float* out, int nq, int ns, void* scratch, const int* order, cudaStream_t stream) {
   SPR_CHECK_ARG(H <= 64, "kpconv_forward_gather: at most 64 neighbour columns are supported (got %d)", H);
   SPR_CHECK_ARG(C <= 32 || scratch, "kpconv_forward_gather: scratch buffer missing");
-  EncodeTiledFn enc = encode_tiled();
-  SPR_CHECK_ARG(enc, "kpconv_forward_gather: cuTensorMapEncodeTiled is not available from this driver");
-  // the pre-split feature rows as a [ns, 2C] fp16 matrix; a box is one row of 64 elements (32 channels x hi/lo)
-  CUtensorMap tmap;
-  const cuuint64_t dims[2] = {(cuuint64_t)(2 * C), (cuuint64_t)ns};
-  const cuuint64_t strides[1] = {(cuuint64_t)(4 * C)};
-  const cuuint32_t box[2] = {64, 1};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint32_t*>(x16), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  SPR_CHECK_ARG(r == CUDA_SUCCESS, "kpconv_forward_gather: cuTensorMapEncodeTiled failed (%d)", (int)r);
   int tq = 64;
   {
     const int waves = (nq + kNumSMs * 64 - 1) / (kNumSMs * 64);
@@ -609,7 +697,7 @@ int launch_g(const float* q, const void* idx, int row_stride, int H, const uint3
   do {                                                                                                                    \
     using K = GCfg<C, KS_>;                                                                                               \
     SPR_CUDA(ensure_max_dynamic_smem(reinterpret_cast<const void*>(k_kpconv_g<C, IdxT, KS_>), K::SMEM));                  \
-    k_kpconv_g<C, IdxT, KS_><<<grid, K::THREADS, K::SMEM, stream>>>(tmap, q, idx_t, row_stride, H, img, kp, pts4,         \
+    k_kpconv_g<C, IdxT, KS_><<<grid, K::THREADS, K::SMEM, stream>>>(x16, q, idx_t, row_stride, H, img, kp, pts4,         \
                                                                     amax_x_bits, amax_w_bits, extent, out, nq, ns, tq,    \
                                                                     n_tiles, scr, order);                                 \
   } while (0)
@@ -640,6 +728,12 @@ int prepare_weights_g(const float* w, unsigned char* img, unsigned int* amax_w_b
 }  // namespace spr
 
 using namespace spr;
+
+#ifdef SPR_G_TRACE
+extern "C" __attribute__((visibility("default"))) int spr_kpconv_g_trace(long long* host_buf) {
+  return (int)cudaMemcpyFromSymbol(host_buf, g_trace, sizeof(long long) * 8 * 4096);
+}
+#endif
 
 extern "C" int spr_kpconv_gather_supported(int c, int H) { return (c == 32 || c == 64 || c == 128) && H > 0 && H <= 64; }
 

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256, STEPS == 1 ? 6 : 4)
                   const float2* __restrict__ stats, float slope, const float* __restrict__ residual,
                   float* __restrict__ out_f32, unsigned char* __restrict__ out_img, float a_scale,
                   uint32_t* __restrict__ out_x16, float4* __restrict__ out_pts4, const float* __restrict__ s_pts,
-                  unsigned int* __restrict__ amax_bits) {
+                  unsigned int* __restrict__ amax_bits, int x16_planar) {
   const int lane = threadIdx.x & 31;
   const int G = c / 8 < 32 ? c / 8 : 32;
   const int rpw = 32 / G;
@@ -335,8 +335,22 @@ __global__ void __launch_bounds__(256, STEPS == 1 ? 6 : 4)
           const __half lo = __float2half_rn(v - __half2float(hi));
           o8[i] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
         }
-        *reinterpret_cast<uint4*>(out_x16 + (size_t)row * c + ch) = make_uint4(o8[0], o8[1], o8[2], o8[3]);
-        *reinterpret_cast<uint4*>(out_x16 + (size_t)row * c + ch + 4) = make_uint4(o8[4], o8[5], o8[6], o8[7]);
+        if (x16_planar) {
+          // planar per group of 32 channels: [32 hi | 32 lo] fp16 (the gather kernel, kpconv_g.cu, copies the two
+          // 64-byte halves into separate operand blocks); this lane's 8 channels are 16 bytes of each half
+          unsigned char* grp = reinterpret_cast<unsigned char*>(out_x16 + (size_t)row * c) + (ch >> 5) * 128 + (ch & 31) * 2;
+          uint32_t hh[4], ll[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            hh[i] = __byte_perm(o8[2 * i], o8[2 * i + 1], 0x5410);
+            ll[i] = __byte_perm(o8[2 * i], o8[2 * i + 1], 0x7632);
+          }
+          *reinterpret_cast<uint4*>(grp) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+          *reinterpret_cast<uint4*>(grp + 64) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+        } else {
+          *reinterpret_cast<uint4*>(out_x16 + (size_t)row * c + ch) = make_uint4(o8[0], o8[1], o8[2], o8[3]);
+          *reinterpret_cast<uint4*>(out_x16 + (size_t)row * c + ch + 4) = make_uint4(o8[4], o8[5], o8[6], o8[7]);
+        }
       }
       if (gl == 0) {
         const float inv = pow2i(-e);
@@ -436,7 +450,7 @@ extern "C" int spr_instance_norm_lrelu_ex(const float* d_x, const int32_t* d_len
                                           float eps, float slope, const float* d_residual, float* d_out_f32,
                                           void* d_out_img, float a_scale, void* d_out_x16, void* d_out_pts4,
                                           const float* d_points, void* d_amax, const float* d_stats16,
-                                          void* d_workspace, size_t workspace_bytes, void* stream_) {
+                                          int x16_planar, void* d_workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SPR_CHECK_ARG(n > 0 && n_clouds > 0 && c > 0, "instance_norm_ex: empty input (n=%d, clouds=%d, c=%d)", n, n_clouds, c);
   SPR_CHECK_ARG(c % 32 == 0 && c <= 1024 && (c <= 256 || c % 256 == 0),
@@ -475,7 +489,7 @@ extern "C" int spr_instance_norm_lrelu_ex(const float* d_x, const int32_t* d_len
   k_in_apply_ex<S><<<blocks, 256, 0, stream>>>(d_x, offs, n_clouds, n, c, stats, slope, d_residual, d_out_f32,        \
                                                static_cast<unsigned char*>(d_out_img), a_scale,                      \
                                                static_cast<uint32_t*>(d_out_x16), static_cast<float4*>(d_out_pts4),  \
-                                               d_points, static_cast<unsigned int*>(d_amax))
+                                               d_points, static_cast<unsigned int*>(d_amax), x16_planar)
   switch (steps) {
     case 1: SPR_IN_APPLY(1); break;
     case 2: SPR_IN_APPLY(2); break;

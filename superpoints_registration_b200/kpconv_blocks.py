@@ -101,13 +101,14 @@ class BatchNormBlock(nn.Module):
         return y if slope == 1.0 else torch.nn.functional.leaky_relu(y, slope)
 
     def forward_ex(self, x, stack_lengths, slope: float = 1.0, residual=None, want_f32=True, want_image=False,
-                   kpconv_points=None, stats16=None):
+                   kpconv_points=None, stats16=None, kpconv_planar=False):
         """Format-aware variant (ops.instance_norm_lrelu_ex): the consumer's operand formats come out of the
         normalisation kernel itself.  Only with instance norm (every shipped config)."""
         if not self.use_bn:
             raise NotImplementedError("format-aware outputs need use_batch_norm=True")
         return ops.instance_norm_lrelu_ex(x, stack_lengths, IN_EPS, slope, residual, want_f32=want_f32,
-                                          want_image=want_image, kpconv_points=kpconv_points, stats16=stats16)
+                                          want_image=want_image, kpconv_points=kpconv_points, stats16=stats16,
+                                          kpconv_planar=kpconv_planar)
 
     def __repr__(self):
         return f'BatchNormBlock(in_feat: {self.in_dim:d}, momentum: {self.bn_momentum:.3f}, only_bias: {not self.use_bn})'
@@ -227,7 +228,9 @@ class ResnetBottleneckBlock(nn.Module):
         # handed to a later tensor)
         f_img = stash[1] if stash is not None and stash[0] is features else ops.gemm_prepare_input(features)
 
-        x = self.unary1.forward_ex(f_img, n_in, pre_lengths, want_f32=False, kpconv_points=s_pts)['kpconv']
+        planar = ops.kpconv_kernel_generation(self.out_dim // 4, inds.shape[1]) == 2
+        x = self.unary1.forward_ex(f_img, n_in, pre_lengths, want_f32=False, kpconv_points=s_pts,
+                                   kpconv_planar=planar)['kpconv']
         orders = getattr(batch, 'order', None)
         order = orders[self.layer_ind + 1 if strided else self.layer_ind] if orders is not None else None
         x = ops.kpconv_forward_prepared(q_pts, inds, x, self.KPConv.weights, self.KPConv.kernel_points,

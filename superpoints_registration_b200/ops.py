@@ -242,7 +242,7 @@ def block_stats(n_rows: int, c: int, device) -> torch.Tensor:
 
 
 def instance_norm_lrelu_ex(x, lengths, eps: float = 1e-5, slope: float = 1.0, residual=None, want_f32: bool = True,
-                           want_image: bool = False, kpconv_points=None, stats16=None):
+                           want_image: bool = False, kpconv_points=None, stats16=None, kpconv_planar: bool = False):
     """InstanceNorm (+ residual) + LeakyReLU with format-aware outputs.  Returns a dict with any of
     'f32' (rows), 'image' (operand image of the next tensor-core GEMM, K = c), 'kpconv' (PreparedFeatures for
     kpconv_forward_prepared; needs kpconv_points = the [n,3] points the rows belong to)."""
@@ -265,22 +265,25 @@ def instance_norm_lrelu_ex(x, lengths, eps: float = 1e-5, slope: float = 1.0, re
     ws = _ws(L.spr_instance_norm_workspace_bytes(n, lens.shape[0], c), xx.device)
     rc = L.spr_instance_norm_lrelu_ex(xx.data_ptr(), lens.data_ptr(), n, lens.shape[0], c, float(eps), float(slope),
                                       _ptr(res), _ptr(f32), _ptr(img), A_SCALE, _ptr(x16), _ptr(pts4), _ptr(pts),
-                                      _ptr(amax), _ptr(stats16), ws.data_ptr(), ws.numel(), _stream())
+                                      _ptr(amax), _ptr(stats16), 1 if kpconv_planar else 0, ws.data_ptr(), ws.numel(),
+                                      _stream())
     _lib.check(rc, "spr_instance_norm_lrelu_ex")
     if f32 is not None:
         out["f32"] = f32
     if img is not None:
         out["image"] = img
     if x16 is not None:
-        out["kpconv"] = PreparedFeatures(x16, pts4, amax, c)
+        out["kpconv"] = PreparedFeatures(x16, pts4, amax, c, planar=kpconv_planar)
     return out
 
 
 class PreparedFeatures:
     """Inputs of the tensor-core KPConv already in kernel format (pre-split rows, packed points, max|x|)."""
 
-    def __init__(self, x16, pts4, amax, c):
-        self.x16, self.pts4, self.amax, self.c = x16, pts4, amax, c
+    def __init__(self, x16, pts4, amax, c, planar: bool = False):
+        # planar: x16 holds per group of 32 channels [32 hi | 32 lo] halves (generation-2 kernel) instead of one
+        # (hi | lo << 16) word per channel (generation 1)
+        self.x16, self.pts4, self.amax, self.c, self.planar = x16, pts4, amax, c, planar
 
 
 class KPConvWeightImage:
@@ -327,10 +330,17 @@ def kpconv_gather_weight_image(weights: torch.Tensor) -> KPConvGatherWeightImage
     return wi
 
 
-def kpconv_kernel_generation() -> int:
-    """2 = csrc/kpconv_g.cu (TMA gather + both products on tcgen05) where it applies, 1 = csrc/kpconv_tc.cu.
-    SPR_KPCONV_GEN=1|2 selects."""
-    return int(os.environ.get("SPR_KPCONV_GEN", "1"))
+def kpconv_kernel_generation(c: int, H: int) -> int:
+    """Which tensor-core KPConv kernel a layer of c channels and H neighbour columns runs on: 2 = csrc/kpconv_g.cu
+    (asynchronous gather + both products on tcgen05) where it applies, 1 = csrc/kpconv_tc.cu.  SPR_KPCONV_GEN=1|2
+    selects the preference."""
+    want = int(os.environ.get("SPR_KPCONV_GEN", str(DEFAULT_KPCONV_GEN)))
+    if want == 2 and _lib.lib().spr_kpconv_gather_supported(int(c), int(H)):
+        return 2
+    return 1
+
+
+DEFAULT_KPCONV_GEN = 1
 
 
 def kpconv_forward_prepared(q_pts, neighb_inds, feats: PreparedFeatures, weights, kernel_points, extent: float,
@@ -339,9 +349,16 @@ def kpconv_forward_prepared(q_pts, neighb_inds, feats: PreparedFeatures, weights
     order: optional int32 permutation of the queries (CellGrid.order()) = processing order."""
     L = _lib.lib()
     if generation is None:
-        generation = kpconv_kernel_generation()
-    if generation == 2 and L.spr_kpconv_gather_supported(int(feats.c), int(neighb_inds.shape[1])):
+        generation = 2 if feats.planar else 1
+    if generation == 2:
+        if not L.spr_kpconv_gather_supported(int(feats.c), int(neighb_inds.shape[1])):
+            raise RuntimeError("kpconv_forward_prepared: the generation-2 kernel does not support this shape")
+        if not feats.planar:
+            raise RuntimeError("kpconv_forward_prepared: the generation-2 kernel needs planar pre-split rows "
+                               "(instance_norm_lrelu_ex(..., kpconv_planar=True))")
         return _kpconv_forward_gather(q_pts, neighb_inds, feats, weights, kernel_points, extent, order)
+    if feats.planar:
+        raise RuntimeError("kpconv_forward_prepared: the generation-1 kernel needs interleaved pre-split rows")
     q = _f32c(q_pts, "q_pts")
     kp = _f32c(kernel_points, "kernel_points")
     idx, is64, stride, H = _idx_arg(neighb_inds)

@@ -28,7 +28,7 @@ def _case(c, lens, H, r, seed, dense_first=True):
     tp, tl = _t(pts), _t(lens)
     grid = ops.CellGrid(tp, tl, r)
     x = rng.normal(size=(n, c)).astype(np.float32) * 1.5 + 0.2
-    o = ops.instance_norm_lrelu_ex(_t(x), tl, slope=0.1, want_f32=True, kpconv_points=tp)
+    o = ops.instance_norm_lrelu_ex(_t(x), tl, slope=0.1, want_f32=True, kpconv_points=tp, kpconv_planar=True)
     w = _t((rng.normal(size=(15, c, c)) / np.sqrt(15 * c)).astype(np.float32))
     kp = _t(load_kernels(r, 15))
     return pts, tp, tl, grid, o["f32"], o["kpconv"], w, kp, r * 2.0 / 2.5
@@ -68,8 +68,9 @@ def test_gather_kernel_multi_tile_parity_and_determinism(c):
                 assert torch.equal(outs[0], other), (c, dtype, order is not None)
             err = (outs[0] - anchor).abs().max().item()
             assert err <= FEAT_RTOL * scale, (c, dtype, order is not None, err, scale)
-        gen1 = ops.kpconv_forward_prepared(tp, idx, prep, w, kp, ext, generation=1)
-        assert (outs[0] - gen1).abs().max().item() <= FEAT_RTOL * scale
+        prep1 = ops.instance_norm_lrelu_ex(f32, tl, slope=1.0, want_f32=False, kpconv_points=tp)["kpconv"]   # same rows, gen-1 layout
+        with pytest.raises(RuntimeError):
+            ops.kpconv_forward_prepared(tp, idx, prep1, w, kp, ext, generation=2)                          # wrong layout is refused
 
 
 def test_gather_kernel_strided_queries_and_empty_rows():

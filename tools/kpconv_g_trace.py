@@ -15,7 +15,7 @@ grid = ops.CellGrid(tp, tl, r)
 idx, mc = grid.query(tp, tl, H, index_dtype=torch.int32)
 print("valid/row", float((idx < n).sum()) / n)
 x = torch.from_numpy(rng.normal(size=(n, c)).astype(np.float32)).to(dev)
-prep = ops.instance_norm_lrelu_ex(x, tl, slope=0.1, want_f32=False, kpconv_points=tp)["kpconv"]
+prep = ops.instance_norm_lrelu_ex(x, tl, slope=0.1, want_f32=False, kpconv_points=tp, kpconv_planar=True)["kpconv"]
 w = torch.from_numpy((rng.normal(size=(15, c, c)) / np.sqrt(15 * c)).astype(np.float32)).to(dev)
 kp = torch.from_numpy(load_kernels(r, 15)).to(dev)
 for _ in range(2):
@@ -26,16 +26,21 @@ buf = np.zeros(8 * 4096, np.int64)
 rc = L.spr_kpconv_g_trace(buf.ctypes.data_as(ctypes.c_void_p))
 t = buf.reshape(8, 4096)
 t0 = t[0, 0]
-names = ["P0 before slot wait", "P0 slot free", "P0 arrived", "MMA full seen", "MMA d1free seen", "MMA committed", "R0 d1full seen", "R0 ld done"]
-nsl = 8 if c == 32 else 6
-print("first 6 fills of producer slot 0 (clocks since start):")
-for u in range(1, 7):
-    q = u * nsl   # global query index in CTA order handled by slot 0 at use u (pass structure ignored for C=32)
-    print(f" use {u}: P wait-start {t[0,u]-t0:7d} free {t[1,u]-t0:7d} arrive {t[2,u]-t0:7d} | MMA(q={q}) full {t[3,q]-t0:7d} d1free {t[4,q]-t0:7d} commit {t[5,q]-t0:7d}")
-d = np.diff(t[5, :400])
-print("MMA commit-to-commit interval: median", np.median(d), "mean", d.mean())
-print("MMA wait for full  (full seen - previous commit): median", np.median(t[3, 1:400] - t[5, 0:399]))
-print("MMA wait for d1free: median", np.median(t[4, 1:400] - t[3, 1:400]))
-print("P0: slot wait median", np.median(t[1, 1:50] - t[0, 1:50]), " fill (free->arrive) median", np.median(t[2, 1:50] - t[1, 1:50]), " period median", np.median(np.diff(t[2, 1:50])))
-print("P0 arrive -> MMA full seen (copy latency + queue): median", np.median([t[3, u * nsl] - t[2, u] for u in range(1, 40)]))
-print("R0: ld latency median", np.median(t[7, 1:100] - t[6, 1:100]), " pair period median", np.median(np.diff(t[6, 1:100])))
+# CTA 0, slot pair 0 (needs NSLOT = 8: C = 32, or H <= 32): fill f of the pair is produced by warp half f % 2 (traced: slot 0,
+# half 0 -> even fills, item f / 2), multiplied by issuer 0 (its event 2 f; 2 f + 1 is pair 2) and read back by group 0
+print("fill:  P wait-start  slot-free  arrived | MMA full-seen d1free-seen committed | R d1full-seen ld-done   (clocks)")
+for f in range(2, 26, 2):
+    i = f // 2
+    print(f" {f:3d}: {t[0,i]-t0:9d} {t[1,i]-t0:9d} {t[2,i]-t0:9d} | {t[3,2*f]-t0:9d} {t[4,2*f]-t0:9d} {t[5,2*f]-t0:9d} |"
+          f" {t[6,f]-t0:9d} {t[7,f]-t0:9d}")
+F = np.arange(4, 200, 2)
+I = F // 2
+med = lambda a: float(np.median(a))
+print("pair-0 fill period (R d1full seen, per fill):", med(np.diff(t[6, 4:200])))
+print("P: prepare (previous arrive -> wait-start)", med(t[0, I] - t[2, I - 1]), " slot wait", med(t[1, I] - t[0, I]),
+      " copy issue (free -> arrived)", med(t[2, I] - t[1, I]), " own period", med(np.diff(t[2, I])))
+print("P arrived -> MMA full seen (copy latency + other slot + queue)", med(t[3, 2 * F] - t[2, I]))
+print("MMA: full -> d1free seen", med(t[4, 2 * F] - t[3, 2 * F]), " issue (d1free -> committed)", med(t[5, 2 * F] - t[4, 2 * F]),
+      " issuer event period", med(np.diff(t[5, 8:400])))
+print("MMA committed -> R d1full seen", med(t[6, F] - t[5, 2 * F]), " R ld", med(t[7, F] - t[6, F]))
+print("R ld-done -> next fill's P slot-free (other warp, not traced); R ld-done(f-1) -> P slot-free(f)", med(t[1, I] - t[7, F - 1]))

@@ -43,7 +43,8 @@ for l in range(L):
         order = meta.order[l + 1 if strided else l]
         ns, nq, H = s.shape[0], q.shape[0], idx.shape[1]
         x = torch.from_numpy(rng.normal(size=(ns, c)).astype(np.float32)).to(dev)
-        prep = ops.instance_norm_lrelu_ex(x, lens, slope=0.1, want_f32=False, kpconv_points=s)["kpconv"]
+        preps = {1: ops.instance_norm_lrelu_ex(x, lens, slope=0.1, want_f32=False, kpconv_points=s)["kpconv"],
+                 2: ops.instance_norm_lrelu_ex(x, lens, slope=0.1, want_f32=False, kpconv_points=s, kpconv_planar=True)["kpconv"]}
         w = torch.from_numpy((rng.normal(size=(15, c, c)) / np.sqrt(15 * c)).astype(np.float32)).to(dev)
         kp = torch.from_numpy(load_kernels(r, 15)).to(dev)
         res, outs = {}, {}
@@ -53,7 +54,7 @@ for l in range(L):
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                outs[gen] = ops.kpconv_forward_prepared(q, idx, prep, w, kp, ext, order=order, generation=gen)
+                outs[gen] = ops.kpconv_forward_prepared(q, idx, preps[gen], w, kp, ext, order=order, generation=gen)
                 e1.record()
                 torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1))

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
       for (int tile = first; tile < limit; tile += step) {
         const int mt = resident ? tile : tile / n_tiles, nt = resident ? nt_fixed : tile % n_tiles;
         for (int a = 0; a < KA; ++a) {
-          mbar_wait(&bar_empty[stage], phase ^ 1);
+          mbar_wait_park(&bar_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bar_full[stage], resident ? A_STAGE : A_STAGE + B_STAGE);
           bulk_g2s(sA + stage * A_STAGE, g.a_img + ((size_t)mt * KA + a) * A_STAGE, A_STAGE, &bar_full[stage]);
           if (!resident)
@@ -147,13 +147,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      if (resident && first < limit) mbar_wait(bar_w, 0);
+      if (resident && first < limit) mbar_wait_park(bar_w, 0);
       for (int tile = first; tile < limit; tile += step, ++it) {
         const int buf = it & 1;
-        mbar_wait(&bar_acce[buf], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        mbar_wait_park(&bar_acce[buf], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         for (int a = 0; a < KA; ++a) {
-          mbar_wait(&bar_full[stage], phase);
+          mbar_wait_park(&bar_full[stage], phase);
           tc_fence_after();
           const int bslot = resident ? a : stage;
 #pragma unroll
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const GemmArgs g, i
     for (int it = set, tile = first + set * step; tile < limit; tile += 2 * step, it += 2) {
       const int buf = set;
       const int mt = resident ? tile : tile / n_tiles, nt = resident ? nt_fixed : tile % n_tiles;
-      mbar_wait(&bar_accf[buf], (it >> 1) & 1);
+      mbar_wait_park(&bar_accf[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16) + buf * 256 + chalf * 64;
       // The accumulator rows are per-lane (lane = stacked token row): writing them directly costs one memory

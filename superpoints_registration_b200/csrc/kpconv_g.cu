@@ -91,19 +91,6 @@ struct GCfg {
 };
 
 // ---- PTX pieces that tc05.cuh does not have ---------------------------------------------------------------------
-// mbarrier wait that parks the thread in hardware (suspend-time hint) instead of spinning: a polling warp costs issue
-// slots -- the first profile of this kernel spent 64 % of its issued instructions in try_wait loops
-__device__ __forceinline__ void mbar_wait_park(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra.uni WAIT_DONE;\n\t"
-      "bra.uni WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(20000u)
-      : "memory");
-}
 // 16-byte asynchronous copy global -> shared through L2 (LDGSTS); src_bytes = 0 writes zeros
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");

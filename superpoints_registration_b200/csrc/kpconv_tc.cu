@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
             // ---- the query is complete: split to fp16 pairs and store its two A rows ----
             // the A tile still feeds the MMAs of the previous pass until bar_done completes
             if (first) {
-              if (seq > 0) mbar_wait_sleep(bar_done, (seq - 1) & 1);
+              if (seq > 0) mbar_wait_park(bar_done, (seq - 1) & 1);
               if (pass == 0 && titer > 0) epilogue(prev_q0, prev_cnt, sInv + ((titer - 1) & 1) * K::TQ);
               first = false;
             }
@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
           }
         }
         if (first) {  // warp without a query in this pass
-          if (seq > 0) mbar_wait_sleep(bar_done, (seq - 1) & 1);
+          if (seq > 0) mbar_wait_park(bar_done, (seq - 1) & 1);
           if (pass == 0 && titer > 0) epilogue(prev_q0, prev_cnt, sInv + ((titer - 1) & 1) * K::TQ);
         }
         fence_proxy_async_smem();
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
       prev_cnt = cnt;
     }
     if (titer > 0) {  // the last tile's epilogue
-      mbar_wait_sleep(bar_done, (seq - 1) & 1);
+      mbar_wait_park(bar_done, (seq - 1) & 1);
       epilogue(prev_q0, prev_cnt, sInv + ((titer - 1) & 1) * K::TQ);
     }
   } else if (warp == K::WORKERS) {
@@ -578,11 +578,11 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int pass = 0; pass < K::PASSES; ++pass, ++seq) {
-          mbar_wait_sleep(bar_afull, seq & 1);
+          mbar_wait_park(bar_afull, seq & 1);
           tc_fence_after();
           for (int a = 0; a < 8; ++a) {
             for (int sub = 0; sub < K::NSUB; ++sub) {
-              mbar_wait_sleep(&bar_full[stage], phase);
+              mbar_wait_park(&bar_full[stage], phase);
               tc_fence_after();
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int blk = 0; blk < K::PASSES * K::BLOCKS_PER_PASS; ++blk) {
-          mbar_wait_sleep(&bar_empty[stage], phase ^ 1);
+          mbar_wait_park(&bar_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bar_full[stage], K::STAGE_BYTES);
           bulk_g2s(sRing + stage * K::STAGE_BYTES, wimg + (size_t)blk * K::STAGE_BYTES, K::STAGE_BYTES,
                    &bar_full[stage]);

@@ -44,7 +44,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// for the single-thread role warps, whose waits are long: back off so the spin does not take issue slots
+// for waits that are long (the single-thread role warps, a producer waiting for the tensor pipe): the thread is parked
+// in hardware up to `hint_ns` per attempt instead of spinning.  A polling loop -- even one with __nanosleep(64), which
+// returns after ~10 ns -- took 17 % of the issued instructions of kpconv_tc.cu (profiles/README.md, round 2).
+__device__ __forceinline__ void mbar_wait_park(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 20000u) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(hint_ns)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns = 64) {
   while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
 }

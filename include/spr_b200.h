@@ -193,6 +193,19 @@ SPR_API int spr_kpconv_forward_gather(const float* d_q, const void* d_idx, int i
                               const void* d_amax_w, const float* d_kp, float extent, float* d_out, int nq, int ns,
                               void* d_scratch, const int32_t* d_order, void* stream);
 
+/* Third-generation tensor-core KPConv (csrc/kpconv_s.cu): the structure of spr_kpconv_forward_prepared with the
+ * neighbours' rows staged through per-warp shared-memory rings by asynchronous copies (two 8-neighbour blocks ahead) and
+ * the warp-level MMA fragments read with ldmatrix.  Consumes the PLANAR pre-split rows (x16_planar = 1 of
+ * spr_instance_norm_lrelu_ex) and its own weight image (channels of a pass permuted); no scratch.  c in {32, 64, 128,
+ * 256}, H <= 96 (spr_kpconv_staged_supported).  Replaces the same reference operator, kpconv_blocks.py:269-414. */
+SPR_API int spr_kpconv_staged_supported(int c, int H);
+SPR_API size_t spr_kpconv_staged_weight_image_bytes(int c);
+SPR_API int spr_kpconv_staged_prepare_weights(const float* d_w, int c, void* d_img, void* d_amax_w, void* stream);
+SPR_API int spr_kpconv_forward_staged(const float* d_q, const void* d_idx, int idx_is_64, int row_stride, int H,
+                                      const void* d_pts4, const void* d_x16, const void* d_amax_x, int c,
+                                      const void* d_wimg, const void* d_amax_w, const float* d_kp, float extent,
+                                      float* d_out, int nq, int ns, const int32_t* d_order, void* stream);
+
 /* max_pool(x, inds)  kpconv_blocks.py:127-143: out[n,c] = max_h xpad[idx[n,h],c] where xpad has a zero
  * row appended for the shadow index. */
 SPR_API int spr_max_pool(const float* d_x, const void* d_idx, int idx_is_64, int row_stride, int H, int nq, int ns, int c,

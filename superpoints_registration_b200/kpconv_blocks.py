@@ -228,7 +228,7 @@ class ResnetBottleneckBlock(nn.Module):
         # handed to a later tensor)
         f_img = stash[1] if stash is not None and stash[0] is features else ops.gemm_prepare_input(features)
 
-        planar = ops.kpconv_kernel_generation(self.out_dim // 4, inds.shape[1]) == 2
+        planar = ops.kpconv_kernel_generation(self.out_dim // 4, inds.shape[1]) in (2, 3)
         x = self.unary1.forward_ex(f_img, n_in, pre_lengths, want_f32=False, kpconv_points=s_pts,
                                    kpconv_planar=planar)['kpconv']
         orders = getattr(batch, 'order', None)

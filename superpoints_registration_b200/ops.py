@@ -330,17 +330,46 @@ def kpconv_gather_weight_image(weights: torch.Tensor) -> KPConvGatherWeightImage
     return wi
 
 
+class KPConvStagedWeightImage:
+    """Weight image of the staged kernel (csrc/kpconv_s.cu: channels of a pass permuted to its accumulator layout)."""
+
+    def __init__(self, weights: torch.Tensor):
+        L = _lib.lib()
+        w = _f32c(weights.detach(), "weights")
+        self.c = w.shape[1]
+        self.img = torch.empty(L.spr_kpconv_staged_weight_image_bytes(self.c), dtype=torch.uint8, device=w.device)
+        self.amax = torch.empty(1, dtype=torch.int32, device=w.device)
+        rc = L.spr_kpconv_staged_prepare_weights(w.data_ptr(), self.c, self.img.data_ptr(), self.amax.data_ptr(), _stream())
+        _lib.check(rc, "spr_kpconv_staged_prepare_weights")
+        self.key = (weights.data_ptr(), weights._version)
+
+
+def kpconv_staged_weight_image(weights: torch.Tensor) -> KPConvStagedWeightImage:
+    key = (weights.data_ptr(), weights._version)
+    wi = getattr(weights, "_spr_kpconv_staged_image", None)
+    if wi is None or wi.key != key:
+        wi = KPConvStagedWeightImage(weights)
+        weights._spr_kpconv_staged_image = wi
+    return wi
+
+
 def kpconv_kernel_generation(c: int, H: int) -> int:
-    """Which tensor-core KPConv kernel a layer of c channels and H neighbour columns runs on: 2 = csrc/kpconv_g.cu
-    (asynchronous gather + both products on tcgen05) where it applies, 1 = csrc/kpconv_tc.cu.  SPR_KPCONV_GEN=1|2
-    selects the preference."""
+    """Which tensor-core KPConv kernel a layer of c channels and H neighbour columns runs on: 1 = csrc/kpconv_tc.cu,
+    2 = csrc/kpconv_g.cu (asynchronous gather + both products on tcgen05), 3 = csrc/kpconv_s.cu (rows staged through
+    per-warp shared-memory rings).  SPR_KPCONV_GEN=1|2|3 selects the preference (default 3); a shape the preferred
+    kernel does not support falls back to generation 1, which supports every shape of the tensor-core path.  With
+    preference 3, layers of 256 channels stay on generation 1: at the bench size the last level has ~1.3 tiles per SM,
+    where generation 3's deeper pipeline fill per channel pass costs more than its prefetch distance gains
+    (profiles/r2c_kpconv_gen_bench.log: 0.86x at C = 256, 1.02-1.24x below)."""
     want = int(os.environ.get("SPR_KPCONV_GEN", str(DEFAULT_KPCONV_GEN)))
+    if want == 3 and int(c) <= 128 and _lib.lib().spr_kpconv_staged_supported(int(c), int(H)):
+        return 3
     if want == 2 and _lib.lib().spr_kpconv_gather_supported(int(c), int(H)):
         return 2
     return 1
 
 
-DEFAULT_KPCONV_GEN = 1
+DEFAULT_KPCONV_GEN = 3
 
 
 def kpconv_forward_prepared(q_pts, neighb_inds, feats: PreparedFeatures, weights, kernel_points, extent: float,
@@ -349,7 +378,18 @@ def kpconv_forward_prepared(q_pts, neighb_inds, feats: PreparedFeatures, weights
     order: optional int32 permutation of the queries (CellGrid.order()) = processing order."""
     L = _lib.lib()
     if generation is None:
-        generation = 2 if feats.planar else 1
+        generation = 1
+        if feats.planar:  # planar rows are read by generations 2 and 3 only
+            generation = kpconv_kernel_generation(feats.c, neighb_inds.shape[1])
+            if generation == 1:
+                generation = 3
+    if generation == 3:
+        if not L.spr_kpconv_staged_supported(int(feats.c), int(neighb_inds.shape[1])):
+            raise RuntimeError("kpconv_forward_prepared: the generation-3 kernel does not support this shape")
+        if not feats.planar:
+            raise RuntimeError("kpconv_forward_prepared: the generation-3 kernel needs planar pre-split rows "
+                               "(instance_norm_lrelu_ex(..., kpconv_planar=True))")
+        return _kpconv_forward_staged(q_pts, neighb_inds, feats, weights, kernel_points, extent, order)
     if generation == 2:
         if not L.spr_kpconv_gather_supported(int(feats.c), int(neighb_inds.shape[1])):
             raise RuntimeError("kpconv_forward_prepared: the generation-2 kernel does not support this shape")
@@ -376,6 +416,26 @@ def kpconv_forward_prepared(q_pts, neighb_inds, feats: PreparedFeatures, weights
                                        wi.amax.data_ptr(), kp.data_ptr(), float(extent), out.data_ptr(), nq, ns,
                                        _ptr(scratch), _ptr(order), _stream())
     _lib.check(rc, "spr_kpconv_forward_prepared")
+    return out
+
+
+def _kpconv_forward_staged(q_pts, neighb_inds, feats: PreparedFeatures, weights, kernel_points, extent, order):
+    L = _lib.lib()
+    q = _f32c(q_pts, "q_pts")
+    kp = _f32c(kernel_points, "kernel_points")
+    idx, is64, stride, H = _idx_arg(neighb_inds)
+    nq, ns = q.shape[0], feats.x16.shape[0]
+    if order is not None and (order.dtype != torch.int32 or order.shape[0] != nq or not order.is_cuda):
+        raise RuntimeError("kpconv_forward_prepared: order must be an int32 CUDA tensor with one entry per query")
+    wi = kpconv_staged_weight_image(weights)
+    if wi.c != feats.c:
+        raise RuntimeError("kpconv_forward_prepared: channel mismatch between features and weights")
+    out = torch.empty((nq, feats.c), dtype=torch.float32, device=q.device)
+    rc = L.spr_kpconv_forward_staged(q.data_ptr(), idx.data_ptr(), is64, stride, H, feats.pts4.data_ptr(),
+                                     feats.x16.data_ptr(), feats.amax.data_ptr(), feats.c, wi.img.data_ptr(),
+                                     wi.amax.data_ptr(), kp.data_ptr(), float(extent), out.data_ptr(), nq, ns,
+                                     _ptr(order), _stream())
+    _lib.check(rc, "spr_kpconv_forward_staged")
     return out
 
 

@@ -1,6 +1,6 @@
-"""KPConv layer shapes of the 4-stage encoder on a 3DMatch-shape pyramid: generation 1 (kpconv_tc.cu) against generation 2
-(kpconv_g.cu) through the prepared entry point, CUDA-event timings, L2 flushed.
-    python tools/kpconv_gen_bench.py [--pairs 8] [--reps 5]"""
+"""KPConv layer shapes of the 4-stage encoder on a 3DMatch-shape pyramid: generation 1 (kpconv_tc.cu) against generations 2
+(kpconv_g.cu) and 3 (kpconv_s.cu) through the prepared entry point, CUDA-event timings, L2 flushed.
+    python tools/kpconv_gen_bench.py [--pairs 8] [--reps 5] [--gens 1,3]"""
 import argparse
 import os
 import sys
@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--pairs", type=int, default=8)
 ap.add_argument("--points", type=int, default=20000)
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--gens", default="1,2,3")
 args = ap.parse_args()
 dev = "cuda:0"
 cfg = spr.threedmatch_4stage_config()
@@ -27,13 +28,12 @@ rng = np.random.default_rng(0)
 r0 = cfg.first_subsampling_dl * cfg.conv_radius
 L = len(meta["points"])
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-print("level strided   C       Nq   H |  gen1 ms   GB/s |  gen2 ms   GB/s | speed-up  max|diff|/max|out|")
-tot = {1: 0.0, 2: 0.0}
+GENS = [int(g) for g in args.gens.split(",")]
+print("level strided   C       Nq   H | " + " | ".join(f" gen{g} ms   GB/s" for g in GENS) + " | vs gen1, max|diff|/max|out|")
+tot = {g: 0.0 for g in GENS}
 for l in range(L):
     c = (cfg.first_feats_dim // 4) * 2 ** l
     for strided in ((False, True) if l + 1 < L else (False,)):
-        if not ops._lib.lib().spr_kpconv_gather_supported(c, 40):
-            continue
         r = r0 * 2 ** l
         ext = r * cfg.KP_extent / cfg.conv_radius
         s = meta["points"][l]
@@ -43,12 +43,14 @@ for l in range(L):
         order = meta.order[l + 1 if strided else l]
         ns, nq, H = s.shape[0], q.shape[0], idx.shape[1]
         x = torch.from_numpy(rng.normal(size=(ns, c)).astype(np.float32)).to(dev)
-        preps = {1: ops.instance_norm_lrelu_ex(x, lens, slope=0.1, want_f32=False, kpconv_points=s)["kpconv"],
-                 2: ops.instance_norm_lrelu_ex(x, lens, slope=0.1, want_f32=False, kpconv_points=s, kpconv_planar=True)["kpconv"]}
+        p_il = ops.instance_norm_lrelu_ex(x, lens, slope=0.1, want_f32=False, kpconv_points=s)["kpconv"]
+        p_pl = ops.instance_norm_lrelu_ex(x, lens, slope=0.1, want_f32=False, kpconv_points=s, kpconv_planar=True)["kpconv"]
+        preps = {1: p_il, 2: p_pl, 3: p_pl}
+        gens = [g for g in GENS if g != 2 or ops._lib.lib().spr_kpconv_gather_supported(c, H)]
         w = torch.from_numpy((rng.normal(size=(15, c, c)) / np.sqrt(15 * c)).astype(np.float32)).to(dev)
         kp = torch.from_numpy(load_kernels(r, 15)).to(dev)
         res, outs = {}, {}
-        for gen in (1, 2):
+        for gen in gens:
             best = 1e9
             for _ in range(args.reps):
                 flush.zero_()
@@ -61,7 +63,8 @@ for l in range(L):
             res[gen] = best
             tot[gen] += best * (1 if strided else 2 if l > 0 else 1)
         by = nq * H * (4 * c + 16) + nq * (12 + 4 * c) + 4 * 15 * c * c + 180
-        diff = (outs[1] - outs[2]).abs().max().item() / outs[1].abs().max().item()
-        print(f"{l:5d} {str(strided):7s} {c:4d} {nq:8d} {H:3d} | {res[1]:8.3f} {by / res[1] / 1e6:6.0f} | {res[2]:8.3f} "
-              f"{by / res[2] / 1e6:6.0f} | {res[1] / res[2]:6.2f}x   {diff:.2e}")
-print(f"encoder sum (two plain layers per level >= 1): gen1 {tot[1]:.3f} ms, gen2 {tot[2]:.3f} ms")
+        cols = " | ".join(f"{res[g]:8.3f} {by / res[g] / 1e6:6.0f}" if g in res else " " * 15 for g in GENS)
+        rel = "  ".join(f"gen{g} {res[1] / res[g]:4.2f}x {(outs[1] - outs[g]).abs().max().item() / outs[1].abs().max().item():.1e}"
+                        for g in gens if g != 1 and 1 in res)
+        print(f"{l:5d} {str(strided):7s} {c:4d} {nq:8d} {H:3d} | {cols} | {rel}")
+print("encoder sum (two plain layers per level >= 1): " + ", ".join(f"gen{g} {tot[g]:.3f} ms" for g in GENS))

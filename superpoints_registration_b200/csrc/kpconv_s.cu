@@ -76,9 +76,20 @@ __device__ __forceinline__ float influence_scaled(float cx, float cy, float cz, 
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(d2));  // MUFU.SQRT, rel. error ~2^-23, sqrt(0) = 0
   return fmaxf(fmaf(-d, s_ie, s), 0.f);
 }
-// 16-byte asynchronous copy global -> shared through L2 (LDGSTS); src_bytes = 0 writes zeros
+// 16-byte asynchronous copy global -> shared through L2 (LDGSTS); src_bytes = 0 writes zeros without touching memory.
+// (Absent neighbours must NOT be redirected to a shared all-zero row instead: every SM then reads the same line for a
+// quarter of its copies -- measured 2x slower for the whole kernel.)
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+// keeps a per-lane constant in its register: without it the compiler re-derives these offsets from the lane number in
+// every iteration (~100 of the ~1150 warp instructions per query in the first profile of this kernel)
+__device__ __forceinline__ uint32_t pinned(uint32_t v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -204,16 +215,19 @@ __global__ void __launch_bounds__(SCfg<C>::THREADS, 1)
     const float k1x = g < 7 ? sKp[3 * (g + 8)] : 1.0e18f, k1y = g < 7 ? sKp[3 * (g + 8) + 1] : 0.f,
                 k1z = g < 7 ? sKp[3 * (g + 8) + 2] : 0.f;
     // ---- the warp's ring of block slots ----
-    const uint32_t ring = smem_u32(smem + K::OFF_STAGING + warp * (K::DEPTH * K::SLOT_BYTES));
+    const uint32_t ring = pinned(smem_u32(smem + K::OFF_STAGING + warp * (K::DEPTH * K::SLOT_BYTES)));
+    const uint32_t sA32 = smem_u32(sA);
     // copy role: rows crow and crow + 4 of a block, 16-byte chunk cch of the 128-byte row (chunks 0..3 = hi halves of
     // channels 0-7 .. 24-31, chunks 4..7 = lo halves); chunk c of row r is stored at chunk position c ^ r
     const int crow = lane >> 3, cch = lane & 7;
-    const uint32_t xdst0 = crow * 128 + ((cch ^ crow) << 4), xdst1 = (crow + 4) * 128 + ((cch ^ (crow + 4)) << 4);
-    const uint32_t pdst0 = K::SLOT_X + crow * 16, pdst1 = K::SLOT_X + (crow + 4) * 16;
+    // (row crow + 4: 512 bytes further, chunk position with bit 2 flipped)
+    const uint32_t xdst0 = pinned(crow * 128 + ((cch ^ crow) << 4));
+    const uint32_t pdst0 = pinned(K::SLOT_X + crow * 16);
     // read role: ldmatrix row address of matrix lane / 8 (= channel tile), row lane % 8 (= neighbour of the block)
     const int lrow = lane & 7, lm = lane >> 3;
-    const uint32_t hi_off = lrow * 128 + ((lm ^ lrow) << 4), lo_off = lrow * 128 + (((4 + lm) ^ lrow) << 4);
-    const uint32_t pa_off = K::SLOT_X + 32 * t, hdr_off = K::SLOT_X + K::SLOT_P;
+    const uint32_t hi_off = pinned(lrow * 128 + ((lm ^ lrow) << 4));  // lo parts: chunk 4 + lm, i.e. bit 6 flipped
+    const uint32_t pa_off = pinned(K::SLOT_X + 32 * t);
+    constexpr uint32_t hdr_off = K::SLOT_X + K::SLOT_P;
 
     uint32_t seq = 0;
     int titer = 0;
@@ -327,12 +341,13 @@ __global__ void __launch_bounds__(SCfg<C>::THREADS, 1)
             const int j0 = __shfl_sync(kFull, jsel, src);
             const int j1 = __shfl_sync(kFull, jsel, src + 4);
             const uint32_t slot = ring + s * K::SLOT_BYTES;
-            const size_t r0 = j0 >= 0 ? (size_t)j0 : 0, r1 = j1 >= 0 ? (size_t)j1 : 0;
-            cp_async16(slot + xdst0, xpass + r0 * (4 * C), j0 >= 0 ? 16u : 0u);
-            cp_async16(slot + xdst1, xpass + r1 * (4 * C), j1 >= 0 ? 16u : 0u);
+            const uint32_t n0 = j0 >= 0 ? 16u : 0u, n1 = j1 >= 0 ? 16u : 0u;  // absent neighbours: zero fill
+            const unsigned r0 = max(j0, 0), r1 = max(j1, 0);
+            cp_async16(slot + xdst0, xpass + (size_t)r0 * (4 * C), n0);
+            cp_async16(slot + ((xdst0 ^ 64u) + 512u), xpass + (size_t)r1 * (4 * C), n1);
             if (cch == 0) {
-              cp_async16(slot + pdst0, pts4 + r0, j0 >= 0 ? 16u : 0u);
-              cp_async16(slot + pdst1, pts4 + r1, j1 >= 0 ? 16u : 0u);
+              cp_async16(slot + pdst0, pts4 + r0, n0);
+              cp_async16(slot + pdst0 + 64, pts4 + r1, n1);
             }
             if (lane == 0) {
               const int meta = ql_iss | (b << 8) | (bm == 0 ? 1 << 16 : 0) | (firstblk ? 1 << 17 : 0);
@@ -381,7 +396,7 @@ __global__ void __launch_bounds__(SCfg<C>::THREADS, 1)
           const float4 pa = lds128(slot + pa_off), pb = lds128(slot + pa_off + 16);
           uint32_t bh[4], bl[4];
           ldmatrix_x4_trans(slot + hi_off, bh);
-          ldmatrix_x4_trans(slot + lo_off, bl);
+          ldmatrix_x4_trans(slot + (hi_off ^ 64u), bl);
           {
             const float ax = pa.x - hdr.x, ay = pa.y - hdr.y, az = pa.z - hdr.z;
             const float bx = pb.x - hdr.x, by = pb.y - hdr.y, bz = pb.z - hdr.z;
@@ -433,10 +448,10 @@ __global__ void __launch_bounds__(SCfg<C>::THREADS, 1)
               lo[i] = h2_bits(__floats2half2_rn(v0 - hf.x, v1 - hf.y));
             }
             const int k = g + 8 * half;
-            unsigned char* atom = sA + (k >> 1) * K::A_ATOM_BYTES;
+            const uint32_t atom = sA32 + (k >> 1) * K::A_ATOM_BYTES;
             const uint32_t j = (k & 1) * 4 + t;
-            *reinterpret_cast<uint4*>(atom + sw128_offset(r0, j)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(atom + sw128_offset(r1, j)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            sts128u(atom + sw128_offset(r0, j), hi[0], hi[1], hi[2], hi[3]);
+            sts128u(atom + sw128_offset(r1, j), lo[0], lo[1], lo[2], lo[3]);
           }
           if (pass == 0) {
             // a neighbour is replicated over g: count the g == 0 copies (lanes 0..3)

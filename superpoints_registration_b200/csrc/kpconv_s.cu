@@ -7,9 +7,9 @@
 // the 640 threads x 96 registers leave none -- and each block pays 8 PRMT + 2 LDG.128 + 64-bit address arithmetic to
 // assemble the B fragments of the warp-level MMAs.  Here
 //   * every producer warp owns a ring of three block slots in shared memory (8 feature rows of 128 B + 8 packed
-//     points + a 16-byte header); the rows of block i + 2 are requested with 16-byte asynchronous copies (cp.async
-//     through L2, zero-fill for absent neighbours) while block i is multiplied: two blocks of prefetch distance, no
-//     register holds data in flight;
+//     points + a 16-byte header; two slots from C = 64 on, where the third weight-ring stage needs the room); the rows
+//     of the next block(s) are requested with 16-byte asynchronous copies (cp.async through L2, zero-fill for absent
+//     neighbours) while block i is multiplied: no register holds data in flight;
 //   * the feature rows are in the PLANAR pre-split format (per 32-channel group 32 fp16 hi halves, then 32 lo halves),
 //     so the B fragments of the four channel tiles are ONE ldmatrix.x4.trans for the hi parts and one for the lo parts
 //     (rows XOR-swizzled in the slot: conflict-free);
@@ -39,14 +39,18 @@ struct SCfg {
   static constexpr int NS = NCOL < 128 ? NCOL : 128;  // N of one MMA = rows of one ring stage
   static constexpr int NSUB = NCOL / NS;
   static constexpr int STAGE_BYTES = NS * 128;
-  static constexpr int NSTAGES = C <= 32 ? 3 : 2;
+  // The shared memory left by the A tile is split between the weight ring and the producers' block slots.  Measured
+  // (profiles/r2c_kpconv_gen_bench_32pairs.log and the runs before it): a third ring stage is worth 6 % at C = 128 and
+  // 16 % at C = 256 -- the MMAs of a pass wait for 256 KB and more of weights through the ring while the producers wait
+  // for them (bar_done) -- whereas a third block slot per warp is worth 1 % (C = 32) or nothing (C = 64).
+  static constexpr int NSTAGES = 3;
   static constexpr int BLOCKS_PER_PASS = 8 * NSUB;  // 8 K atoms of 64 fp16 per pass
   static constexpr int TQ = 64;
   static constexpr int WORKERS = 18;  // (20 warps fit the shared memory at C = 32 but cap the registers at 80: measured 5 % slower)
   static constexpr int THREADS = (WORKERS + 2) * 32;
   static constexpr int A_ATOM_BYTES = 128 * 128;
   static constexpr int A_BYTES = 8 * A_ATOM_BYTES;
-  static constexpr int DEPTH = 3;                     // block slots per producer warp
+  static constexpr int DEPTH = C <= 32 ? 3 : 2;       // block slots per producer warp
   static constexpr int SLOT_X = 1024, SLOT_P = 128;   // 8 rows x 128 B, 8 packed points
   static constexpr int SLOT_BYTES = SLOT_X + SLOT_P + 16;
   static constexpr int STAGING_BYTES = WORKERS * DEPTH * SLOT_BYTES;
@@ -371,13 +375,13 @@ __global__ void __launch_bounds__(SCfg<C>::THREADS, 1)
           start_query();
         }
         issue_one(0);
-        issue_one(1);
+        if (K::DEPTH > 2) issue_one(1);
         float d[4][4];
         float fcount = 0.f;
-        int cs = 0, is = 2;  // ring slots of the block being multiplied / requested
+        int cs = 0, is = K::DEPTH - 1;  // ring slots of the block being multiplied / requested
 #pragma unroll 1
         while (n_done < n_iss) {
-          cp_async_wait<1>();  // this lane's copies of the oldest block have landed ...
+          cp_async_wait<K::DEPTH - 2>();  // this lane's copies of the oldest block have landed ...
           __syncwarp();        // ... and so have everybody's; the slot freed by the previous iteration is reusable
           issue_one(is);
           is = is == K::DEPTH - 1 ? 0 : is + 1;

@@ -356,13 +356,11 @@ def kpconv_staged_weight_image(weights: torch.Tensor) -> KPConvStagedWeightImage
 def kpconv_kernel_generation(c: int, H: int) -> int:
     """Which tensor-core KPConv kernel a layer of c channels and H neighbour columns runs on: 1 = csrc/kpconv_tc.cu,
     2 = csrc/kpconv_g.cu (asynchronous gather + both products on tcgen05), 3 = csrc/kpconv_s.cu (rows staged through
-    per-warp shared-memory rings).  SPR_KPCONV_GEN=1|2|3 selects the preference (default 3); a shape the preferred
-    kernel does not support falls back to generation 1, which supports every shape of the tensor-core path.  With
-    preference 3, layers of 256 channels stay on generation 1: at the bench size the last level has ~1.3 tiles per SM,
-    where generation 3's deeper pipeline fill per channel pass costs more than its prefetch distance gains
-    (profiles/r2c_kpconv_gen_bench.log: 0.86x at C = 256, 1.02-1.24x below)."""
+    per-warp shared-memory rings).  SPR_KPCONV_GEN=1|2|3 selects the preference (default 3: 1.01-1.26x of generation 1
+    at the bench layer shapes, profiles/r2c_kpconv_gen_bench_32pairs.log); a shape the preferred kernel does not support
+    falls back to generation 1, which supports every shape of the tensor-core path."""
     want = int(os.environ.get("SPR_KPCONV_GEN", str(DEFAULT_KPCONV_GEN)))
-    if want == 3 and int(c) <= 128 and _lib.lib().spr_kpconv_staged_supported(int(c), int(H)):
+    if want == 3 and _lib.lib().spr_kpconv_staged_supported(int(c), int(H)):
         return 3
     if want == 2 and _lib.lib().spr_kpconv_gather_supported(int(c), int(H)):
         return 2

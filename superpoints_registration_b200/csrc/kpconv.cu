@@ -193,6 +193,114 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Cin == 1, second version (round 2): ONE THREAD per query.  The warp-per-query kernel above spends ~535 warp
+// instructions per query, of which only ~200 are influence arithmetic: the rest is the per-block choreography
+// (ballots, shuffles of indices, the butterfly at the end, a padded 16th kernel point).  With a thread per query there
+// is no cross-lane traffic at all: the 15 kernel points live in registers, a neighbour costs one 16-byte gather and
+// 15 x 9 arithmetic instructions (3 FADD, FMUL, 2 FFMA, MUFU.SQRT, FFMA.SAT, FFMA), the neighbours of the NEXT group
+// of four are in flight while the current group is evaluated, and the 15 x Cout mat-vec reads W from shared memory
+// with broadcast 16-byte loads.  A group of four columns that is padding in all 32 rows of the warp is skipped.
+// ---------------------------------------------------------------------------------------------
+template <typename IdxT, int COUT>
+__global__ void __launch_bounds__(128, 4)
+    k_kpconv_cin1_t(const float* __restrict__ q, const float4* __restrict__ packed, const IdxT* __restrict__ idx,
+                    int row_stride, int H, const float* __restrict__ w, const float* __restrict__ kp, float extent,
+                    float* __restrict__ out, int nq, int ns) {
+  __shared__ __align__(16) float s_w[KP * COUT];
+  for (int i = threadIdx.x; i < KP * COUT; i += blockDim.x) s_w[i] = __ldg(w + i);
+  float kx[KP], ky[KP], kz[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    kx[k] = __ldg(kp + 3 * k);
+    ky[k] = __ldg(kp + 3 * k + 1);
+    kz[k] = __ldg(kp + 3 * k + 2);
+  }
+  __syncthreads();
+  const float inv_extent = 1.f / extent;
+  const int n_groups = (H + 3) >> 2;
+  for (int base = blockIdx.x * blockDim.x; base < nq; base += gridDim.x * blockDim.x) {
+    const int n = base + threadIdx.x;
+    const bool live = n < nq;
+    const IdxT* row = idx + (size_t)(live ? n : nq - 1) * row_stride;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (live) {
+      qx = __ldg(q + 3 * (size_t)n);
+      qy = __ldg(q + 3 * (size_t)n + 1);
+      qz = __ldg(q + 3 * (size_t)n + 2);
+    }
+    float acc[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[k] = 0.f;
+    float cnt = 0.f;
+    // group of four neighbours: indices -> packed points (an absent neighbour is the zero record: x = 0)
+    auto fetch = [&](int grp, float4 (&p)[4]) -> bool {
+      bool any = false;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int h = 4 * grp + e;
+        int j = -1;
+        if (live && h < H) j = load_idx(row + h);
+        p[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j >= 0 && j < ns) {
+          p[e] = __ldg(packed + j);
+          any = true;
+        }
+      }
+      return any;
+    };
+    float4 cur[4], nxt[4];
+    bool cur_any = __any_sync(kFull, fetch(0, cur));
+    for (int grp = 0; grp < n_groups; ++grp) {
+      bool nxt_any = false;
+      if (grp + 1 < n_groups) nxt_any = __any_sync(kFull, fetch(grp + 1, nxt));
+      // (warp-uniform) a group without a neighbour in any of the warp's 32 rows -- the padded tails -- costs 4 loads
+      if (cur_any) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float cx = cur[e].x - qx, cy = cur[e].y - qy, cz = cur[e].z - qz, x = cur[e].w;
+        cnt += x > 0.f ? 1.f : 0.f;  // neighbour_num: rowsum(x) = x for Cin = 1
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          const float dx = cx - kx[k], dy = cy - ky[k], dz = cz - kz[k];
+          const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          float d;
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(d2));
+          acc[k] = fmaf(__saturatef(fmaf(-d, inv_extent, 1.f)), x, acc[k]);  // 1 - d/extent <= 1: sat == max(0, .)
+        }
+      }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) cur[e] = nxt[e];
+      cur_any = nxt_any;
+    }
+    if (!live) continue;
+    const float inv = 1.f / fmaxf(cnt, 1.f);
+    float* orow = out + (size_t)n * COUT;
+#pragma unroll 1
+    for (int oc = 0; oc < COUT; oc += 16) {
+      float o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const float4 wv = *reinterpret_cast<const float4*>(s_w + k * COUT + oc + 4 * v);
+          o[4 * v] = fmaf(acc[k], wv.x, o[4 * v]);
+          o[4 * v + 1] = fmaf(acc[k], wv.y, o[4 * v + 1]);
+          o[4 * v + 2] = fmaf(acc[k], wv.z, o[4 * v + 2]);
+          o[4 * v + 3] = fmaf(acc[k], wv.w, o[4 * v + 3]);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        *reinterpret_cast<float4*>(orow + oc + 4 * v) =
+            make_float4(o[4 * v] * inv, o[4 * v + 1] * inv, o[4 * v + 2] * inv, o[4 * v + 3] * inv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // main fused kernel, Cin = Cout = C in {32, 64, 128, 256}
 // ---------------------------------------------------------------------------------------------
 // V selects the tile shape: V = 0 -> one big CTA per SM (TQ rows, 512 threads for C >= 64),
@@ -553,6 +661,33 @@ extern "C" int spr_kpconv_forward(const float* d_q, const float* d_s, const void
     float4* packed = static_cast<float4*>(d_workspace);
     k_pack_points<<<(ns + 255) / 256, 256, 0, stream>>>(d_s, d_x, ns, packed);
     SPR_LAUNCH_CHECK("k_pack_points");
+    // thread-per-query kernel (round 2); SPR_STEM_GEN=1 selects the warp-per-query kernel of round 1 for A/B runs
+    static const bool stem_gen1 = [] {
+      const char* e = getenv("SPR_STEM_GEN");
+      return e && e[0] == '1';
+    }();
+    if (!stem_gen1 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
+      int grid_t = (nq + 127) / 128;
+      if (grid_t > kNumSMs * 4) grid_t = kNumSMs * 4;
+#define SPR_CIN1T(CO)                                                                                                \
+  do {                                                                                                               \
+    if (idx_is_64)                                                                                                   \
+      k_kpconv_cin1_t<long long, CO><<<grid_t, 128, 0, stream>>>(d_q, packed, static_cast<const long long*>(d_idx),  \
+                                                                 row_stride, H, d_w, d_kp, extent, d_out, nq, ns);   \
+    else                                                                                                             \
+      k_kpconv_cin1_t<int, CO><<<grid_t, 128, 0, stream>>>(d_q, packed, static_cast<const int*>(d_idx), row_stride, H, \
+                                                           d_w, d_kp, extent, d_out, nq, ns);                        \
+  } while (0)
+      switch (cout) {
+        case 32: SPR_CIN1T(32); break;
+        case 64: SPR_CIN1T(64); break;
+        case 128: SPR_CIN1T(128); break;
+        default: SPR_CIN1T(256); break;
+      }
+#undef SPR_CIN1T
+      SPR_LAUNCH_CHECK("k_kpconv_cin1_t");
+      return SPR_OK;
+    }
     const int warps = 8;
     int grid = (nq + warps - 1) / warps;
     if (grid > kNumSMs * 6) grid = kNumSMs * 6;

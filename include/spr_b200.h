@@ -173,12 +173,16 @@ SPR_API int spr_instance_norm_lrelu(const float* d_x, const int32_t* d_lengths, 
  * d_stats16 (optional): [ceil(n/16), c] pairs (sum, sum of squares) of every 16-row block of d_x, as written by the
  * producer of d_x (spr_gemm_tc / spr_kpconv_forward_prepared `d_stats16`).  With it the statistics pass over d_x is
  * skipped: blocks inside a cloud come from d_stats16, the ragged rows at the two ends of each cloud from d_x.
+ * d_residual_stats16 (optional, needs d_residual): the residual is itself a raw producer output with these block sums;
+ * it is normalised with its own per-cloud statistics (no activation) inside the apply kernel before it is added --
+ * the shortcut branch of a bottleneck block (kpconv_blocks.py:706-741) without a pass of its own.
  * x16_planar selects the layout of d_out_x16: 0 = one 32-bit word (hi | lo << 16) per channel (spr_kpconv_forward_prepared),
  * 1 = per group of 32 channels 32 hi halves then 32 lo halves (spr_kpconv_forward_gather, spr_kpconv_forward_staged). */
 SPR_API int spr_instance_norm_lrelu_ex(const float* d_x, const int32_t* d_lengths, int n, int n_clouds, int c, float eps,
                                float slope, const float* d_residual, float* d_out_f32, void* d_out_img, float a_scale,
                                void* d_out_x16, void* d_out_pts4, const float* d_points, void* d_amax,
-                               const float* d_stats16, int x16_planar, void* d_workspace, size_t workspace_bytes,
+                               const float* d_stats16, const float* d_residual_stats16, int x16_planar,
+                               void* d_workspace, size_t workspace_bytes,
                                void* stream);
 
 /* Second-generation tensor-core KPConv (csrc/kpconv_g.cu): the neighbour features are gathered by the TMA engine

@@ -40,7 +40,7 @@ _SIGNATURES = {
     "spr_instance_norm_lrelu": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_float, c_float, c_fp, c_fp, c_fp, c_size_t,
                                         c_void_p]),
     "spr_instance_norm_lrelu_ex": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_float, c_float, c_fp, c_fp, c_fp, c_float,
-                                           c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_size_t, c_void_p]),
+                                           c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_size_t, c_void_p]),
     "spr_kpconv_weight_image_bytes": (c_size_t, [c_int]),
     "spr_kpconv_prepare_weights": (c_int, [c_fp, c_int, c_fp, c_fp, c_void_p]),
     "spr_kpconv_scratch_bytes": (c_size_t, [c_int, c_int]),

@@ -243,7 +243,8 @@ template <int STEPS>
 __global__ void __launch_bounds__(256, STEPS == 1 ? 6 : 4)
     k_in_apply_ex(const float* __restrict__ x, const int* __restrict__ offs, int B, int n, int c,
                   const float2* __restrict__ stats, float slope, const float* __restrict__ residual,
-                  float* __restrict__ out_f32, unsigned char* __restrict__ out_img, float a_scale,
+                  const float2* __restrict__ res_stats, float* __restrict__ out_f32,
+                  unsigned char* __restrict__ out_img, float a_scale,
                   uint32_t* __restrict__ out_x16, float4* __restrict__ out_pts4, const float* __restrict__ s_pts,
                   unsigned int* __restrict__ amax_bits, int x16_planar) {
   const int lane = threadIdx.x & 31;
@@ -275,6 +276,16 @@ __global__ void __launch_bounds__(256, STEPS == 1 ? 6 : 4)
         const float4 r0 = *reinterpret_cast<const float4*>(residual + (size_t)row * c + ch);
         const float4 r1 = *reinterpret_cast<const float4*>(residual + (size_t)row * c + ch + 4);
         r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+        if (res_stats) {  // the residual is a raw producer output too: normalise it here (its own statistics, no
+                          // activation) instead of in a pass of its own -- same roundings as the two-pass route
+          const float4* rs4 = reinterpret_cast<const float4*>(res_stats + (size_t)b * c + ch);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 s2 = __ldg(rs4 + i);
+            r[2 * i] = __fmul_rn(r[2 * i] - s2.x, s2.y);
+            r[2 * i + 1] = __fmul_rn(r[2 * i + 1] - s2.z, s2.w);
+          }
+        }
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -307,9 +318,11 @@ __global__ void __launch_bounds__(256, STEPS == 1 ? 6 : 4)
         const uint32_t r2 = 2 * (row & 63);
         *reinterpret_cast<uint4*>(blk + sw128_off(r2, chunk & 7)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(blk + sw128_off(r2 + 1, chunk & 7)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        if (c < 64 && gl + c / 8 < 8) {  // K is padded to one 64-wide atom: the padding chunks must be finite
-          *reinterpret_cast<uint4*>(blk + sw128_off(r2, gl + c / 8)) = make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(blk + sw128_off(r2 + 1, gl + c / 8)) = make_uint4(0u, 0u, 0u, 0u);
+        if (st == 0 && gl < KA * 8 - c / 8) {  // K is padded to whole 64-wide atoms: the padding chunks must be finite
+          unsigned char* last = out_img + ((size_t)(row >> 6) * KA + (KA - 1)) * 16384;
+          const int pc = (c / 8 + gl) & 7;
+          *reinterpret_cast<uint4*>(last + sw128_off(r2, pc)) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(last + sw128_off(r2 + 1, pc)) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
     }
@@ -410,7 +423,7 @@ static size_t in_chunks_upper(int n, int B) { return (size_t)(n + kRowsPerChunk 
 extern "C" size_t spr_instance_norm_workspace_bytes(int n_rows, int n_clouds, int c) {
   if (n_rows < 0 || n_clouds < 0 || c < 0) return 0;
   size_t bytes = align_up(in_chunks_upper(n_rows, n_clouds) * (size_t)c * sizeof(double2), 256);
-  bytes += align_up((size_t)n_clouds * c * sizeof(float2), 256);
+  bytes += 2 * align_up((size_t)n_clouds * c * sizeof(float2), 256);  // statistics of x and of a raw residual
   bytes += align_up(((size_t)n_clouds + 1) * 4, 256);
   return bytes + 512;
 }
@@ -450,7 +463,8 @@ extern "C" int spr_instance_norm_lrelu_ex(const float* d_x, const int32_t* d_len
                                           float eps, float slope, const float* d_residual, float* d_out_f32,
                                           void* d_out_img, float a_scale, void* d_out_x16, void* d_out_pts4,
                                           const float* d_points, void* d_amax, const float* d_stats16,
-                                          int x16_planar, void* d_workspace, size_t workspace_bytes, void* stream_) {
+                                          const float* d_residual_stats16, int x16_planar, void* d_workspace,
+                                          size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SPR_CHECK_ARG(n > 0 && n_clouds > 0 && c > 0, "instance_norm_ex: empty input (n=%d, clouds=%d, c=%d)", n, n_clouds, c);
   SPR_CHECK_ARG(c % 32 == 0 && c <= 1024 && (c <= 256 || c % 256 == 0),
@@ -458,6 +472,7 @@ extern "C" int spr_instance_norm_lrelu_ex(const float* d_x, const int32_t* d_len
   SPR_CHECK_ARG(d_x && d_lengths && d_workspace, "instance_norm_ex: null pointer");
   SPR_CHECK_ARG(d_out_f32 || d_out_img || d_out_x16, "instance_norm_ex: no output requested");
   SPR_CHECK_ARG(!d_out_x16 || (d_out_pts4 && d_points && d_amax), "instance_norm_ex: KPConv outputs need pts4, points, amax");
+  SPR_CHECK_ARG(!d_residual_stats16 || d_residual, "instance_norm_ex: residual statistics without a residual");
   if (workspace_bytes < spr_instance_norm_workspace_bytes(n, n_clouds, c)) {
     set_error("instance_norm_ex: workspace too small");
     return SPR_ENOSPACE;
@@ -466,6 +481,7 @@ extern "C" int spr_instance_norm_lrelu_ex(const float* d_x, const int32_t* d_len
   const size_t chunks = in_chunks_upper(n, n_clouds);
   double2* part = ws.take<double2>(chunks * (size_t)c);
   float2* stats = ws.take<float2>((size_t)n_clouds * c);
+  float2* res_stats = ws.take<float2>((size_t)n_clouds * c);
   int* offs = ws.take<int>((size_t)n_clouds + 1);
   // the statistics kernels also write the clouds' row offsets (offs) that the apply kernel looks rows up in
   if (d_stats16) {  // the producer already summed 16-row blocks: no pass over x for the statistics
@@ -480,13 +496,20 @@ extern "C" int spr_instance_norm_lrelu_ex(const float* d_x, const int32_t* d_len
     k_in_stats<<<gs, 256, 0, stream>>>(part, d_lengths, n_clouds, c, eps, stats, offs);
     SPR_LAUNCH_CHECK("k_in_stats");
   }
+  if (d_residual_stats16) {  // raw residual (a producer's output with its 16-row block sums): normalised in the apply kernel
+    dim3 g16((c + 31) / 32, n_clouds);
+    k_in_stats16<<<g16, 256, 0, stream>>>(reinterpret_cast<const float2*>(d_residual_stats16), d_residual, d_lengths, c,
+                                          eps, res_stats, offs);
+    SPR_LAUNCH_CHECK("k_in_stats16 (residual)");
+  }
   if (d_amax) SPR_CUDA(cudaMemsetAsync(d_amax, 0, sizeof(unsigned int), stream));
   const int G = c / 8 < 32 ? c / 8 : 32;
   const int rows_per_block = 8 * (32 / G);
   const int steps = c / (8 * G);
   const unsigned blocks = (unsigned)((n + rows_per_block - 1) / rows_per_block);
 #define SPR_IN_APPLY(S)                                                                                              \
-  k_in_apply_ex<S><<<blocks, 256, 0, stream>>>(d_x, offs, n_clouds, n, c, stats, slope, d_residual, d_out_f32,        \
+  k_in_apply_ex<S><<<blocks, 256, 0, stream>>>(d_x, offs, n_clouds, n, c, stats, slope, d_residual,                   \
+                                               d_residual_stats16 ? res_stats : nullptr, d_out_f32,                  \
                                                static_cast<unsigned char*>(d_out_img), a_scale,                      \
                                                static_cast<uint32_t*>(d_out_x16), static_cast<float4*>(d_out_pts4),  \
                                                d_points, static_cast<unsigned int*>(d_amax), x16_planar)

@@ -201,23 +201,61 @@ __global__ void __launch_bounds__(256)
 // of four are in flight while the current group is evaluated, and the 15 x Cout mat-vec reads W from shared memory
 // with broadcast 16-byte loads.  A group of four columns that is padding in all 32 rows of the warp is skipped.
 // ---------------------------------------------------------------------------------------------
+// Packed fp32 pairs (sm_100 add/mul/fma.f32x2: one issue slot for two lanes of the FMA pipe).  The kernel is bound by
+// instruction issue, not by the pipe: kernel points are processed two at a time.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
+  f2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
+  f2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+  f2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 template <typename IdxT, int COUT>
 __global__ void __launch_bounds__(128, 4)
     k_kpconv_cin1_t(const float* __restrict__ q, const float4* __restrict__ packed, const IdxT* __restrict__ idx,
                     int row_stride, int H, const float* __restrict__ w, const float* __restrict__ kp, float extent,
                     float* __restrict__ out, int nq, int ns) {
+  constexpr int NP = KP / 2;  // kernel-point pairs (2p, 2p + 1); the last kernel point is handled alone
+  // The first version of this kernel was bound by the L1 data pipe (79 % of its wavefront peak, ncu): a scalar index
+  // load, a gather or a 16-byte row store of 32 threads that work on 32 different rows is 32 wavefronts.  Index rows are
+  // therefore read 16 bytes at a time, and (Cout <= 64) the output rows leave through a shared-memory transposition as
+  // contiguous 512-byte stores.
+  constexpr bool STAGED_OUT = COUT <= 64;
+  constexpr int OSTRIDE = COUT + 4;  // floats; 16-byte accesses of 8 consecutive rows fall into distinct banks
   __shared__ __align__(16) float s_w[KP * COUT];
+  __shared__ __align__(16) float s_out[STAGED_OUT ? 4 * 32 * OSTRIDE : 4];
   for (int i = threadIdx.x; i < KP * COUT; i += blockDim.x) s_w[i] = __ldg(w + i);
-  float kx[KP], ky[KP], kz[KP];
+  f2_t nkx[NP], nky[NP], nkz[NP];  // NEGATED kernel points (there is no packed subtraction)
 #pragma unroll
-  for (int k = 0; k < KP; ++k) {
-    kx[k] = __ldg(kp + 3 * k);
-    ky[k] = __ldg(kp + 3 * k + 1);
-    kz[k] = __ldg(kp + 3 * k + 2);
+  for (int p = 0; p < NP; ++p) {
+    nkx[p] = f2_pack(-__ldg(kp + 6 * p), -__ldg(kp + 6 * p + 3));
+    nky[p] = f2_pack(-__ldg(kp + 6 * p + 1), -__ldg(kp + 6 * p + 4));
+    nkz[p] = f2_pack(-__ldg(kp + 6 * p + 2), -__ldg(kp + 6 * p + 5));
   }
+  const float lx = __ldg(kp + 3 * (KP - 1)), ly = __ldg(kp + 3 * (KP - 1) + 1), lz = __ldg(kp + 3 * (KP - 1) + 2);
   __syncthreads();
   const float inv_extent = 1.f / extent;
   const int n_groups = (H + 3) >> 2;
+  // 16-byte index loads: 32-bit indices, rows that start on 16-byte boundaries
+  const bool vec_idx = sizeof(IdxT) == 4 && (row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(idx) & 15) == 0;
   for (int base = blockIdx.x * blockDim.x; base < nq; base += gridDim.x * blockDim.x) {
     const int n = base + threadIdx.x;
     const bool live = n < nq;
@@ -228,54 +266,86 @@ __global__ void __launch_bounds__(128, 4)
       qy = __ldg(q + 3 * (size_t)n + 1);
       qz = __ldg(q + 3 * (size_t)n + 2);
     }
-    float acc[KP];
+    f2_t acc2[NP];
 #pragma unroll
-    for (int k = 0; k < KP; ++k) acc[k] = 0.f;
-    float cnt = 0.f;
-    // group of four neighbours: indices -> packed points (an absent neighbour is the zero record: x = 0)
-    auto fetch = [&](int grp, float4 (&p)[4]) -> bool {
+    for (int p = 0; p < NP; ++p) acc2[p] = 0ull;
+    float acc_l = 0.f, cnt = 0.f;
+    // group of four neighbours: indices (requested TWO groups ahead) -> packed points (one group ahead); an absent
+    // neighbour is the zero record (x = 0).  Index load and gather are a dependent pair: with both in the same
+    // pipeline stage the warp waited for the index before it could request the point.
+    auto load_j = [&](int grp, int (&j4)[4]) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) j4[e] = -1;
+      if (grp >= n_groups || !live) return;
+      if (vec_idx && 4 * grp + 4 <= H) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(row) + grp);
+        j4[0] = v.x; j4[1] = v.y; j4[2] = v.z; j4[3] = v.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (4 * grp + e < H) j4[e] = load_idx(row + 4 * grp + e);
+      }
+    };
+    auto gather = [&](const int (&j4)[4], float4 (&p)[4]) -> bool {
       bool any = false;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int h = 4 * grp + e;
-        int j = -1;
-        if (live && h < H) j = load_idx(row + h);
         p[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j >= 0 && j < ns) {
-          p[e] = __ldg(packed + j);
+        if (j4[e] >= 0 && j4[e] < ns) {
+          p[e] = __ldg(packed + j4[e]);
           any = true;
         }
       }
       return any;
     };
     float4 cur[4], nxt[4];
-    bool cur_any = __any_sync(kFull, fetch(0, cur));
+    int jn[4];
+    load_j(0, jn);
+    bool cur_any = __any_sync(kFull, gather(jn, cur));
+    load_j(1, jn);
     for (int grp = 0; grp < n_groups; ++grp) {
-      bool nxt_any = false;
-      if (grp + 1 < n_groups) nxt_any = __any_sync(kFull, fetch(grp + 1, nxt));
+      const bool nxt_any = __any_sync(kFull, gather(jn, nxt));  // group grp + 1 (all absent past the end)
+      load_j(grp + 2, jn);
       // (warp-uniform) a group without a neighbour in any of the warp's 32 rows -- the padded tails -- costs 4 loads
       if (cur_any) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float cx = cur[e].x - qx, cy = cur[e].y - qy, cz = cur[e].z - qz, x = cur[e].w;
-        cnt += x > 0.f ? 1.f : 0.f;  // neighbour_num: rowsum(x) = x for Cin = 1
+        for (int e = 0; e < 4; ++e) {
+          const float cx = cur[e].x - qx, cy = cur[e].y - qy, cz = cur[e].z - qz, x = cur[e].w;
+          cnt += x > 0.f ? 1.f : 0.f;  // neighbour_num: rowsum(x) = x for Cin = 1
+          const f2_t cx2 = f2_pack(cx, cx), cy2 = f2_pack(cy, cy), cz2 = f2_pack(cz, cz), x2 = f2_pack(x, x);
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-          const float dx = cx - kx[k], dy = cy - ky[k], dz = cz - kz[k];
-          const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-          float d;
-          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(d2));
-          acc[k] = fmaf(__saturatef(fmaf(-d, inv_extent, 1.f)), x, acc[k]);  // 1 - d/extent <= 1: sat == max(0, .)
+          for (int p = 0; p < NP; ++p) {
+            const f2_t dx = f2_add(cx2, nkx[p]), dy = f2_add(cy2, nky[p]), dz = f2_add(cz2, nkz[p]);
+            const f2_t d2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+            float d2a, d2b, da, db;
+            f2_unpack(d2, d2a, d2b);
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(da) : "f"(d2a));
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(db) : "f"(d2b));
+            // 1 - d/extent <= 1: saturation to [0, 1] is max(0, .)
+            const f2_t w2 = f2_pack(__saturatef(fmaf(-da, inv_extent, 1.f)), __saturatef(fmaf(-db, inv_extent, 1.f)));
+            acc2[p] = f2_fma(w2, x2, acc2[p]);
+          }
+          {
+            const float dx = cx - lx, dy = cy - ly, dz = cz - lz;
+            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            float d;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(d2));
+            acc_l = fmaf(__saturatef(fmaf(-d, inv_extent, 1.f)), x, acc_l);
+          }
         }
-      }
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) cur[e] = nxt[e];
       cur_any = nxt_any;
     }
-    if (!live) continue;
+    if (!STAGED_OUT && !live) continue;
+    float acc[KP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) f2_unpack(acc2[p], acc[2 * p], acc[2 * p + 1]);
+    acc[KP - 1] = acc_l;
     const float inv = 1.f / fmaxf(cnt, 1.f);
-    float* orow = out + (size_t)n * COUT;
+    float* stage = s_out + ((threadIdx.x >> 5) * 32 + (threadIdx.x & 31)) * OSTRIDE;
+    float* orow = STAGED_OUT ? stage : out + (size_t)n * COUT;
 #pragma unroll 1
     for (int oc = 0; oc < COUT; oc += 16) {
       float o[16];
@@ -296,6 +366,21 @@ __global__ void __launch_bounds__(128, 4)
       for (int v = 0; v < 4; ++v)
         *reinterpret_cast<float4*>(orow + oc + 4 * v) =
             make_float4(o[4 * v] * inv, o[4 * v + 1] * inv, o[4 * v + 2] * inv, o[4 * v + 3] * inv);
+    }
+    if (STAGED_OUT) {  // the warp's 32 rows are contiguous in `out`: write them 512 bytes per instruction
+      __syncwarp();
+      constexpr int LPR = COUT / 4;  // lanes per row
+      const int lane = threadIdx.x & 31;
+      const float* wstage = s_out + (threadIdx.x >> 5) * 32 * OSTRIDE;
+      const int row0 = base + (threadIdx.x & ~31);
+#pragma unroll
+      for (int i = 0; i < LPR; ++i) {
+        const int f = i * 32 + lane, r = f / LPR, c4 = (f % LPR) * 4;
+        if (row0 + r < nq)
+          *reinterpret_cast<float4*>(out + (size_t)(row0 + r) * COUT + c4) =
+              *reinterpret_cast<const float4*>(wstage + r * OSTRIDE + c4);
+      }
+      __syncwarp();
     }
   }
 }

@@ -101,14 +101,14 @@ class BatchNormBlock(nn.Module):
         return y if slope == 1.0 else torch.nn.functional.leaky_relu(y, slope)
 
     def forward_ex(self, x, stack_lengths, slope: float = 1.0, residual=None, want_f32=True, want_image=False,
-                   kpconv_points=None, stats16=None, kpconv_planar=False):
+                   kpconv_points=None, stats16=None, kpconv_planar=False, residual_stats16=None):
         """Format-aware variant (ops.instance_norm_lrelu_ex): the consumer's operand formats come out of the
         normalisation kernel itself.  Only with instance norm (every shipped config)."""
         if not self.use_bn:
             raise NotImplementedError("format-aware outputs need use_batch_norm=True")
         return ops.instance_norm_lrelu_ex(x, stack_lengths, IN_EPS, slope, residual, want_f32=want_f32,
                                           want_image=want_image, kpconv_points=kpconv_points, stats16=stats16,
-                                          kpconv_planar=kpconv_planar)
+                                          kpconv_planar=kpconv_planar, residual_stats16=residual_stats16)
 
     def __repr__(self):
         return f'BatchNormBlock(in_feat: {self.in_dim:d}, momentum: {self.bn_momentum:.3f}, only_bias: {not self.use_bn})'
@@ -142,6 +142,13 @@ class UnaryBlock(nn.Module):
         stats = ops.block_stats(n_rows, self.out_dim, x_image.device) if self.use_bn else None
         y = ops.gemm_tc(x_image, ops.weight_image(self.mlp.weight), self.mlp.bias, n_rows, ops.OUT_F32, stats16=stats)
         return self.batch_norm.forward_ex(y, stack_lengths, slope=slope, residual=residual, stats16=stats, **wants)
+
+    def linear_raw(self, x_image, n_rows):
+        """The Linear alone, with the 16-row block sums of its output: (y, stats16).  For a consumer that applies this
+        block's normalisation itself (the projected shortcut, normalised inside unary2's apply kernel)."""
+        stats = ops.block_stats(n_rows, self.out_dim, x_image.device)
+        y = ops.gemm_tc(x_image, ops.weight_image(self.mlp.weight), self.mlp.bias, n_rows, ops.OUT_F32, stats16=stats)
+        return y, stats
 
     def __repr__(self):
         return (f'UnaryBlock(in_feat: {self.in_dim:d}, out_feat: {self.out_dim:d}, BN: {self.use_bn}, '
@@ -243,10 +250,13 @@ class ResnetBottleneckBlock(nn.Module):
             s_img = ops.gemm_prepare_input(shortcut) if isinstance(self.unary_shortcut, UnaryBlock) else None
         else:
             shortcut, s_img = features, f_img
+        shortcut_stats = None
         if isinstance(self.unary_shortcut, UnaryBlock):
-            shortcut = self.unary_shortcut.forward_ex(s_img, n_out, post_lengths, want_f32=True)['f32']
+            # the projected shortcut stays raw: its normalisation (no activation) happens inside unary2's apply kernel,
+            # which saves one write and one read of an [n, out_dim] tensor per block
+            shortcut, shortcut_stats = self.unary_shortcut.linear_raw(s_img, n_out)
         o = self.unary2.forward_ex(x_img, n_out, post_lengths, residual=shortcut, slope=LRELU_SLOPE, want_f32=True,
-                                   want_image=True)
+                                   want_image=True, residual_stats16=shortcut_stats)
         batch['_operand_image'] = (o['f32'], o['image'])
         return o['f32']
 

@@ -242,10 +242,13 @@ def block_stats(n_rows: int, c: int, device) -> torch.Tensor:
 
 
 def instance_norm_lrelu_ex(x, lengths, eps: float = 1e-5, slope: float = 1.0, residual=None, want_f32: bool = True,
-                           want_image: bool = False, kpconv_points=None, stats16=None, kpconv_planar: bool = False):
+                           want_image: bool = False, kpconv_points=None, stats16=None, kpconv_planar: bool = False,
+                           residual_stats16=None):
     """InstanceNorm (+ residual) + LeakyReLU with format-aware outputs.  Returns a dict with any of
     'f32' (rows), 'image' (operand image of the next tensor-core GEMM, K = c), 'kpconv' (PreparedFeatures for
-    kpconv_forward_prepared; needs kpconv_points = the [n,3] points the rows belong to)."""
+    kpconv_forward_prepared; needs kpconv_points = the [n,3] points the rows belong to).
+    residual_stats16: `residual` is a raw producer output (with these 16-row block sums) and is instance-normalised,
+    without activation, inside the same kernel before it is added (the projected shortcut of a bottleneck block)."""
     L = _lib.lib()
     xx = _f32c(x, "x")
     lens = _i32c(lengths, "stack_lengths")
@@ -262,10 +265,15 @@ def instance_norm_lrelu_ex(x, lengths, eps: float = 1e-5, slope: float = 1.0, re
         amax = torch.empty(1, dtype=torch.int32, device=xx.device)
     if stats16 is not None and tuple(stats16.shape) != ((n + 15) // 16, c, 2):
         raise RuntimeError("instance_norm_lrelu_ex: stats16 does not match x")
+    if residual_stats16 is not None and (res is None or tuple(residual_stats16.shape) != ((n + 15) // 16, c, 2)):
+        raise RuntimeError("instance_norm_lrelu_ex: residual_stats16 does not match the residual")
+    if res is not None and tuple(res.shape) != (n, c):
+        raise RuntimeError("instance_norm_lrelu_ex: residual does not match x")
     ws = _ws(L.spr_instance_norm_workspace_bytes(n, lens.shape[0], c), xx.device)
     rc = L.spr_instance_norm_lrelu_ex(xx.data_ptr(), lens.data_ptr(), n, lens.shape[0], c, float(eps), float(slope),
                                       _ptr(res), _ptr(f32), _ptr(img), A_SCALE, _ptr(x16), _ptr(pts4), _ptr(pts),
-                                      _ptr(amax), _ptr(stats16), 1 if kpconv_planar else 0, ws.data_ptr(), ws.numel(),
+                                      _ptr(amax), _ptr(stats16), _ptr(residual_stats16), 1 if kpconv_planar else 0,
+                                      ws.data_ptr(), ws.numel(),
                                       _stream())
     _lib.check(rc, "spr_instance_norm_lrelu_ex")
     if f32 is not None:

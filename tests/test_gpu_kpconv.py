@@ -247,6 +247,20 @@ def test_producer_block_statistics_feed_instance_norm(n_out, lens):
     assert (a - b).abs().max().item() <= 2e-6 * a.abs().max().item()
     with pytest.raises(RuntimeError):
         ops.instance_norm_lrelu_ex(y, _t(lens), stats16=stats[:-1])
+    # a RAW residual (another GEMM's output + its block sums) normalised inside the same apply kernel: bit-identical to
+    # normalising it in a pass of its own (the projected shortcut of a bottleneck block, kpconv_blocks.py:706-741)
+    w2 = torch.randn(n_out, k, device=DEV) / 8 - 0.02
+    stats2 = ops.block_stats(n, n_out, DEV)
+    raw = ops.gemm_tc(img, ops.weight_image(w2), None, n, ops.OUT_F32, stats16=stats2)
+    two_pass = ops.instance_norm_lrelu_ex(raw, _t(lens), slope=1.0, stats16=stats2)["f32"]
+    want = ops.instance_norm_lrelu_ex(y, _t(lens), slope=0.1, residual=two_pass, stats16=stats, want_image=True)
+    got = ops.instance_norm_lrelu_ex(y, _t(lens), slope=0.1, residual=raw, stats16=stats, want_image=True,
+                                     residual_stats16=stats2)
+    assert torch.equal(got["f32"], want["f32"])
+    w3 = ops.weight_image(torch.randn(32, n_out, device=DEV) / 8)
+    assert torch.equal(ops.gemm_tc(got["image"], w3, None, n, ops.OUT_F32), ops.gemm_tc(want["image"], w3, None, n, ops.OUT_F32))
+    with pytest.raises(RuntimeError):
+        ops.instance_norm_lrelu_ex(y, _t(lens), residual_stats16=stats2)
 
 
 @pytest.mark.parametrize("c", [32, 128])

@@ -17,13 +17,19 @@ ap.add_argument("--pairs", type=int, default=8)
 ap.add_argument("--points", type=int, default=20000)
 ap.add_argument("--top", type=int, default=32)
 ap.add_argument("--arch", default="4stage", choices=["3stage", "4stage"])
+ap.add_argument("--kind", default="3dmatch", choices=["3dmatch", "kitti", "modelnet"])
 args = ap.parse_args()
 dev = "cuda:0"
 cfg = spr.threedmatch_config() if args.arch == "3stage" else spr.threedmatch_4stage_config()
+gen_kw = dict(n_points=args.points)
+if args.kind == "kitti":
+    cfg, gen_kw = spr.kitti_config(first_subsampling_dl=0.3), dict(n_points=30000, voxel=0.3)
+elif args.kind == "modelnet":
+    cfg, gen_kw = spr.modelnet_config(), {}
 torch.manual_seed(0); np.random.seed(0)
 model = spr.RegTR(cfg).to(dev).eval()
 model.return_attn = False
-data = synthetic.make_batch("3dmatch", args.pairs, seed=2, n_points=args.points)
+data = synthetic.make_batch(args.kind, args.pairs, seed=2, **gen_kw)
 batch = {"src_xyz": [torch.from_numpy(c).to(dev) for c in data["src_xyz"]],
          "tgt_xyz": [torch.from_numpy(c).to(dev) for c in data["tgt_xyz"]]}
 for _ in range(3):

@@ -201,33 +201,6 @@ __global__ void __launch_bounds__(256)
 // of four are in flight while the current group is evaluated, and the 15 x Cout mat-vec reads W from shared memory
 // with broadcast 16-byte loads.  A group of four columns that is padding in all 32 rows of the warp is skipped.
 // ---------------------------------------------------------------------------------------------
-// Packed fp32 pairs (sm_100 add/mul/fma.f32x2: one issue slot for two lanes of the FMA pipe).  The kernel is bound by
-// instruction issue, not by the pipe: kernel points are processed two at a time.
-typedef unsigned long long f2_t;
-__device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
-  f2_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(f2_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
-  f2_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
-  f2_t r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
-  f2_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-
 template <typename IdxT, int COUT>
 __global__ void __launch_bounds__(128, 4)
     k_kpconv_cin1_t(const float* __restrict__ q, const float4* __restrict__ packed, const IdxT* __restrict__ idx,

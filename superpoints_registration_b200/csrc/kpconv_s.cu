@@ -46,7 +46,7 @@ struct SCfg {
   static constexpr int NSTAGES = 3;
   static constexpr int BLOCKS_PER_PASS = 8 * NSUB;  // 8 K atoms of 64 fp16 per pass
   static constexpr int TQ = 64;
-  static constexpr int WORKERS = 18;  // (20 warps fit the shared memory at C = 32 but cap the registers at 80: measured 5 % slower)
+  static constexpr int WORKERS = 18;  // (a 21st warp makes six on one scheduler: 16384 / 6 caps the registers at 80 and spills; measured 5 % slower)
   static constexpr int THREADS = (WORKERS + 2) * 32;
   static constexpr int A_ATOM_BYTES = 128 * 128;
   static constexpr int A_BYTES = 8 * A_ATOM_BYTES;
@@ -70,15 +70,6 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1,
   asm("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(b0));
-}
-// s * max(0, 1 - d / extent), with s / extent and s given
-__device__ __forceinline__ float influence_scaled(float cx, float cy, float cz, float kx, float ky, float kz, float s_ie,
-                                                  float s) {
-  const float dx = cx - kx, dy = cy - ky, dz = cz - kz;
-  const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-  float d;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(d2));  // MUFU.SQRT, rel. error ~2^-23, sqrt(0) = 0
-  return fmaxf(fmaf(-d, s_ie, s), 0.f);
 }
 // 16-byte asynchronous copy global -> shared through L2 (LDGSTS); src_bytes = 0 writes zeros without touching memory.
 // (Absent neighbours must NOT be redirected to a shared all-zero row instead: every SM then reads the same line for a
@@ -218,6 +209,9 @@ __global__ void __launch_bounds__(SCfg<C>::THREADS, 1)
     // row 15 of the A fragment is padding: a kernel point infinitely far away has influence exactly 0
     const float k1x = g < 7 ? sKp[3 * (g + 8)] : 1.0e18f, k1y = g < 7 ? sKp[3 * (g + 8) + 1] : 0.f,
                 k1z = g < 7 ? sKp[3 * (g + 8) + 2] : 0.f;
+    // negated and duplicated for the packed (two neighbours at a time) influence arithmetic
+    const f2_t nk0x = f2_pack(-k0x, -k0x), nk0y = f2_pack(-k0y, -k0y), nk0z = f2_pack(-k0z, -k0z);
+    const f2_t nk1x = f2_pack(-k1x, -k1x), nk1y = f2_pack(-k1y, -k1y), nk1z = f2_pack(-k1z, -k1z);
     // ---- the warp's ring of block slots ----
     const uint32_t ring = pinned(smem_u32(smem + K::OFF_STAGING + warp * (K::DEPTH * K::SLOT_BYTES)));
     const uint32_t sA32 = smem_u32(sA);
@@ -410,10 +404,30 @@ __global__ void __launch_bounds__(SCfg<C>::THREADS, 1)
             // A fragment: a0 = (k = g; h = 2t, 2t+1), a1 = (k = g+8; h = 2t, 2t+1), fp16 hi + lo.  The influences are
             // re-evaluated in every channel pass: caching the fragments of pass 0 (as kpconv_tc.cu does) was measured
             // slower here -- a fragment load one block ahead stalls longer than the 4 influences take
-            const float f00 = influence_scaled(ax, ay, az, k0x, k0y, k0z, sae, sa);
-            const float f01 = influence_scaled(bx, by, bz, k0x, k0y, k0z, sbe, sb);
-            const float f10 = influence_scaled(ax, ay, az, k1x, k1y, k1z, sae, sa);
-            const float f11 = influence_scaled(bx, by, bz, k1x, k1y, k1z, sbe, sb);
+            // two neighbours per instruction (packed fp32): s * max(0, 1 - d / extent) = max(0, s - d * (s / extent))
+            const f2_t cx = f2_pack(ax, bx), cy = f2_pack(ay, by), cz = f2_pack(az, bz);
+            const f2_t s2 = f2_pack(sa, sb), nse2 = f2_pack(-sae, -sbe);
+            float f00, f01, f10, f11;
+            {
+              const f2_t dx = f2_add(cx, nk0x), dy = f2_add(cy, nk0y), dz = f2_add(cz, nk0z);
+              float d2a, d2b, da, db;
+              f2_unpack(f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx))), d2a, d2b);
+              asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(da) : "f"(d2a));  // MUFU.SQRT, rel. error ~2^-23, sqrt(0) = 0
+              asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(db) : "f"(d2b));
+              f2_unpack(f2_fma(f2_pack(da, db), nse2, s2), f00, f01);
+              f00 = fmaxf(f00, 0.f);
+              f01 = fmaxf(f01, 0.f);
+            }
+            {
+              const f2_t dx = f2_add(cx, nk1x), dy = f2_add(cy, nk1y), dz = f2_add(cz, nk1z);
+              float d2a, d2b, da, db;
+              f2_unpack(f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx))), d2a, d2b);
+              asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(da) : "f"(d2a));
+              asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(db) : "f"(d2b));
+              f2_unpack(f2_fma(f2_pack(da, db), nse2, s2), f10, f11);
+              f10 = fmaxf(f10, 0.f);
+              f11 = fmaxf(f11, 0.f);
+            }
             const __half2 h0 = __floats2half2_rn(f00, f01), h1 = __floats2half2_rn(f10, f11);
             const float2 h0f = __half22float2(h0), h1f = __half22float2(h1);
             const uint32_t ah0 = h2_bits(h0), ah1 = h2_bits(h1);

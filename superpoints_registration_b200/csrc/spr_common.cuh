@@ -80,6 +80,34 @@ struct Carver {
 
 constexpr unsigned kFull = 0xffffffffu;
 
+// Packed fp32 pairs (sm_100 add/mul/fma.f32x2: one issue slot for two lanes of the FMA pipe).  The kernel is bound by
+// instruction issue, not by the pipe: the KPConv kernels evaluate their influences two at a time.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
+  f2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
+  f2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+  f2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+
 // Monotone map float -> uint32 so that atomicMin/atomicMax on the image order floats.
 __device__ __forceinline__ uint32_t f2ord(float f) {
   uint32_t u = __float_as_uint(f);

@@ -75,7 +75,7 @@ struct AttnTile {
 };
 
 // planes: hi and lo fp16 matrices with `ld` halves per row; q_col / k_col / v_col = first column of head 0
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
     k_attention(const __half* __restrict__ hi, const __half* __restrict__ lo, int ld, int q_col, int k_col, int v_col,
                 const AttnTile* __restrict__ tiles, float* __restrict__ out, int out_ld,
                 unsigned char* __restrict__ out_img, int img_katoms, float img_scale) {

@@ -318,6 +318,12 @@ SPR_API int spr_split_f16(const float* d_x, int rows, int cols, int ld_in, void*
 SPR_API int spr_attention_varlen(const void* d_hi, const void* d_lo, int ld, int q_col, int k_col, int v_col,
                                  int n_heads, int head_dim, const int32_t* d_tiles, int n_tiles, float* d_out,
                                  int out_ld, void* d_out_img, float img_scale, void* stream);
+/* Same operator on the tcgen05 tensor cores (csrc/attention_tc.cu): a tile holds up to 128 query rows, the scores
+ * and the per-tile P V product live in tensor memory, one soft-max thread per query row.  Same operands, same
+ * split-precision products, same outputs; out_ld must be a multiple of 4. */
+SPR_API int spr_attention_varlen_tc(const void* d_hi, const void* d_lo, int ld, int q_col, int k_col, int v_col,
+                                    int n_heads, int head_dim, const int32_t* d_tiles, int n_tiles, float* d_out,
+                                    int out_ld, void* d_out_img, float img_scale, void* stream);
 
 /* Dense layers on the tcgen05 tensor cores with fp32-level accuracy (nn.Linear of the cross-encoder:
  * in/out projections of nn.MultiheadAttention and the FFN, transformers.py:184-245):

@@ -238,6 +238,6 @@ const char* spr_last_error(void) { return spr::g_err; }
 unsigned long long spr_launch_count(void) { return spr::g_launches.load(); }
 unsigned int spr_numeric_flags(int reset) {
   return spr::gemm_numeric_flags(reset != 0) | spr::blocks_numeric_flags(reset != 0) |
-         spr::attention_numeric_flags(reset != 0);
+         spr::attention_numeric_flags(reset != 0) | spr::attention_tc_numeric_flags(reset != 0);
 }
 }

@@ -56,6 +56,7 @@ cudaError_t ensure_max_dynamic_smem(const void* func, size_t bytes);
 unsigned int gemm_numeric_flags(bool reset);
 unsigned int blocks_numeric_flags(bool reset);
 unsigned int attention_numeric_flags(bool reset);
+unsigned int attention_tc_numeric_flags(bool reset);
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -690,8 +690,17 @@ def split_f16(x: torch.Tensor, n_scaled: int = 0, scale: float = 1.0):
     return hi, lo
 
 
-def attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q: int = 64) -> torch.Tensor:
-    """Tile list of spr_attention_varlen: one row {first query row, rows, first key row, key rows} per 64 queries."""
+def attention_generation() -> int:
+    """2 (default): csrc/attention_tc.cu -- tcgen05 products, scores in tensor memory, tiles of up to 128 queries;
+    1 (SPR_ATTENTION_GEN=1): csrc/attention.cu -- the warp-level tensor path of round 1, tiles of up to 64 queries."""
+    return 1 if os.environ.get("SPR_ATTENTION_GEN", "2") == "1" else 2
+
+
+def attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q: Optional[int] = None) -> torch.Tensor:
+    """Tile list of spr_attention_varlen(_tc): one row {first query row, rows, first key row, key rows} per block_q
+    queries (default: the tile height of the selected kernel generation)."""
+    if block_q is None:
+        block_q = 128 if attention_generation() == 2 else 64
     key = ("tiles", tuple(q_offsets), tuple(q_lens), tuple(kv_offsets), tuple(kv_lens), str(device), block_q)
     return _memo(key, lambda: _attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q))
 
@@ -709,9 +718,11 @@ def _attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q):
 
 
 def attention_varlen(hi: torch.Tensor, lo: torch.Tensor, tiles: torch.Tensor, n_heads: int, q_col: int, k_col: int,
-                     v_col: int, d_model: int, out_image: Optional[torch.Tensor] = None, image_scale: float = 1.0):
+                     v_col: int, d_model: int, out_image: Optional[torch.Tensor] = None, image_scale: float = 1.0,
+                     generation: Optional[int] = None):
     """Multi-head attention over packed tokens; hi/lo are the fp16 planes of the (pre-scaled) QKV projection.
-    With out_image the result is written as the A image of the output projection (gemm_tc) instead of fp32 rows."""
+    With out_image the result is written as the A image of the output projection (gemm_tc) instead of fp32 rows.
+    `tiles` must have been built for the kernel generation that runs (attention_tiles: 128 / 64 query rows)."""
     L = _lib.lib()
     _need_cuda(hi, "hi")
     if hi.dtype != torch.float16 or lo.dtype != torch.float16 or hi.shape != lo.shape or not hi.is_contiguous() \
@@ -720,10 +731,11 @@ def attention_varlen(hi: torch.Tensor, lo: torch.Tensor, tiles: torch.Tensor, n_
     rows, ld = hi.shape
     head_dim = d_model // n_heads
     out = None if out_image is not None else torch.empty((rows, d_model), dtype=torch.float32, device=hi.device)
-    rc = L.spr_attention_varlen(hi.data_ptr(), lo.data_ptr(), ld, q_col, k_col, v_col, n_heads, head_dim,
-                                tiles.data_ptr(), tiles.shape[0], _ptr(out), d_model, _ptr(out_image),
-                                float(image_scale), _stream())
-    _lib.check(rc, "spr_attention_varlen")
+    gen = attention_generation() if generation is None else generation
+    fn = L.spr_attention_varlen_tc if gen == 2 else L.spr_attention_varlen
+    rc = fn(hi.data_ptr(), lo.data_ptr(), ld, q_col, k_col, v_col, n_heads, head_dim, tiles.data_ptr(), tiles.shape[0],
+            _ptr(out), d_model, _ptr(out_image), float(image_scale), _stream())
+    _lib.check(rc, "spr_attention_varlen_tc" if gen == 2 else "spr_attention_varlen")
     return out_image if out is None else out
 
 

@@ -28,8 +28,10 @@ def _ref_attention(qkv, tiles_spec, n_heads, d):
     return out
 
 
+@pytest.mark.parametrize("generation", [2, 1])
 @pytest.mark.parametrize("lens", [[5, 64, 65, 130], [1, 1], [700, 333, 128, 257, 64, 63]])
-def test_attention_varlen_against_fp64(lens):
+def test_attention_varlen_against_fp64(lens, generation):
+    """generation 2 = tcgen05 kernel (attention_tc.cu, 128-query tiles), 1 = warp-level kernel (attention.cu)."""
     torch.manual_seed(len(lens))
     d, nh = 256, 8
     T = sum(lens)
@@ -40,13 +42,23 @@ def test_attention_varlen_against_fp64(lens):
     for kind in ("self", "cross"):
         ko = offs[:-1] if kind == "self" else [offs[p] for p in partner]
         kn = lens if kind == "self" else [lens[p] for p in partner]
-        tiles = ops.attention_tiles(offs[:-1], lens, ko, kn, DEV)
+        tiles = ops.attention_tiles(offs[:-1], lens, ko, kn, DEV, block_q=128 if generation == 2 else 64)
         hi, lo = ops.split_f16(qkv, n_scaled=d, scale=math.log2(math.e) / math.sqrt(d // nh))
-        out = ops.attention_varlen(hi, lo, tiles, nh, 0, d, 2 * d, d).cpu().double()
+        out = ops.attention_varlen(hi, lo, tiles, nh, 0, d, 2 * d, d, generation=generation).cpu().double()
         ref = _ref_attention(qkv, list(zip(offs[:-1], lens, ko, kn)), nh, d)
         err = (out - ref).abs().max().item()
+        print(f"gen {generation} {kind}: max err {err:.2e} = {err / ref.abs().max().item():.2e} x max|out|")
         # logits reach +-16 here: 22-bit operand products leave ~|S| * 2^-22 relative error on P, the same order as fp32
         assert err <= 6e-6 * ref.abs().max().item(), (kind, err, ref.abs().max().item())
+        # the operand-image output (what the fused encoder layer consumes) through the output projection's GEMM
+        img = ops.gemm_a_image(T, d, DEV)
+        ops.attention_varlen(hi, lo, tiles, nh, 0, d, 2 * d, d, out_image=img, image_scale=ops.A_SCALE,
+                             generation=generation)
+        eye = ops.weight_image(torch.eye(d, device=DEV))
+        back = ops.gemm_tc(img, eye, None, T).cpu().double()
+        assert (back - ref).abs().max().item() <= 6e-6 * ref.abs().max().item()
+        again = ops.attention_varlen(hi, lo, tiles, nh, 0, d, 2 * d, d, generation=generation).cpu().double()
+        assert torch.equal(out, again)   # deterministic
 
 
 def test_split_f16_reconstructs_fp32():

@@ -8,8 +8,11 @@
 // issued by one thread, the scores and the per-tile P V product live in TMEM, and the four soft-max warps own one query
 // row per thread (one TMEM lane: no shuffles, no shared-memory reductions).
 //
-//   CTA = (tile of <= 128 queries, head); warps 0-3 soft-max (TMEM lane quadrant w), warp 4 loads key / value tiles
-//   (16-byte cp.async, mbarrier completion), warp 5 issues the MMAs.
+//   CTA = (tile of <= 128 queries, head); warps 0-7 soft-max (TMEM lane quadrant w % 4, key columns / output channels
+//   half w / 4: a query row is shared by two threads that exchange their partial row maximum through shared memory),
+//   warp 8 loads key / value tiles (16-byte cp.async, mbarrier completion), warp 9 issues the MMAs.
+//   (The first version had one thread per row: 925 instructions per warp and tile in long dependent chains, two such
+//   warps per scheduler -- 27 % issue utilisation.  Half rows, packed fp32 arithmetic and twice the warps halved it.)
 //   shared memory (SWIZZLE_128B, 128-byte rows):
 //     Q  [128 rows]: row = [Q_hi (32 halves) | Q_lo (32)]                        A operand of the score product, K-major
 //     K  [64 rows] x 3 stages: row = [K_hi | K_lo]                               B operand, K-major
@@ -44,8 +47,10 @@ constexpr int OFF_P = Q_BYTES;
 constexpr int OFF_K = OFF_P + 2 * P_ATOM;
 constexpr int OFF_V = OFF_K + NSTAGE * KV_BYTES;
 constexpr int OFF_BAR = OFF_V + NSTAGE * KV_BYTES;
-constexpr size_t ATTN_SMEM = 1024 + OFF_BAR + 256;
-constexpr int ATTN_THREADS = 192;
+constexpr int OFF_MAX = OFF_BAR + 256;             // [2 tiles][2 halves][128 rows] partial row maxima
+constexpr size_t ATTN_SMEM = 1024 + OFF_MAX + 2 * 2 * BQ * 4;
+constexpr int SM_WARPS = 8;
+constexpr int ATTN_THREADS = (SM_WARPS + 2) * 32;
 constexpr uint32_t TMEM_COLS = 256;  // S0 @ 0, S1 @ 64, D @ 128; two CTAs per SM share the 512 columns
 static_assert(2 * ATTN_SMEM <= 227 * 1024, "two CTAs per SM");
 
@@ -87,6 +92,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -110,6 +132,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
   uint64_t* s_full = bars + 8;     // [2] tcgen05.commit
   uint64_t* s_empty = bars + 10;   // [2] one arrival per soft-max warp
   uint64_t* p_full = bars + 12;    // one arrival per soft-max warp
+  float* s_max = reinterpret_cast<float*>(smem + OFF_MAX);
   uint64_t* pv_done = bars + 13;   // tcgen05.commit
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
   const AttnTile tl = tiles[blockIdx.x];
@@ -125,13 +148,13 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+      mbar_init(&s_empty[i], SM_WARPS);
     }
-    mbar_init(p_full, 4);
+    mbar_init(p_full, SM_WARPS);
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(s_tmem, TMEM_COLS);
+  if (warp == SM_WARPS + 1) tmem_alloc(s_tmem, TMEM_COLS);
   // Q tile: 128 rows x 8 chunks (4 hi, 4 lo); rows past the end of the segment are zero
   for (int i = tid; i < BQ * 8; i += ATTN_THREADS) {
     const int r = i >> 3, c = i & 7;
@@ -146,101 +169,133 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  if (warp < 4) {
+  if (warp < SM_WARPS) {
     // ============================================ soft-max ============================================
-    const int row = warp * 32 + lane;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    float o[HD];
+    // thread = (query row, half): key columns 32 hf .. 32 hf + 31 of every tile, output channels 16 hf .. 16 hf + 15
+    const int quad = warp & 3, hf = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
+    f2_t o2[8];  // (o[2i], o[2i+1]) of this thread's 16 channels
 #pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+    for (int d = 0; d < 8; ++d) o2[d] = 0ull;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       const int sb = j & 1;
-      mbar_wait_park(&s_full[sb], (j >> 1) & 1);
+      mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
-      float s[BK];
-      {
-        float a[32], b[32];
-        tmem_ld32(trow + sb * 64, a);
-        tmem_ld32(trow + sb * 64 + 32, b);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          s[i] = a[i];
-          s[32 + i] = b[i];
-        }
-      }
+      float s[32];
+      tmem_ld32(trow + sb * 64 + hf * 32, s);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);  // the score buffer may take tile j + 2
-      const int valid = tl.kv_len - j * BK;      // columns >= valid are past the end of the segment
-      if (valid < BK) {
+      const int valid = tl.kv_len - j * BK - hf * 32;  // columns >= valid are past the end of the segment
+      if (valid < 32) {
 #pragma unroll
-        for (int i = 0; i < BK; ++i)
+        for (int i = 0; i < 32; ++i)
           if (i >= valid) s[i] = -INFINITY;
       }
-      float mx = m;
+      // row maximum: this half, then the partner's through shared memory
+      float mh[4];
 #pragma unroll
-      for (int i = 0; i < BK; ++i) mx = fmaxf(mx, s[i]);
+      for (int u = 0; u < 4; ++u) mh[u] = max3(s[8 * u], s[8 * u + 1], s[8 * u + 2]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mh[u] = max3(mh[u], s[8 * u + 3], s[8 * u + 4]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mh[u] = max3(mh[u], s[8 * u + 5], s[8 * u + 6]);
+      const float mine = fmaxf(max3(mh[0], mh[1], s[7]), max3(mh[2], mh[3], fmaxf(fmaxf(s[15], s[23]), s[31])));
+      float* mx_buf = s_max + sb * (2 * BQ);
+      mx_buf[hf * BQ + row] = mine;
+      pair_barrier(1 + quad);
+      const float mx = max3(m, mine, mx_buf[(hf ^ 1) * BQ + row]);  // (never -inf: column 0 of tile 0 is valid)
       const float alpha = ex2(m - mx);  // first tile: exp2(-inf) = 0
       m = mx;
-      float rs = 0.f;
+      const f2_t nmx = f2_pack(-mx, -mx);
+      f2_t rs0 = 0ull, rs1 = 0ull;
 #pragma unroll
-      for (int i = 0; i < BK; ++i) {
-        s[i] = ex2(s[i] - mx);
-        rs += s[i];
+      for (int i = 0; i < 16; i += 2) {
+        float a0, a1, b0, b1;
+        f2_unpack(f2_add(f2_pack(s[2 * i], s[2 * i + 1]), nmx), a0, a1);
+        f2_unpack(f2_add(f2_pack(s[2 * i + 2], s[2 * i + 3]), nmx), b0, b1);
+        s[2 * i] = ex2(a0);
+        s[2 * i + 1] = ex2(a1);
+        s[2 * i + 2] = ex2(b0);
+        s[2 * i + 3] = ex2(b1);
+        rs0 = f2_add(rs0, f2_pack(s[2 * i], s[2 * i + 1]));
+        rs1 = f2_add(rs1, f2_pack(s[2 * i + 2], s[2 * i + 3]));
       }
-      l = l * alpha + rs;
+      {
+        float r0, r1;
+        f2_unpack(f2_add(rs0, rs1), r0, r1);
+        l = fmaf(l, alpha, r0 + r1);
+      }
       // the P tile and the D accumulator are free once the previous tile's P V product has completed
       if (j > 0) {
-        mbar_wait_park(pv_done, (j - 1) & 1);
+        mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
       }
-      // P tile: chunk c = keys 8c .. 8c+7 of this row, hi atom and lo atom
+      // P tile: chunk c = keys 32 hf + 8 c .. + 7 of this row, hi atom and lo atom
+      const f2_t neg1 = f2_pack(-1.f, -1.f);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t ph[4], pl[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float v0 = s[8 * c + 2 * e], v1 = s[8 * c + 2 * e + 1];
           const __half2 hh = __floats2half2_rn(v0, v1);
-          const float2 hf = __half22float2(hh);
+          const float2 hf2 = __half22float2(hh);
+          float l0, l1;
+          f2_unpack(f2_fma(f2_pack(hf2.x, hf2.y), neg1, f2_pack(v0, v1)), l0, l1);  // v - hi, exact
           ph[e] = h2u(hh);
-          pl[e] = h2u(__floats2half2_rn(v0 - hf.x, v1 - hf.y));
+          pl[e] = h2u(__floats2half2_rn(l0, l1));
         }
-        const uint32_t off = sw128_offset(row, c);
+        const uint32_t off = sw128_offset(row, 4 * hf + c);
         sts128(sP + off, ph[0], ph[1], ph[2], ph[3]);
         sts128(sP + P_ATOM + off, pl[0], pl[1], pl[2], pl[3]);
       }
       if (j > 0) {  // O += D of the previous tile (relative to the previous maximum), then rescale to the new one
-        float a[32], b[32];
-        tmem_ld32(trow + 128, a);
-        tmem_ld32(trow + 160, b);
+        float a[16], b[16];
+        tmem_ld16(trow + 128 + hf * 16, a);
+        tmem_ld16(trow + 160 + hf * 16, b);
+        const f2_t al2 = f2_pack(alpha, alpha);
 #pragma unroll
-        for (int d = 0; d < HD; ++d) o[d] = (o[d] + (a[d] + b[d])) * alpha;
+        for (int d = 0; d < 8; ++d)
+          o2[d] = f2_mul(f2_add(o2[d], f2_add(f2_pack(a[2 * d], a[2 * d + 1]), f2_pack(b[2 * d], b[2 * d + 1]))), al2);
         tc_fence_before();
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
+    // the two halves of a row have summed different keys: exchange the partial sums
+    float* l_buf = s_max + (n_kv & 1) * (2 * BQ);  // (the buffer the last tile did not use)
+    l_buf[hf * BQ + row] = l;
+    pair_barrier(1 + quad);
+    l += l_buf[(hf ^ 1) * BQ + row];
     // last tile's product, normalisation, store
-    mbar_wait_park(pv_done, (n_kv - 1) & 1);
+    mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
+    float o[16];
     {
-      float a[32], b[32];
-      tmem_ld32(trow + 128, a);
-      tmem_ld32(trow + 160, b);
+      float a[16], b[16];
+      tmem_ld16(trow + 128 + hf * 16, a);
+      tmem_ld16(trow + 160 + hf * 16, b);
       const float inv = 1.f / l;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) o[d] = (o[d] + (a[d] + b[d])) * inv;
+      for (int d = 0; d < 8; ++d) {
+        float x0, x1;
+        f2_unpack(o2[d], x0, x1);
+        o[2 * d] = (x0 + (a[2 * d] + b[2 * d])) * inv;
+        o[2 * d + 1] = (x1 + (a[2 * d + 1] + b[2 * d + 1])) * inv;
+      }
     }
     tc_fence_before();
     if (row < tl.q_rows) {
       const int token = tl.q_row0 + row;
+      const int c0 = head * HD + 16 * hf;  // first output column of this thread
       if (out) {
-        float4* dst = reinterpret_cast<float4*>(out + (size_t)token * out_ld + head * HD);
+        float4* dst = reinterpret_cast<float4*>(out + (size_t)token * out_ld + c0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
       }
       if (out_img) {
         // A image of the output projection (gemm_tc.cu): token -> tile token / 64, stacked rows 2r (hi), 2r + 1 (lo);
@@ -248,17 +303,17 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
         float amax16 = 0.f;
         const uint32_t r2 = 2 * (token & 63);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = head * HD + 8 * i;
+        for (int i = 0; i < 2; ++i) {
+          const int c = c0 + 8 * i;
           uint32_t ph[4], pl[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float v0 = o[8 * i + 2 * e] * img_scale, v1 = o[8 * i + 2 * e + 1] * img_scale;
             amax16 = fmaxf(amax16, fmaxf(fabsf(v0), fabsf(v1)));
             const __half2 hh = __floats2half2_rn(v0, v1);
-            const float2 hf = __half22float2(hh);
+            const float2 hf2 = __half22float2(hh);
             ph[e] = h2u(hh);
-            pl[e] = h2u(__floats2half2_rn(v0 - hf.x, v1 - hf.y));
+            pl[e] = h2u(__floats2half2_rn(v0 - hf2.x, v1 - hf2.y));
           }
           unsigned char* blk = out_img + ((size_t)(token >> 6) * img_katoms + (c >> 6)) * 16384;
           const uint32_t chunk = (c & 63) >> 3;
@@ -268,19 +323,45 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
         if (!(amax16 <= 65504.f)) atomicOr(&g_attention_tc_flags, SPR_FLAG_FP16_OVERFLOW);  // false for NaN as well
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == SM_WARPS) {
     // ============================================ key / value loader ============================================
+    // ONE warp feeds the CTA: everything that does not change from copy to copy is a per-lane constant (the first
+    // version recomputed row, chunk, plane and swizzle per copy -- ~800 dependent instructions per tile, and the
+    // whole CTA ran at the speed of this warp).  Lane -> 16-byte chunk c = lane % 8 (0-3 hi plane, 4-7 lo plane) of rows
+    // lane / 8 + 4 it, it = 0..15; rows r and r + 4 differ in their swizzle phase, rows r and r + 8 by 1024 bytes.
+    const int c = lane & 7, r0 = lane >> 3;
+    const __half* plane = (c & 4) ? lo : hi;
+    const size_t col = (size_t)head * HD + (c & 3) * 8;
+    const __half* kbase = plane + (size_t)tl.kv_row0 * ld + k_col + col;
+    const __half* vbase = plane + (size_t)tl.kv_row0 * ld + v_col + col;
+    const uint32_t off_e = r0 * 128 + ((c ^ r0) << 4), off_o = (r0 + 4) * 128 + ((c ^ (r0 + 4)) << 4);
+    const size_t step = (size_t)4 * ld;
     for (int j = 0; j < n_kv; ++j) {
       const int st = j % NSTAGE;
       mbar_wait_park(&kv_empty[st], ((j / NSTAGE) & 1) ^ 1);
-#pragma unroll 8
-      for (int i = lane; i < 2 * BK * 8; i += 32) {
-        const int which = i >> 9, r = (i >> 3) & 63, c = i & 7;
-        const int kv = j * BK + r;
-        const bool ok = kv < tl.kv_len;
-        const __half* src = ((c & 4) ? lo : hi) + (size_t)(tl.kv_row0 + (ok ? kv : 0)) * ld + (which ? v_col : k_col) +
-                            head * HD + (c & 3) * 8;
-        cp_async16((which ? sV : sK) + st * KV_BYTES + sw128_offset(r, c), src, ok ? 16u : 0u);
+      const int kv0 = j * BK + r0;
+      const uint32_t dK = sK + st * KV_BYTES, dV = sV + st * KV_BYTES;
+      if (kv0 + 60 < tl.kv_len) {  // every row of this lane exists
+        const __half* ks = kbase + (size_t)kv0 * ld;
+        const __half* vs = vbase + (size_t)kv0 * ld;
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const uint32_t d = ((it & 1) ? off_o : off_e) + (it >> 1) * 1024;
+          cp_async16(dK + d, ks, 16u);
+          cp_async16(dV + d, vs, 16u);
+          ks += step;
+          vs += step;
+        }
+      } else {  // the segment's last tile: rows past its end are zero-filled
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+          const uint32_t d = ((it & 1) ? off_o : off_e) + (it >> 1) * 1024;
+          const int kv = kv0 + 4 * it;
+          const bool ok = kv < tl.kv_len;
+          const size_t ro = (size_t)(ok ? kv : 0) * ld;
+          cp_async16(dK + d, kbase + ro, ok ? 16u : 0u);
+          cp_async16(dV + d, vbase + ro, ok ? 16u : 0u);
+        }
       }
       cp_async_arrive_noinc(&kv_full[st]);
     }
@@ -309,7 +390,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
       for (int j = 0; j < n_kv; ++j) {
         if (j + 1 < n_kv) issue_s(j + 1);
         const int st = j % NSTAGE;
-        mbar_wait_park(p_full, j & 1);
+        mbar_wait(p_full, j & 1);  // (spinning: the soft-max -> P V -> soft-max hand-over is the critical loop)
         tc_fence_after();
         const uint32_t vt = sV + st * KV_BYTES;
 #pragma unroll
@@ -326,7 +407,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == SM_WARPS + 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 }  // namespace

@@ -23,7 +23,8 @@
 //   (P_hi, P_lo) x [V_hi | V_lo] with N = 64: columns 0-31 + columns 32-63 of D are the tile's contribution to O
 //   (the P_lo V_lo term is noise far below fp32 rounding).
 //   Soft-max thread, per tile j:  S_j -> running maximum m_j, p = exp2(s - m_j) (Q arrives pre-scaled by
-//   log2(e)/sqrt(32)), (hi, lo) split of p into the P tile;  O += D_(j-1);  O *= exp2(m_(j-1) - m_j).
+//   log2(e)/sqrt(32)), (hi, lo) split of p into the P tile;  O += D_(j-1);  O *= exp2(m_(j-1) - m_j).  D alternates
+//   between two TMEM buffers, so the read-back of D_(j-1) runs while P_j V_j is being multiplied.
 //   The MMA thread issues S_(j+1) before it waits for P_j, so the score product of the next tile and the P V product of
 //   the previous one overlap the soft-max of the current one (two score buffers in TMEM).
 #include "spr_common.cuh"
@@ -51,7 +52,7 @@ constexpr int OFF_MAX = OFF_BAR + 256;             // [2 tiles][2 halves][128 ro
 constexpr size_t ATTN_SMEM = 1024 + OFF_MAX + 2 * 2 * BQ * 4;
 constexpr int SM_WARPS = 8;
 constexpr int ATTN_THREADS = (SM_WARPS + 2) * 32;
-constexpr uint32_t TMEM_COLS = 256;  // S0 @ 0, S1 @ 64, D @ 128; two CTAs per SM share the 512 columns
+constexpr uint32_t TMEM_COLS = 256;  // S0 @ 0, S1 @ 64, D0 @ 128, D1 @ 192; two CTAs per SM share the 512 columns
 static_assert(2 * ATTN_SMEM <= 227 * 1024, "two CTAs per SM");
 
 __device__ unsigned int g_attention_tc_flags;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       const int sb = j & 1;
-      mbar_wait(&s_full[sb], (j >> 1) & 1);
+      mbar_wait_park(&s_full[sb], (j >> 1) & 1, 2000u);
       tc_fence_after();
       float s[32];
       tmem_ld32(trow + sb * 64 + hf * 32, s);
@@ -228,43 +229,43 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
         f2_unpack(f2_add(rs0, rs1), r0, r1);
         l = fmaf(l, alpha, r0 + r1);
       }
-      // the P tile and the D accumulator are free once the previous tile's P V product has completed
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);
-        tc_fence_after();
-      }
-      // P tile: chunk c = keys 32 hf + 8 c .. + 7 of this row, hi atom and lo atom
+      // (hi, lo) split of this thread's 32 probabilities: registers only, BEFORE the wait for the P tile
       const f2_t neg1 = f2_pack(-1.f, -1.f);
+      uint32_t ph[16], pl[16];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t ph[4], pl[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float v0 = s[8 * c + 2 * e], v1 = s[8 * c + 2 * e + 1];
-          const __half2 hh = __floats2half2_rn(v0, v1);
-          const float2 hf2 = __half22float2(hh);
-          float l0, l1;
-          f2_unpack(f2_fma(f2_pack(hf2.x, hf2.y), neg1, f2_pack(v0, v1)), l0, l1);  // v - hi, exact
-          ph[e] = h2u(hh);
-          pl[e] = h2u(__floats2half2_rn(l0, l1));
-        }
-        const uint32_t off = sw128_offset(row, 4 * hf + c);
-        sts128(sP + off, ph[0], ph[1], ph[2], ph[3]);
-        sts128(sP + P_ATOM + off, pl[0], pl[1], pl[2], pl[3]);
+      for (int e = 0; e < 16; ++e) {
+        const float v0 = s[2 * e], v1 = s[2 * e + 1];
+        const __half2 hh = __floats2half2_rn(v0, v1);
+        const float2 hf2 = __half22float2(hh);
+        float l0, l1;
+        f2_unpack(f2_fma(f2_pack(hf2.x, hf2.y), neg1, f2_pack(v0, v1)), l0, l1);  // v - hi, exact
+        ph[e] = h2u(hh);
+        pl[e] = h2u(__floats2half2_rn(l0, l1));
       }
-      if (j > 0) {  // O += D of the previous tile (relative to the previous maximum), then rescale to the new one
+      // the P tile is free once the previous tile's P V product has completed.  From here to the arrival on p_full
+      // is the critical hand-over (soft-max -> P V -> soft-max): eight stores and a fence, nothing else
+      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {  // chunk = keys 32 hf + 8 c .. + 7 of this row, hi atom and lo atom
+        const uint32_t off = sw128_offset(row, 4 * hf + c);
+        sts128(sP + off, ph[4 * c], ph[4 * c + 1], ph[4 * c + 2], ph[4 * c + 3]);
+        sts128(sP + P_ATOM + off, pl[4 * c], pl[4 * c + 1], pl[4 * c + 2], pl[4 * c + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (j > 0) {  // O += D of the previous tile (its own TMEM buffer; relative to the previous maximum), then rescale
+        tc_fence_after();
         float a[16], b[16];
-        tmem_ld16(trow + 128 + hf * 16, a);
-        tmem_ld16(trow + 160 + hf * 16, b);
+        const uint32_t dcol = 128 + ((j - 1) & 1) * 64 + hf * 16;
+        tmem_ld16(trow + dcol, a);
+        tmem_ld16(trow + dcol + 32, b);
         const f2_t al2 = f2_pack(alpha, alpha);
 #pragma unroll
         for (int d = 0; d < 8; ++d)
           o2[d] = f2_mul(f2_add(o2[d], f2_add(f2_pack(a[2 * d], a[2 * d + 1]), f2_pack(b[2 * d], b[2 * d + 1]))), al2);
         tc_fence_before();
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
     }
     // the two halves of a row have summed different keys: exchange the partial sums
     float* l_buf = s_max + (n_kv & 1) * (2 * BQ);  // (the buffer the last tile did not use)
@@ -277,8 +278,9 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
     float o[16];
     {
       float a[16], b[16];
-      tmem_ld16(trow + 128 + hf * 16, a);
-      tmem_ld16(trow + 160 + hf * 16, b);
+      const uint32_t dcol = 128 + ((n_kv - 1) & 1) * 64 + hf * 16;
+      tmem_ld16(trow + dcol, a);
+      tmem_ld16(trow + dcol + 32, b);
       const float inv = 1.f / l;
 #pragma unroll
       for (int d = 0; d < 8; ++d) {
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
         for (int part = 0; part < 2; ++part)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma_f16(tmem + 128, desc_sw128_kmajor(sP + part * P_ATOM + ks * 32), desc_sw128_mnmajor(vt + ks * 2048),
+            umma_f16(tmem + 128 + (j & 1) * 64, desc_sw128_kmajor(sP + part * P_ATOM + ks * 32), desc_sw128_mnmajor(vt + ks * 2048),
                      idesc_pv, (part | ks) != 0);
         umma_commit(pv_done);
         umma_commit(&kv_empty[st]);

@@ -13,6 +13,8 @@
 //   warp 8 loads key / value tiles (16-byte cp.async, mbarrier completion), warp 9 issues the MMAs.
 //   (The first version had one thread per row: 925 instructions per warp and tile in long dependent chains, two such
 //   warps per scheduler -- 27 % issue utilisation.  Half rows, packed fp32 arithmetic and twice the warps halved it.)
+//   NPART = 4 (a quarter row per thread, 16 soft-max warps, 56 registers) was measured too: 7-15 % SLOWER than NPART = 2
+//   at all three bench shapes -- the per-tile fixed cost (barriers, exchange, TMEM loads) is paid by twice the warps.
 //   shared memory (SWIZZLE_128B, 128-byte rows):
 //     Q  [128 rows]: row = [Q_hi (32 halves) | Q_lo (32)]                        A operand of the score product, K-major
 //     K  [64 rows] x 3 stages: row = [K_hi | K_lo]                               B operand, K-major
@@ -48,9 +50,15 @@ constexpr int OFF_P = Q_BYTES;
 constexpr int OFF_K = OFF_P + 2 * P_ATOM;
 constexpr int OFF_V = OFF_K + NSTAGE * KV_BYTES;
 constexpr int OFF_BAR = OFF_V + NSTAGE * KV_BYTES;
-constexpr int OFF_MAX = OFF_BAR + 256;             // [2 tiles][2 halves][128 rows] partial row maxima
-constexpr size_t ATTN_SMEM = 1024 + OFF_MAX + 2 * 2 * BQ * 4;
-constexpr int SM_WARPS = 8;
+#ifndef SPR_ATTN_NPART
+#define SPR_ATTN_NPART 2
+#endif
+constexpr int NPART = SPR_ATTN_NPART;             // threads per query row (2 or 4)
+constexpr int PCOLS = BK / NPART;                 // key columns of a tile per thread
+constexpr int PCH = HD / NPART;                   // output channels per thread
+constexpr int OFF_MAX = OFF_BAR + 256;             // [2 tiles][NPART][128 rows] partial row maxima
+constexpr size_t ATTN_SMEM = 1024 + OFF_MAX + 2 * NPART * BQ * 4;
+constexpr int SM_WARPS = 4 * NPART;
 constexpr int ATTN_THREADS = (SM_WARPS + 2) * 32;
 constexpr uint32_t TMEM_COLS = 256;  // S0 @ 0, S1 @ 64, D0 @ 128, D1 @ 192; two CTAs per SM share the 512 columns
 static_assert(2 * ATTN_SMEM <= 227 * 1024, "two CTAs per SM");
@@ -104,12 +112,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8w(uint32_t taddr, float (&v)[8]) {
+  tmem_ld8(taddr, v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_ldn<32>(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ldn<16>(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ldn<8>(uint32_t taddr, float (&v)[8]) { tmem_ld8w(taddr, v); }
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+// named barrier of the NPART warps that share a TMEM lane quadrant
+__device__ __forceinline__ void row_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(32 * NPART) : "memory"); }
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -172,48 +193,50 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
 
   if (warp < SM_WARPS) {
     // ============================================ soft-max ============================================
-    // thread = (query row, half): key columns 32 hf .. 32 hf + 31 of every tile, output channels 16 hf .. 16 hf + 15
-    const int quad = warp & 3, hf = warp >> 2;
+    // thread = (query row, part): key columns PCOLS * part .. of every tile, output channels PCH * part ..
+    const int quad = warp & 3, part = warp >> 2;
     const int row = quad * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
-    f2_t o2[8];  // (o[2i], o[2i+1]) of this thread's 16 channels
+    f2_t o2[PCH / 2];  // (o[2i], o[2i+1]) of this thread's channels
 #pragma unroll
-    for (int d = 0; d < 8; ++d) o2[d] = 0ull;
+    for (int d = 0; d < PCH / 2; ++d) o2[d] = 0ull;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       const int sb = j & 1;
       mbar_wait_park(&s_full[sb], (j >> 1) & 1, 2000u);
       tc_fence_after();
-      float s[32];
-      tmem_ld32(trow + sb * 64 + hf * 32, s);
+      float s[PCOLS];
+      tmem_ldn<PCOLS>(trow + sb * 64 + part * PCOLS, s);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);  // the score buffer may take tile j + 2
-      const int valid = tl.kv_len - j * BK - hf * 32;  // columns >= valid are past the end of the segment
-      if (valid < 32) {
+      const int valid = tl.kv_len - j * BK - part * PCOLS;  // columns >= valid are past the end of the segment
+      if (valid < PCOLS) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
+        for (int i = 0; i < PCOLS; ++i)
           if (i >= valid) s[i] = -INFINITY;
       }
-      // row maximum: this half, then the partner's through shared memory
+      // row maximum: this thread's columns, then the other parts' through shared memory
       float mh[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) mh[u] = max3(s[8 * u], s[8 * u + 1], s[8 * u + 2]);
+      for (int u = 0; u < 4; ++u) mh[u] = fmaxf(s[u], s[u + 4]);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) mh[u] = max3(mh[u], s[8 * u + 3], s[8 * u + 4]);
+      for (int i = 8; i < PCOLS; i += 8)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) mh[u] = max3(mh[u], s[8 * u + 5], s[8 * u + 6]);
-      const float mine = fmaxf(max3(mh[0], mh[1], s[7]), max3(mh[2], mh[3], fmaxf(fmaxf(s[15], s[23]), s[31])));
-      float* mx_buf = s_max + sb * (2 * BQ);
-      mx_buf[hf * BQ + row] = mine;
-      pair_barrier(1 + quad);
-      const float mx = max3(m, mine, mx_buf[(hf ^ 1) * BQ + row]);  // (never -inf: column 0 of tile 0 is valid)
+        for (int u = 0; u < 4; ++u) mh[u] = max3(mh[u], s[i + u], s[i + u + 4]);
+      const float mine = fmaxf(fmaxf(mh[0], mh[1]), fmaxf(mh[2], mh[3]));
+      float* mx_buf = s_max + sb * (NPART * BQ);
+      mx_buf[part * BQ + row] = mine;
+      row_barrier(1 + quad);
+      float mx = fmaxf(m, mine);  // (never -inf: column 0 of tile 0 is valid)
+#pragma unroll
+      for (int o = 1; o < NPART; ++o) mx = fmaxf(mx, mx_buf[((part + o) % NPART) * BQ + row]);
       const float alpha = ex2(m - mx);  // first tile: exp2(-inf) = 0
       m = mx;
       const f2_t nmx = f2_pack(-mx, -mx);
       f2_t rs0 = 0ull, rs1 = 0ull;
 #pragma unroll
-      for (int i = 0; i < 16; i += 2) {
+      for (int i = 0; i < PCOLS / 2; i += 2) {
         float a0, a1, b0, b1;
         f2_unpack(f2_add(f2_pack(s[2 * i], s[2 * i + 1]), nmx), a0, a1);
         f2_unpack(f2_add(f2_pack(s[2 * i + 2], s[2 * i + 3]), nmx), b0, b1);
@@ -229,11 +252,11 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
         f2_unpack(f2_add(rs0, rs1), r0, r1);
         l = fmaf(l, alpha, r0 + r1);
       }
-      // (hi, lo) split of this thread's 32 probabilities: registers only, BEFORE the wait for the P tile
+      // (hi, lo) split of this thread's probabilities: registers only, BEFORE the wait for the P tile
       const f2_t neg1 = f2_pack(-1.f, -1.f);
-      uint32_t ph[16], pl[16];
+      uint32_t ph[PCOLS / 2], pl[PCOLS / 2];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
+      for (int e = 0; e < PCOLS / 2; ++e) {
         const float v0 = s[2 * e], v1 = s[2 * e + 1];
         const __half2 hh = __floats2half2_rn(v0, v1);
         const float2 hf2 = __half22float2(hh);
@@ -243,11 +266,11 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
         pl[e] = h2u(__floats2half2_rn(l0, l1));
       }
       // the P tile is free once the previous tile's P V product has completed.  From here to the arrival on p_full
-      // is the critical hand-over (soft-max -> P V -> soft-max): eight stores and a fence, nothing else
+      // is the critical hand-over (soft-max -> P V -> soft-max): a few stores and a fence, nothing else
       if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {  // chunk = keys 32 hf + 8 c .. + 7 of this row, hi atom and lo atom
-        const uint32_t off = sw128_offset(row, 4 * hf + c);
+      for (int c = 0; c < PCOLS / 8; ++c) {  // chunk = keys PCOLS part + 8 c .. + 7 of this row, hi atom and lo atom
+        const uint32_t off = sw128_offset(row, (PCOLS / 8) * part + c);
         sts128(sP + off, ph[4 * c], ph[4 * c + 1], ph[4 * c + 2], ph[4 * c + 3]);
         sts128(sP + P_ATOM + off, pl[4 * c], pl[4 * c + 1], pl[4 * c + 2], pl[4 * c + 3]);
       }
@@ -256,34 +279,35 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
       if (lane == 0) mbar_arrive(p_full);
       if (j > 0) {  // O += D of the previous tile (its own TMEM buffer; relative to the previous maximum), then rescale
         tc_fence_after();
-        float a[16], b[16];
-        const uint32_t dcol = 128 + ((j - 1) & 1) * 64 + hf * 16;
-        tmem_ld16(trow + dcol, a);
-        tmem_ld16(trow + dcol + 32, b);
+        float a[PCH], b[PCH];
+        const uint32_t dcol = 128 + ((j - 1) & 1) * 64 + part * PCH;
+        tmem_ldn<PCH>(trow + dcol, a);
+        tmem_ldn<PCH>(trow + dcol + 32, b);
         const f2_t al2 = f2_pack(alpha, alpha);
 #pragma unroll
-        for (int d = 0; d < 8; ++d)
+        for (int d = 0; d < PCH / 2; ++d)
           o2[d] = f2_mul(f2_add(o2[d], f2_add(f2_pack(a[2 * d], a[2 * d + 1]), f2_pack(b[2 * d], b[2 * d + 1]))), al2);
         tc_fence_before();
       }
     }
-    // the two halves of a row have summed different keys: exchange the partial sums
-    float* l_buf = s_max + (n_kv & 1) * (2 * BQ);  // (the buffer the last tile did not use)
-    l_buf[hf * BQ + row] = l;
-    pair_barrier(1 + quad);
-    l += l_buf[(hf ^ 1) * BQ + row];
+    // the threads of a row have summed different keys: exchange the partial sums
+    float* l_buf = s_max + (n_kv & 1) * (NPART * BQ);  // (the buffer the last tile did not use)
+    l_buf[part * BQ + row] = l;
+    row_barrier(1 + quad);
+#pragma unroll
+    for (int o = 1; o < NPART; ++o) l += l_buf[((part + o) % NPART) * BQ + row];
     // last tile's product, normalisation, store
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
-    float o[16];
+    float o[PCH];
     {
-      float a[16], b[16];
-      const uint32_t dcol = 128 + ((n_kv - 1) & 1) * 64 + hf * 16;
-      tmem_ld16(trow + dcol, a);
-      tmem_ld16(trow + dcol + 32, b);
+      float a[PCH], b[PCH];
+      const uint32_t dcol = 128 + ((n_kv - 1) & 1) * 64 + part * PCH;
+      tmem_ldn<PCH>(trow + dcol, a);
+      tmem_ldn<PCH>(trow + dcol + 32, b);
       const float inv = 1.f / l;
 #pragma unroll
-      for (int d = 0; d < 8; ++d) {
+      for (int d = 0; d < PCH / 2; ++d) {
         float x0, x1;
         f2_unpack(o2[d], x0, x1);
         o[2 * d] = (x0 + (a[2 * d] + b[2 * d])) * inv;
@@ -293,11 +317,11 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
     tc_fence_before();
     if (row < tl.q_rows) {
       const int token = tl.q_row0 + row;
-      const int c0 = head * HD + 16 * hf;  // first output column of this thread
+      const int c0 = head * HD + PCH * part;  // first output column of this thread
       if (out) {
         float4* dst = reinterpret_cast<float4*>(out + (size_t)token * out_ld + c0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        for (int i = 0; i < PCH / 4; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
       }
       if (out_img) {
         // A image of the output projection (gemm_tc.cu): token -> tile token / 64, stacked rows 2r (hi), 2r + 1 (lo);
@@ -305,22 +329,22 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
         float amax16 = 0.f;
         const uint32_t r2 = 2 * (token & 63);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < PCH / 8; ++i) {
           const int c = c0 + 8 * i;
-          uint32_t ph[4], pl[4];
+          uint32_t qh[4], ql[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float v0 = o[8 * i + 2 * e] * img_scale, v1 = o[8 * i + 2 * e + 1] * img_scale;
             amax16 = fmaxf(amax16, fmaxf(fabsf(v0), fabsf(v1)));
             const __half2 hh = __floats2half2_rn(v0, v1);
             const float2 hf2 = __half22float2(hh);
-            ph[e] = h2u(hh);
-            pl[e] = h2u(__floats2half2_rn(v0 - hf2.x, v1 - hf2.y));
+            qh[e] = h2u(hh);
+            ql[e] = h2u(__floats2half2_rn(v0 - hf2.x, v1 - hf2.y));
           }
           unsigned char* blk = out_img + ((size_t)(token >> 6) * img_katoms + (c >> 6)) * 16384;
           const uint32_t chunk = (c & 63) >> 3;
-          *reinterpret_cast<uint4*>(blk + sw128_offset(r2, chunk)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-          *reinterpret_cast<uint4*>(blk + sw128_offset(r2 + 1, chunk)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          *reinterpret_cast<uint4*>(blk + sw128_offset(r2, chunk)) = make_uint4(qh[0], qh[1], qh[2], qh[3]);
+          *reinterpret_cast<uint4*>(blk + sw128_offset(r2 + 1, chunk)) = make_uint4(ql[0], ql[1], ql[2], ql[3]);
         }
         if (!(amax16 <= 65504.f)) atomicOr(&g_attention_tc_flags, SPR_FLAG_FP16_OVERFLOW);  // false for NaN as well
       }

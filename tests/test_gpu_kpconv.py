@@ -310,6 +310,17 @@ def test_kpconv_stem_cin1_against_oracle(cout):
     exact = oracle.kpconv_forward(q, s, idx, x, w, kp, 0.3)
     assert np.abs(out - exact).max() <= FEAT_RTOL * np.abs(exact).max()
     assert np.all(out[3] == 0)
+    # the thread-per-query kernel reads 32-bit index rows 16 bytes at a time: whole rows, a trimmed view whose width is
+    # not a multiple of four (row stride 70, 17 and 40 columns), and a view that starts off the 16-byte grid
+    out32 = ops.kpconv_forward(_t(q), _t(s), _t(idx, torch.int32), _t(x), _t(w), _t(kp), 0.3)
+    assert torch.equal(out32, _t(out))
+    idx72 = np.concatenate([idx, np.full((nq, 2), ns, dtype=idx.dtype)], axis=1)   # row stride 72: 16-byte rows
+    i32 = _t(idx72, torch.int32)
+    for lo, hi in ((0, 72), (0, 17), (0, 40), (4, 36), (1, 34)):
+        view = i32[:, lo:hi]
+        got = ops.kpconv_forward(_t(q), _t(s), view, _t(x), _t(w), _t(kp), 0.3).cpu().numpy()
+        want = oracle.kpconv_forward(q, s, idx72[:, lo:hi].copy(), x, w, kp, 0.3)
+        assert np.abs(got - want).max() <= FEAT_RTOL * np.abs(want).max(), (lo, hi)
 
 
 def test_kpconv_tensor_core_wide_rows():

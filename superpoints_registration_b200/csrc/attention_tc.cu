@@ -177,13 +177,63 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
     fence_mbar_init();
   }
   if (warp == SM_WARPS + 1) tmem_alloc(s_tmem, TMEM_COLS);
-  // Q tile: 128 rows x 8 chunks (4 hi, 4 lo); rows past the end of the segment are zero
-  for (int i = tid; i < BQ * 8; i += ATTN_THREADS) {
-    const int r = i >> 3, c = i & 7;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < tl.q_rows)
-      v = *reinterpret_cast<const uint4*>(((c & 4) ? lo : hi) + (size_t)(tl.q_row0 + r) * ld + q_col + head * HD + (c & 3) * 8);
-    sts128(sQ + sw128_offset(r, c), v.x, v.y, v.z, v.w);
+  __syncthreads();  // the barriers exist
+  // ---- key / value loader (warp SM_WARPS) ----
+  // ONE warp feeds the CTA: everything that does not change from copy to copy is a per-lane constant (the first
+  // version recomputed row, chunk, plane and swizzle per copy -- ~800 dependent instructions per tile, and the
+  // whole CTA ran at the speed of this warp).  Lane -> 16-byte chunk c = lane % 8 (0-3 hi plane, 4-7 lo plane) of rows
+  // lane / 8 + 4 it, it = 0..15; rows r and r + 4 differ in their swizzle phase, rows r and r + 8 by 1024 bytes.
+  const int c = lane & 7, r0 = lane >> 3;
+  const __half* plane = (c & 4) ? lo : hi;
+  const size_t col = (size_t)head * HD + (c & 3) * 8;
+  const __half* kbase = plane + (size_t)tl.kv_row0 * ld + k_col + col;
+  const __half* vbase = plane + (size_t)tl.kv_row0 * ld + v_col + col;
+  const uint32_t off_e = r0 * 128 + ((c ^ r0) << 4), off_o = (r0 + 4) * 128 + ((c ^ (r0 + 4)) << 4);
+  const size_t step = (size_t)4 * ld;
+  auto load_tile = [&](int j) {
+    const int st = j % NSTAGE;
+    mbar_wait_park(&kv_empty[st], ((j / NSTAGE) & 1) ^ 1);
+    const int kv0 = j * BK + r0;
+    const uint32_t dK = sK + st * KV_BYTES, dV = sV + st * KV_BYTES;
+    if (kv0 + 60 < tl.kv_len) {  // every row of this lane exists
+      const __half* ks = kbase + (size_t)kv0 * ld;
+      const __half* vs = vbase + (size_t)kv0 * ld;
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const uint32_t d = ((it & 1) ? off_o : off_e) + (it >> 1) * 1024;
+        cp_async16(dK + d, ks, 16u);
+        cp_async16(dV + d, vs, 16u);
+        ks += step;
+        vs += step;
+      }
+    } else {  // the segment's last tile: rows past its end are zero-filled
+#pragma unroll 4
+      for (int it = 0; it < 16; ++it) {
+        const uint32_t d = ((it & 1) ? off_o : off_e) + (it >> 1) * 1024;
+        const int kv = kv0 + 4 * it;
+        const bool ok = kv < tl.kv_len;
+        const size_t ro = (size_t)(ok ? kv : 0) * ld;
+        cp_async16(dK + d, kbase + ro, ok ? 16u : 0u);
+        cp_async16(dV + d, vbase + ro, ok ? 16u : 0u);
+      }
+    }
+    cp_async_arrive_noinc(&kv_full[st]);
+  };
+  // The loader requests its first tiles while the other warps fetch the Q tile: the two latencies overlap (a CTA of the
+  // 3DMatch shape lives for five key tiles only, so its start-up is a third of its life).
+  int j_loaded = 0;
+  if (warp == SM_WARPS) {
+    for (; j_loaded < NSTAGE && j_loaded < n_kv; ++j_loaded) load_tile(j_loaded);
+  } else {
+    // Q tile: 128 rows x 8 chunks (4 hi, 4 lo); rows past the end of the segment are zero
+    const int qt = tid < SM_WARPS * 32 ? tid : tid - 32;
+    for (int i = qt; i < BQ * 8; i += ATTN_THREADS - 32) {
+      const int r = i >> 3, c = i & 7;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (r < tl.q_rows)
+        v = *reinterpret_cast<const uint4*>(((c & 4) ? lo : hi) + (size_t)(tl.q_row0 + r) * ld + q_col + head * HD + (c & 3) * 8);
+      sts128(sQ + sw128_offset(r, c), v.x, v.y, v.z, v.w);
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -351,46 +401,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
     }
   } else if (warp == SM_WARPS) {
     // ============================================ key / value loader ============================================
-    // ONE warp feeds the CTA: everything that does not change from copy to copy is a per-lane constant (the first
-    // version recomputed row, chunk, plane and swizzle per copy -- ~800 dependent instructions per tile, and the
-    // whole CTA ran at the speed of this warp).  Lane -> 16-byte chunk c = lane % 8 (0-3 hi plane, 4-7 lo plane) of rows
-    // lane / 8 + 4 it, it = 0..15; rows r and r + 4 differ in their swizzle phase, rows r and r + 8 by 1024 bytes.
-    const int c = lane & 7, r0 = lane >> 3;
-    const __half* plane = (c & 4) ? lo : hi;
-    const size_t col = (size_t)head * HD + (c & 3) * 8;
-    const __half* kbase = plane + (size_t)tl.kv_row0 * ld + k_col + col;
-    const __half* vbase = plane + (size_t)tl.kv_row0 * ld + v_col + col;
-    const uint32_t off_e = r0 * 128 + ((c ^ r0) << 4), off_o = (r0 + 4) * 128 + ((c ^ (r0 + 4)) << 4);
-    const size_t step = (size_t)4 * ld;
-    for (int j = 0; j < n_kv; ++j) {
-      const int st = j % NSTAGE;
-      mbar_wait_park(&kv_empty[st], ((j / NSTAGE) & 1) ^ 1);
-      const int kv0 = j * BK + r0;
-      const uint32_t dK = sK + st * KV_BYTES, dV = sV + st * KV_BYTES;
-      if (kv0 + 60 < tl.kv_len) {  // every row of this lane exists
-        const __half* ks = kbase + (size_t)kv0 * ld;
-        const __half* vs = vbase + (size_t)kv0 * ld;
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const uint32_t d = ((it & 1) ? off_o : off_e) + (it >> 1) * 1024;
-          cp_async16(dK + d, ks, 16u);
-          cp_async16(dV + d, vs, 16u);
-          ks += step;
-          vs += step;
-        }
-      } else {  // the segment's last tile: rows past its end are zero-filled
-#pragma unroll 4
-        for (int it = 0; it < 16; ++it) {
-          const uint32_t d = ((it & 1) ? off_o : off_e) + (it >> 1) * 1024;
-          const int kv = kv0 + 4 * it;
-          const bool ok = kv < tl.kv_len;
-          const size_t ro = (size_t)(ok ? kv : 0) * ld;
-          cp_async16(dK + d, kbase + ro, ok ? 16u : 0u);
-          cp_async16(dV + d, vbase + ro, ok ? 16u : 0u);
-        }
-      }
-      cp_async_arrive_noinc(&kv_full[st]);
-    }
+    for (int j = j_loaded; j < n_kv; ++j) load_tile(j);
   } else {
     // ============================================ MMA issuer ============================================
     if (lane == 0) {

@@ -310,7 +310,7 @@ SPR_API int spr_select_hypothesis(const float* d_a, const float* d_b, const int3
  * spr_attention_varlen: O[q, h] = softmax_k(Q[q,h] . K[k,h]) V[k,h] over the key segment of each query tile.
  *   d_hi / d_lo: planes with `ld` halves per row holding Q (pre-scaled), K and V at column offsets q_col / k_col /
  *   v_col (+ head * head_dim).  d_tiles: n_tiles x int32[4] = {first query row, query rows in the tile (<= 64),
- *   first key row, key rows}.  d_out: fp32 [rows, out_ld].  Products are hi*hi + lo*hi + hi*lo on the tensor
+ *   first key row, key rows}; an entry with 0 query rows is skipped (padding of a fixed-size list).  d_out: fp32 [rows, out_ld].  Products are hi*hi + lo*hi + hi*lo on the tensor
  *   cores with fp32 accumulation (fp32-level accuracy); the soft-max is online, nothing N x M is materialised.
  * ------------------------------------------------------------------------------------------- */
 SPR_API int spr_split_f16(const float* d_x, int rows, int cols, int ld_in, void* d_hi, void* d_lo, int ld_out,
@@ -349,6 +349,24 @@ SPR_API int spr_gemm_tc(const void* d_a_img, const void* d_w_img, const float* d
                         int ld_res, int T, int N, int K, float out_scale, int relu, int out_mode, void* d_out,
                         void* d_out_lo, int ld_out, int n_scaled, float col_scale, float next_scale, float* d_stats16,
                         void* stream);
+
+/* The whole packed cross-encoder (transformers.py:18-259: n_layers pre-norm TransformerCrossEncoderLayer with
+ * positional values + the final LayerNorm) issued from one call: per layer LN(+pos) -> QKV projection -> attention ->
+ * output projection (+x), the same with the partner cloud's keys, LN -> FFN1 (ReLU) -> FFN2 (+x); 11 launches per layer
+ * through the entry points above, nothing else -- it exists to take the host interpreter out of a launch-bound forward.
+ * d_x [T, 256] is updated in place; d_out (optional) receives the final LayerNorm.  Host arrays, layer-major:
+ *   ptrs[18 l + ..]: 0-5 norm1/2/3 weight, bias; 6-9 self-attention in_proj image, bias, out_proj image, bias; 10-13 the
+ *                    same for the cross-attention; 14-17 linear1 image, bias, linear2 image, bias   (device pointers)
+ *   scal[9 l + ..]:  0-2 eps of norm1/2/3; 3-6 weight-image scales (self in, self out, cross in, cross out); 7, 8
+ *                    linear1, linear2 scales (the `scale` given to spr_gemm_prepare_weight)
+ * Scratch, caller-owned: d_img (A image, K = 256), d_img_ffn (A image, K = d_ff), d_hi / d_lo (fp16 [T, 768] planes).
+ * attention_generation: 2 = spr_attention_varlen_tc (tiles of <= 128 rows), 1 = spr_attention_varlen (<= 64). */
+SPR_API int spr_cross_encoder_forward(float* d_x, const float* d_pos, int T, int d_model, int n_heads, int d_ff,
+                                      int n_layers, const void* const* ptrs, const float* scal,
+                                      const int32_t* d_sa_tiles, int n_sa_tiles, const int32_t* d_ca_tiles,
+                                      int n_ca_tiles, void* d_img, void* d_img_ffn, void* d_hi, void* d_lo,
+                                      float a_scale, int attention_generation, const float* d_final_gamma,
+                                      const float* d_final_beta, float final_eps, float* d_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,9 @@ _SIGNATURES = {
                                      c_fp, c_float, c_void_p]),
     "spr_attention_varlen_tc": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp, c_int, c_fp, c_int,
                                         c_fp, c_float, c_void_p]),
+    "spr_cross_encoder_forward": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_int, c_fp,
+                                          c_int, c_fp, c_fp, c_fp, c_fp, c_float, c_int, c_fp, c_fp, c_float, c_fp,
+                                          c_void_p]),
     "spr_gemm_a_image_bytes": (c_size_t, [c_int, c_int]),
     "spr_gemm_w_image_bytes": (c_size_t, [c_int, c_int]),
     "spr_gemm_prepare_weight": (c_int, [c_fp, c_int, c_int, c_float, c_fp, c_void_p]),

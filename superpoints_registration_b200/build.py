@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(CSRC, "libspr_b200.so")
 OBJ_DIR = os.path.join(CSRC, "build")
-SOURCES = ["common.cu", "grid_subsample.cu", "radius_neighbors.cu", "kpconv.cu", "kpconv_tc.cu", "kpconv_g.cu", "kpconv_s.cu", "blocks.cu", "matching.cu", "refine.cu", "attention.cu", "attention_tc.cu", "gemm_tc.cu",
+SOURCES = ["common.cu", "grid_subsample.cu", "radius_neighbors.cu", "kpconv.cu", "kpconv_tc.cu", "kpconv_g.cu", "kpconv_s.cu", "blocks.cu", "matching.cu", "refine.cu", "attention.cu", "attention_tc.cu", "encoder_seq.cu", "gemm_tc.cu",
            "procrustes.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(128, 4)
                 unsigned char* __restrict__ out_img, int img_katoms, float img_scale) {
   __shared__ __align__(128) unsigned char smem[2 * 4 * PLANE_BYTES];  // 2 stages x {K hi, K lo, V hi, V lo}
   const AttnTile tl = tiles[blockIdx.x];
+  if (tl.q_rows <= 0) return;  // padding entry of a bucketed tile list (CUDA-graph replays keep the grid fixed)
   const int head = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;

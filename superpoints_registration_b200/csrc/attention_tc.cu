@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2)
   uint64_t* pv_done = bars + 13;   // tcgen05.commit
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
   const AttnTile tl = tiles[blockIdx.x];
+  if (tl.q_rows <= 0) return;  // padding entry of a bucketed tile list (CUDA-graph replays keep the grid fixed)
   const int head = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_kv = (tl.kv_len + BK - 1) / BK;

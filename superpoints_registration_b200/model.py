@@ -186,6 +186,8 @@ class TransformerCrossEncoder(nn.Module):
         self.num_layers = num_layers
         self.norm = norm
         self.fused = True  # dense layers on the tcgen05 GEMM (False: cuBLAS fp32 through torch)
+        self.native_sequencer = True  # all layers from one library call (False: one Python call per launch)
+        self.cuda_graphs = True       # small inputs: the sequencer's launches replayed as a CUDA graph per shape bucket
 
     def forward(self, src, tgt, src_key_padding_mask=None, tgt_key_padding_mask=None, src_pos=None, tgt_pos=None):
         for layer in self.layers:
@@ -208,8 +210,21 @@ class TransformerCrossEncoder(nn.Module):
         for n in lens:
             offs.append(offs[-1] + n)
         partner = list(range(B, 2 * B)) + list(range(0, B))
-        sa_tiles = ops.attention_tiles(offs[:-1], lens, offs[:-1], lens, x.device)
-        ca_tiles = ops.attention_tiles(offs[:-1], lens, [offs[p] for p in partner], [lens[p] for p in partner], x.device)
+        native = (self.fused and self.native_sequencer and x.shape[1] == 256
+                  and all(l.activation is F.relu for l in self.layers))
+        graphed = native and self.cuda_graphs and x.shape[0] <= ops.ENCODER_GRAPH_MAX_ROWS
+        pad = ops.ENCODER_GRAPH_TILE_PAD if graphed else 1
+        sa_tiles = ops.attention_tiles(offs[:-1], lens, offs[:-1], lens, x.device, pad_multiple=pad)
+        ca_tiles = ops.attention_tiles(offs[:-1], lens, [offs[p] for p in partner], [lens[p] for p in partner], x.device,
+                                       pad_multiple=pad)
+        if native:
+            # one library call for all layers (csrc/encoder_seq.cu): same launches, same order, no interpreter in
+            # between -- and, for small inputs, replayed as one CUDA graph per shape bucket
+            table = getattr(self, '_seq_table', None)
+            if table is None or table.key != ops.CrossEncoderTable.signature(self.layers):
+                table = self._seq_table = ops.CrossEncoderTable(self.layers)
+            run = ops.cross_encoder_forward_graphed if graphed else ops.cross_encoder_forward
+            return run(x, pos, table, self.layers[0].self_attn.num_heads, sa_tiles, ca_tiles, self.norm)
         if self.fused and x.shape[1] == 256:
             x = x.clone()  # updated in place layer by layer
             img = ops.gemm_a_image(x.shape[0], 256, x.device)

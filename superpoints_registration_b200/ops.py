@@ -696,16 +696,18 @@ def attention_generation() -> int:
     return 1 if os.environ.get("SPR_ATTENTION_GEN", "2") == "1" else 2
 
 
-def attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q: Optional[int] = None) -> torch.Tensor:
+def attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q: Optional[int] = None,
+                    pad_multiple: int = 1) -> torch.Tensor:
     """Tile list of spr_attention_varlen(_tc): one row {first query row, rows, first key row, key rows} per block_q
-    queries (default: the tile height of the selected kernel generation)."""
+    queries (default: the tile height of the selected kernel generation).  pad_multiple > 1 rounds the list up with
+    empty entries (0 query rows: skipped by the kernels) so that launches of similar inputs share a grid size."""
     if block_q is None:
         block_q = 128 if attention_generation() == 2 else 64
-    key = ("tiles", tuple(q_offsets), tuple(q_lens), tuple(kv_offsets), tuple(kv_lens), str(device), block_q)
-    return _memo(key, lambda: _attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q))
+    key = ("tiles", tuple(q_offsets), tuple(q_lens), tuple(kv_offsets), tuple(kv_lens), str(device), block_q, pad_multiple)
+    return _memo(key, lambda: _attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q, pad_multiple))
 
 
-def _attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q):
+def _attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q, pad_multiple=1):
     rows = []
     for qo, qn, ko, kn in zip(q_offsets, q_lens, kv_offsets, kv_lens):
         if qn <= 0:
@@ -714,6 +716,8 @@ def _attention_tiles(q_offsets, q_lens, kv_offsets, kv_lens, device, block_q):
             raise RuntimeError("attention over an empty key segment")
         for q0 in range(0, qn, block_q):
             rows.append((qo + q0, min(block_q, qn - q0), ko, kn))
+    while len(rows) % pad_multiple:
+        rows.append((0, 0, 0, 0))
     return to_device_async(rows, torch.int32, device)
 
 
@@ -838,6 +842,125 @@ def gemm_tc(a_img: torch.Tensor, wi: WeightImage, bias, T: int, mode: int = OUT_
                        float(col_scale), A_SCALE, _ptr(stats16), _stream())
     _lib.check(rc, "spr_gemm_tc")
     return (out, out_lo) if mode == OUT_PLANES else out
+
+
+class CrossEncoderTable:
+    """Host pointer / scalar tables of spr_cross_encoder_forward for a stack of encoder layers, rebuilt when any of the
+    parameters changes (storage or version counter)."""
+
+    def __init__(self, layers):
+        import ctypes
+        self.key = self.signature(layers)
+        ptrs, scal, self.keep = [], [], []
+        for layer in layers:
+            sa, ca = layer.self_attn, layer.multihead_attn
+            wis = [weight_image(sa.in_proj_weight), weight_image(sa.out_proj.weight), weight_image(ca.in_proj_weight),
+                   weight_image(ca.out_proj.weight), weight_image(layer.linear1.weight), weight_image(layer.linear2.weight)]
+            self.keep += wis
+            for n in (layer.norm1, layer.norm2, layer.norm3):
+                ptrs += [_ptr(n.weight), _ptr(n.bias)]
+            ptrs += [wis[0].img.data_ptr(), _ptr(sa.in_proj_bias), wis[1].img.data_ptr(), _ptr(sa.out_proj.bias),
+                     wis[2].img.data_ptr(), _ptr(ca.in_proj_bias), wis[3].img.data_ptr(), _ptr(ca.out_proj.bias),
+                     wis[4].img.data_ptr(), _ptr(layer.linear1.bias), wis[5].img.data_ptr(), _ptr(layer.linear2.bias)]
+            scal += [layer.norm1.eps, layer.norm2.eps, layer.norm3.eps] + [w.w_scale for w in wis]
+        self.ptrs = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        self.scal = (ctypes.c_float * len(scal))(*scal)
+        self.n_layers = len(layers)
+        self.d_ff = layers[0].linear1.out_features
+
+    @staticmethod
+    def signature(layers):
+        sig = []
+        for layer in layers:
+            for t in (layer.norm1.weight, layer.norm1.bias, layer.norm2.weight, layer.norm2.bias, layer.norm3.weight,
+                      layer.norm3.bias, layer.self_attn.in_proj_weight, layer.self_attn.in_proj_bias,
+                      layer.self_attn.out_proj.weight, layer.self_attn.out_proj.bias, layer.multihead_attn.in_proj_weight,
+                      layer.multihead_attn.in_proj_bias, layer.multihead_attn.out_proj.weight,
+                      layer.multihead_attn.out_proj.bias, layer.linear1.weight, layer.linear1.bias, layer.linear2.weight,
+                      layer.linear2.bias):
+                sig.append((0, 0) if t is None else (t.data_ptr(), t._version))
+        return tuple(sig)
+
+
+def cross_encoder_forward(x: torch.Tensor, pos: Optional[torch.Tensor], table: CrossEncoderTable, n_heads: int,
+                          sa_tiles: torch.Tensor, ca_tiles: torch.Tensor, final_norm=None) -> torch.Tensor:
+    """All layers of the packed cross-encoder (+ the final LayerNorm) from ONE library call (csrc/encoder_seq.cu): the
+    launches of TransformerCrossEncoderLayer.forward_fused in the same order, without the interpreter between them.
+    x [T, 256] is not modified (a copy is updated in place)."""
+    import ctypes
+    L = _lib.lib()
+    xx = _f32c(x, "x").clone()
+    T, d = xx.shape
+    pp = None if pos is None else _f32c(pos, "pos")
+    dev = xx.device
+    img = gemm_a_image(T, d, dev)
+    img_ffn = gemm_a_image(T, table.d_ff, dev)
+    hi = torch.empty((T, 3 * d), dtype=torch.float16, device=dev)
+    lo = torch.empty_like(hi)
+    out = torch.empty_like(xx) if final_norm is not None else None
+    rc = L.spr_cross_encoder_forward(
+        xx.data_ptr(), _ptr(pp), T, d, int(n_heads), table.d_ff, table.n_layers,
+        ctypes.cast(table.ptrs, ctypes.c_void_p), ctypes.cast(table.scal, ctypes.c_void_p), sa_tiles.data_ptr(),
+        sa_tiles.shape[0], ca_tiles.data_ptr(), ca_tiles.shape[0], img.data_ptr(), img_ffn.data_ptr(), hi.data_ptr(),
+        lo.data_ptr(), A_SCALE, attention_generation(),
+        None if final_norm is None else final_norm.weight.data_ptr(),
+        None if final_norm is None else final_norm.bias.data_ptr(),
+        0.0 if final_norm is None else float(final_norm.eps), _ptr(out), _stream())
+    _lib.check(rc, "spr_cross_encoder_forward")
+    return xx if out is None else out
+
+
+class _EncoderGraph:
+    """One captured replay of spr_cross_encoder_forward for a shape bucket (rows padded to a multiple of 64, tile lists
+    to a multiple of TILE_PAD): static input buffers, the launches of all layers as ONE graph launch."""
+
+    def __init__(self, table, n_heads, t_pad, n_sa, n_ca, has_pos, final_norm, device):
+        self.x = torch.zeros((t_pad, 256), dtype=torch.float32, device=device)
+        self.pos = torch.zeros((t_pad, 256), dtype=torch.float32, device=device) if has_pos else None
+        self.sa = torch.zeros((n_sa, 4), dtype=torch.int32, device=device)   # all-padding lists: every CTA returns at once
+        self.ca = torch.zeros((n_ca, 4), dtype=torch.int32, device=device)
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):   # eager once: per-kernel attributes are set outside the capture
+            cross_encoder_forward(self.x, self.pos, table, n_heads, self.sa, self.ca, final_norm)
+        torch.cuda.current_stream(device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = cross_encoder_forward(self.x, self.pos, table, n_heads, self.sa, self.ca, final_norm)
+
+    def run(self, x, pos, sa_tiles, ca_tiles):
+        t = x.shape[0]
+        self.x[:t].copy_(x)            # rows past t stay zero: LayerNorm of a zero row is finite, nobody reads the result
+        if self.pos is not None:
+            self.pos[:t].copy_(pos)
+        self.sa.copy_(sa_tiles)
+        self.ca.copy_(ca_tiles)
+        self.graph.replay()
+        return self.out[:t].clone()    # the static output is overwritten by the next replay
+
+
+ENCODER_GRAPH_MAX_ROWS = 16384   # above this the forward is bound by the device, not by launch overhead
+ENCODER_GRAPH_TILE_PAD = 8
+ENCODER_GRAPH_CACHE = 12
+
+
+def cross_encoder_forward_graphed(x, pos, table: CrossEncoderTable, n_heads: int, sa_tiles, ca_tiles, final_norm=None):
+    """cross_encoder_forward through a CUDA graph per shape bucket (token rows rounded up to 64, tile lists to 8 entries):
+    ~70 kernel launches become one graph launch -- the forward of a single pair is bound by launch overhead
+    (tools/host_profile.py).  Bit-identical to the eager call; the tile lists must be padded (attention_tiles(...,
+    pad_multiple=ENCODER_GRAPH_TILE_PAD))."""
+    t = x.shape[0]
+    t_pad = (t + 63) // 64 * 64
+    key = (t_pad, sa_tiles.shape[0], ca_tiles.shape[0], pos is not None, attention_generation(), str(x.device),
+           None if final_norm is None else (final_norm.weight.data_ptr(), final_norm.bias.data_ptr(), float(final_norm.eps)))
+    graphs = table.__dict__.setdefault("graphs", {})
+    g = graphs.pop(key, None)
+    if g is None:
+        if len(graphs) >= ENCODER_GRAPH_CACHE:
+            graphs.pop(next(iter(graphs)))   # least recently used
+        g = _EncoderGraph(table, n_heads, t_pad, sa_tiles.shape[0], ca_tiles.shape[0], pos is not None, final_norm, x.device)
+    graphs[key] = g                          # most recently used last
+    return g.run(_f32c(x, "x"), None if pos is None else _f32c(pos, "pos"), sa_tiles, ca_tiles)
 
 
 def linear_tc(x: torch.Tensor, weight: torch.Tensor, bias=None, relu: bool = False, residual=None) -> torch.Tensor:

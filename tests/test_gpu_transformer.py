@@ -146,6 +146,45 @@ def test_layernorm_prepare_matches_torch():
     assert (y - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
 
 
+def test_native_sequencer_is_bit_identical_to_the_python_sequence():
+    """spr_cross_encoder_forward (all layers from one library call) issues the launches of forward_fused in the same
+    order: the conditioned features must be bit-identical, with and without positions, and follow a weight update."""
+    torch.manual_seed(3)
+    cfg = cfgs.threedmatch_config()
+    model = RegTR(cfg).to(DEV).eval()
+    enc = model.transformer_encoder
+    lens = [300, 17, 129, 64, 250, 31, 128, 90]
+    T = sum(lens)
+    x = torch.randn(T, 256, device=DEV)
+    pos = torch.randn(T, 256, device=DEV) * 0.5
+    for p in (pos, None):
+        enc.native_sequencer, enc.cuda_graphs = True, False
+        a = enc.forward_packed(x, p, lens)
+        enc.native_sequencer = False
+        b = enc.forward_packed(x, p, lens)
+        assert torch.equal(a, b)
+        # ... and replayed as a CUDA graph of its shape bucket (rows padded to 64, tile lists to 8 entries): first call
+        # captures, second replays; another set of lengths in the same bucket reuses the graph
+        enc.native_sequencer, enc.cuda_graphs = True, True
+        g1 = enc.forward_packed(x, p, lens)
+        g2 = enc.forward_packed(x, p, lens)
+        assert torch.equal(g1, b) and torch.equal(g2, b)
+        lens2 = [lens[0] - 5, lens[1] + 3] + lens[2:]          # same bucket (T - 2 rows), different segments
+        x2 = x[:sum(lens2)].contiguous()
+        p2 = None if p is None else p[:sum(lens2)].contiguous()
+        g3 = enc.forward_packed(x2, p2, lens2)
+        enc.native_sequencer = False
+        assert torch.equal(g3, enc.forward_packed(x2, p2, lens2))
+    enc.cuda_graphs = False
+    with torch.no_grad():
+        enc.layers[2].linear1.weight.mul_(1.5)          # version bump: the pointer table and the image must follow
+    enc.native_sequencer = True
+    a2 = enc.forward_packed(x, pos, lens)
+    enc.native_sequencer = False
+    b2 = enc.forward_packed(x, pos, lens)
+    assert torch.equal(a2, b2) and not torch.equal(a2, a)
+
+
 def test_fused_encoder_matches_packed_torch_linears():
     torch.manual_seed(1)
     cfg = cfgs.threedmatch_config()

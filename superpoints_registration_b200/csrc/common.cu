@@ -125,10 +125,44 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const int32_t* __re
   }
 }
 
+// Short inputs (the deeper pyramid levels, every level of a single pair): one block walks the array with a running
+// carry -- one launch instead of three.  Integer sums: identical to the three-kernel scan.
+constexpr size_t kScanSmall = 32768;
+__global__ void __launch_bounds__(1024) k_scan_small(const int32_t* in, int32_t* out, size_t n, int32_t* total) {
+  __shared__ int sw[33];
+  int carry = 0;
+  for (size_t base0 = 0; base0 < n; base0 += (size_t)1024 * kScanItems) {
+    const size_t base = base0 + (size_t)threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int s = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      const size_t i = base + j;
+      v[j] = i < n ? in[i] : 0;
+      s += v[j];
+    }
+    int bt;
+    int ex = block_exclusive_scan(s, sw, bt) + carry;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      const size_t i = base + j;
+      if (i < n) out[i] = ex;
+      ex += v[j];
+    }
+    carry += bt;
+  }
+  if (threadIdx.x == 0 && total) *total = carry;
+}
+
 int exclusive_scan_i32(const int32_t* d_in, int32_t* d_out, size_t n, int32_t* d_total, int32_t* d_tmp,
                        cudaStream_t stream) {
   if (n == 0) {
     if (d_total) SPR_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int32_t), stream));
+    return SPR_OK;
+  }
+  if (n <= kScanSmall) {
+    k_scan_small<<<1, 1024, 0, stream>>>(d_in, d_out, n, d_total);
+    SPR_LAUNCH_CHECK("k_scan_small");
     return SPR_OK;
   }
   const int n_tiles = (int)((n + kScanTile - 1) / kScanTile);

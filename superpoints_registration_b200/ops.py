@@ -925,7 +925,9 @@ class _EncoderGraph:
             cross_encoder_forward(self.x, self.pos, table, n_heads, self.sa, self.ca, final_norm)
         torch.cuda.current_stream(device).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread-local error mode: other threads of the process (NCCL's watchdog, a data loader) may call into CUDA
+        # while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.out = cross_encoder_forward(self.x, self.pos, table, n_heads, self.sa, self.ca, final_norm)
 
     def run(self, x, pos, sa_tiles, ca_tiles):

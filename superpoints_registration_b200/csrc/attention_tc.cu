@@ -5,8 +5,8 @@
 // What attention.cu measured (profiles/README.md, round 2): the warp-level tensor path is 58 % busy at the 3DMatch shape
 // and the kernel sits at `math pipe throttle` -- three split-precision products (hi*hi + lo*hi + hi*lo) of mma.sync per
 // score and per value are the bound.  Here both products of a (128 queries x 64 keys) tile are tcgen05.mma instructions
-// issued by one thread, the scores and the per-tile P V product live in TMEM, and the four soft-max warps own one query
-// row per thread (one TMEM lane: no shuffles, no shared-memory reductions).
+// issued by one thread, the scores and the per-tile P V product live in TMEM, and a query row belongs to the NPART
+// soft-max threads that own its TMEM lane (no shuffles; one shared-memory exchange of the partial row maximum per tile).
 //
 //   CTA = (tile of <= 128 queries, head); warps 0-7 soft-max (TMEM lane quadrant w % 4, key columns / output channels
 //   half w / 4: a query row is shared by two threads that exchange their partial row maximum through shared memory),

@@ -212,7 +212,8 @@ class TransformerCrossEncoder(nn.Module):
         partner = list(range(B, 2 * B)) + list(range(0, B))
         native = (self.fused and self.native_sequencer and x.shape[1] == 256
                   and all(l.activation is F.relu for l in self.layers))
-        graphed = native and self.cuda_graphs and x.shape[0] <= ops.ENCODER_GRAPH_MAX_ROWS
+        graphed = (native and self.cuda_graphs and x.shape[0] <= ops.ENCODER_GRAPH_MAX_ROWS
+                   and not torch.cuda.is_current_stream_capturing())  # (a caller's own capture takes the eager launches)
         pad = ops.ENCODER_GRAPH_TILE_PAD if graphed else 1
         sa_tiles = ops.attention_tiles(offs[:-1], lens, offs[:-1], lens, x.device, pad_multiple=pad)
         ca_tiles = ops.attention_tiles(offs[:-1], lens, [offs[p] for p in partner], [lens[p] for p in partner], x.device,

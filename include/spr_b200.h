@@ -212,9 +212,10 @@ SPR_API int spr_kpconv_forward_staged(const float* d_q, const void* d_idx, int i
                                       float* d_out, int nq, int ns, const int32_t* d_order, void* stream);
 
 /* max_pool(x, inds)  kpconv_blocks.py:127-143: out[n,c] = max_h xpad[idx[n,h],c] where xpad has a zero
- * row appended for the shadow index. */
+ * row appended for the shadow index.  d_order (optional, [nq] i32): a permutation of the pooled points giving the
+ * processing order (results are written at the original rows; cell order keeps the gathers in cache). */
 SPR_API int spr_max_pool(const float* d_x, const void* d_idx, int idx_is_64, int row_stride, int H, int nq, int ns, int c,
-                 float* d_out, void* stream);
+                 float* d_out, const int32_t* d_order, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Superpoint matching.  Replaces the per-pair body of RegTR.softmax_correlation

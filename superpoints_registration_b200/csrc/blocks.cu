@@ -380,11 +380,14 @@ __global__ void __launch_bounds__(256, STEPS == 1 ? 6 : 4)
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
     k_max_pool(const float* __restrict__ x, const IdxT* __restrict__ idx, int row_stride, int H, int nq, int ns, int c,
-               float* __restrict__ out) {
+               float* __restrict__ out, const int* __restrict__ order) {
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
   const int c4 = c >> 2;
-  for (int n = blockIdx.x * warps + (threadIdx.x >> 5); n < nq; n += gridDim.x * warps) {
+  for (int i = blockIdx.x * warps + (threadIdx.x >> 5); i < nq; i += gridDim.x * warps) {
+    // `order` (optional) walks the pooled points in cell order: the eight rows of a CTA are spatial neighbours, their
+    // pooling neighbourhoods overlap and the 512-byte feature rows they gather hit L1 / L2
+    const int n = order ? __ldg(order + i) : i;
     const IdxT* row = idx + (size_t)n * row_stride;
     for (int cc = lane; cc < c4; cc += 32) {
       float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
@@ -525,7 +528,7 @@ extern "C" int spr_instance_norm_lrelu_ex(const float* d_x, const int32_t* d_len
 }
 
 extern "C" int spr_max_pool(const float* d_x, const void* d_idx, int idx_is_64, int row_stride, int H, int nq, int ns,
-                            int c, float* d_out, void* stream_) {
+                            int c, float* d_out, const int32_t* d_order, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SPR_CHECK_ARG(nq > 0 && ns > 0 && c > 0 && H > 0, "max_pool: empty input");
   SPR_CHECK_ARG(c % 4 == 0, "max_pool: channel count %d must be a multiple of 4", c);
@@ -535,9 +538,10 @@ extern "C" int spr_max_pool(const float* d_x, const void* d_idx, int idx_is_64, 
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   if (idx_is_64)
     k_max_pool<long long><<<blocks, 256, 0, stream>>>(d_x, static_cast<const long long*>(d_idx), row_stride, H, nq, ns,
-                                                      c, d_out);
+                                                      c, d_out, d_order);
   else
-    k_max_pool<int><<<blocks, 256, 0, stream>>>(d_x, static_cast<const int*>(d_idx), row_stride, H, nq, ns, c, d_out);
+    k_max_pool<int><<<blocks, 256, 0, stream>>>(d_x, static_cast<const int*>(d_idx), row_stride, H, nq, ns, c, d_out,
+                                                d_order);
   SPR_LAUNCH_CHECK("k_max_pool");
   return SPR_OK;
 }

@@ -29,9 +29,9 @@ LRELU_SLOPE = 0.1
 IN_EPS = 1e-5  # nn.InstanceNorm1d default eps
 
 
-def max_pool(x, inds):
+def max_pool(x, inds, order=None):
     """Pools features with the maximum over each pooling neighbourhood (shadow index -> zero row)."""
-    return ops.max_pool(x, inds)
+    return ops.max_pool(x, inds, order)
 
 
 class KPConv(nn.Module):
@@ -246,7 +246,7 @@ class ResnetBottleneckBlock(nn.Module):
                                                 want_image=True)['image']
         n_out = q_pts.shape[0]
         if strided:
-            shortcut = max_pool(features, inds)
+            shortcut = max_pool(features, inds, order)
             s_img = ops.gemm_prepare_input(shortcut) if isinstance(self.unary_shortcut, UnaryBlock) else None
         else:
             shortcut, s_img = features, f_img

@@ -467,13 +467,18 @@ def _kpconv_forward_gather(q_pts, neighb_inds, feats: PreparedFeatures, weights,
     return out
 
 
-def max_pool(x, inds):
+def max_pool(x, inds, order=None):
+    """order (optional): i32 permutation of the pooled points = the order they are processed in (same result)."""
     L = _lib.lib()
     xx = _f32c(x, "x")
     idx, is64, stride, H = _idx_arg(inds)
     nq, (ns, c) = idx.shape[0], xx.shape
     out = torch.empty((nq, c), dtype=torch.float32, device=xx.device)
-    rc = L.spr_max_pool(xx.data_ptr(), idx.data_ptr(), is64, stride, H, nq, ns, c, out.data_ptr(), _stream())
+    if order is not None:
+        order = _i32c(order, "order")
+        if order.numel() != nq:
+            raise RuntimeError("max_pool: order must have one entry per pooled point")
+    rc = L.spr_max_pool(xx.data_ptr(), idx.data_ptr(), is64, stride, H, nq, ns, c, out.data_ptr(), _ptr(order), _stream())
     _lib.check(rc, "spr_max_pool")
     return out
 

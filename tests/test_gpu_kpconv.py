@@ -153,6 +153,12 @@ def test_instance_norm_and_max_pool_against_golden(golden_dir):
     assert np.abs(y2 - want).max() < 2e-4
     mp = max_pool(_t(g["x"]), _t(g["pool_idx"], torch.int64)).cpu().numpy()
     assert np.array_equal(mp, g["pool_out"])
+    # a processing order (the pyramid's cell order in the encoder) changes which CTA pools which point, not the result
+    perm = torch.randperm(g["pool_idx"].shape[0], device=DEV).to(torch.int32)
+    mp2 = max_pool(_t(g["x"]), _t(g["pool_idx"], torch.int32), perm).cpu().numpy()
+    assert np.array_equal(mp2, g["pool_out"])
+    with pytest.raises(RuntimeError):
+        max_pool(_t(g["x"]), _t(g["pool_idx"], torch.int32), perm[:-1])
 
 
 def test_instance_norm_is_deterministic_and_handles_many_clouds():

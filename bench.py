@@ -395,12 +395,12 @@ def run_ours(args):
     recording = {"on": False}
     raw_kpconv, raw_prepared = ops.kpconv_forward, ops.kpconv_forward_prepared
 
-    def timed_kpconv(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent, mode=0):
+    def timed_kpconv(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent, **kw):
         if not recording["on"]:
-            return raw_kpconv(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent, mode)
+            return raw_kpconv(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent, **kw)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        y = raw_kpconv(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent, mode)
+        y = raw_kpconv(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent, **kw)
         e1.record()
         records.append((e0, e1, q_pts.shape[0], s_pts.shape[0], neighb_inds.shape[1], weights.shape[1], weights.shape[2]))
         return y

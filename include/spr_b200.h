@@ -134,12 +134,14 @@ SPR_API int spr_radius_query_ex(const float* d_queries, const int32_t* d_q_lengt
  *   d_x [ns,cin], d_w [K,cin,cout], d_kp [K,3], d_out [nq,cout]; all fp32 row-major.
  *   mode: 0 = fp32 CUDA-core contraction (parity anchor); 1 = tcgen05 tensor-core contraction with
  *         split-precision operands (when built in; SPR_EUNSUPPORTED otherwise).
+ *   d_order (optional, [nq] i32): a permutation of the queries = the order they are processed in (results are written
+ *         at the original rows); used by the Cin = 1 kernel, whose 32 queries per warp then share their gathers.
  * ------------------------------------------------------------------------------------------- */
 SPR_API size_t spr_kpconv_workspace_bytes(int nq, int ns, int cin, int cout, int n_kernel_points);
 SPR_API int spr_kpconv_forward(const float* d_q, const float* d_s, const void* d_idx, int idx_is_64, int row_stride, int H,
                        const float* d_x, int cin, const float* d_w, int cout, const float* d_kp, int n_kernel_points,
                        float extent, float* d_out, int nq, int ns, int mode, void* d_workspace, size_t workspace_bytes,
-                       void* stream);
+                       const int32_t* d_order, void* stream);
 
 /* KPConv (tensor-core path) with operands prepared by the producing kernels instead of the built-in pre-pass:
  *   spr_kpconv_prepare_weights: [W_hi | W_lo] stage images + max|W| (one word), once per weight

@@ -35,7 +35,7 @@ _SIGNATURES = {
                                     c_void_p]),
     "spr_kpconv_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "spr_kpconv_forward": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_fp, c_int, c_fp, c_int, c_fp, c_int,
-                                   c_float, c_fp, c_int, c_int, c_int, c_fp, c_size_t, c_void_p]),
+                                   c_float, c_fp, c_int, c_int, c_int, c_fp, c_size_t, c_fp, c_void_p]),
     "spr_instance_norm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "spr_instance_norm_lrelu": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_float, c_float, c_fp, c_fp, c_fp, c_size_t,
                                         c_void_p]),

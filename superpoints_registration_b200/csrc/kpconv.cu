@@ -205,7 +205,7 @@ template <typename IdxT, int COUT>
 __global__ void __launch_bounds__(128, 4)
     k_kpconv_cin1_t(const float* __restrict__ q, const float4* __restrict__ packed, const IdxT* __restrict__ idx,
                     int row_stride, int H, const float* __restrict__ w, const float* __restrict__ kp, float extent,
-                    float* __restrict__ out, int nq, int ns) {
+                    float* __restrict__ out, int nq, int ns, const int* __restrict__ order) {
   constexpr int NP = KP / 2;  // kernel-point pairs (2p, 2p + 1); the last kernel point is handled alone
   // The first version of this kernel was bound by the L1 data pipe (79 % of its wavefront peak, ncu): a scalar index
   // load, a gather or a 16-byte row store of 32 threads that work on 32 different rows is 32 wavefronts.  Index rows are
@@ -230,9 +230,11 @@ __global__ void __launch_bounds__(128, 4)
   // 16-byte index loads: 32-bit indices, rows that start on 16-byte boundaries
   const bool vec_idx = sizeof(IdxT) == 4 && (row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(idx) & 15) == 0;
   for (int base = blockIdx.x * blockDim.x; base < nq; base += gridDim.x * blockDim.x) {
-    const int n = base + threadIdx.x;
-    const bool live = n < nq;
-    const IdxT* row = idx + (size_t)(live ? n : nq - 1) * row_stride;
+    // `order` (optional) walks the queries in cell order: the 32 queries of a warp are spatial neighbours, their
+    // neighbourhoods overlap, and a gather instruction touches a third of the lines
+    const bool live = base + (int)threadIdx.x < nq;
+    const int n = live ? (order ? __ldg(order + base + threadIdx.x) : base + (int)threadIdx.x) : nq - 1;
+    const IdxT* row = idx + (size_t)n * row_stride;
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (live) {
       qx = __ldg(q + 3 * (size_t)n);
@@ -349,8 +351,9 @@ __global__ void __launch_bounds__(128, 4)
 #pragma unroll
       for (int i = 0; i < LPR; ++i) {
         const int f = i * 32 + lane, r = f / LPR, c4 = (f % LPR) * 4;
+        const int nr = __shfl_sync(kFull, n, r);  // the row that staged row r belongs to
         if (row0 + r < nq)
-          *reinterpret_cast<float4*>(out + (size_t)(row0 + r) * COUT + c4) =
+          *reinterpret_cast<float4*>(out + (size_t)nr * COUT + c4) =
               *reinterpret_cast<const float4*>(wstage + r * OSTRIDE + c4);
       }
       __syncwarp();
@@ -693,7 +696,7 @@ extern "C" size_t spr_kpconv_workspace_bytes(int nq, int ns, int cin, int cout, 
 extern "C" int spr_kpconv_forward(const float* d_q, const float* d_s, const void* d_idx, int idx_is_64, int row_stride,
                                   int H, const float* d_x, int cin, const float* d_w, int cout, const float* d_kp,
                                   int n_kernel_points, float extent, float* d_out, int nq, int ns, int mode,
-                                  void* d_workspace, size_t workspace_bytes, void* stream_) {
+                                  void* d_workspace, size_t workspace_bytes, const int32_t* d_order, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SPR_CHECK_ARG(nq > 0 && ns > 0, "kpconv_forward: empty input (nq=%d, ns=%d)", nq, ns);
   SPR_CHECK_ARG(H > 0 && row_stride >= H, "kpconv_forward: bad neighbour matrix shape (H=%d, row_stride=%d)", H,
@@ -731,10 +734,11 @@ extern "C" int spr_kpconv_forward(const float* d_q, const float* d_s, const void
   do {                                                                                                               \
     if (idx_is_64)                                                                                                   \
       k_kpconv_cin1_t<long long, CO><<<grid_t, 128, 0, stream>>>(d_q, packed, static_cast<const long long*>(d_idx),  \
-                                                                 row_stride, H, d_w, d_kp, extent, d_out, nq, ns);   \
+                                                                 row_stride, H, d_w, d_kp, extent, d_out, nq, ns,    \
+                                                                 d_order);                                           \
     else                                                                                                             \
       k_kpconv_cin1_t<int, CO><<<grid_t, 128, 0, stream>>>(d_q, packed, static_cast<const int*>(d_idx), row_stride, H, \
-                                                           d_w, d_kp, extent, d_out, nq, ns);                        \
+                                                           d_w, d_kp, extent, d_out, nq, ns, d_order);               \
   } while (0)
       switch (cout) {
         case 32: SPR_CIN1T(32); break;

@@ -70,9 +70,9 @@ class KPConv(nn.Module):
         kp = load_kernels(self.radius, self.K, dimension=self.p_dim, fixed=self.fixed_kernel_points)
         self.kernel_points = Parameter(torch.tensor(kp, dtype=torch.float32), requires_grad=False)
 
-    def forward(self, q_pts, s_pts, neighb_inds, x):
+    def forward(self, q_pts, s_pts, neighb_inds, x, order=None):
         return ops.kpconv_forward(q_pts, s_pts, neighb_inds, x, self.weights, self.kernel_points,
-                                  float(self.KP_extent), mode=self.mode)
+                                  float(self.KP_extent), mode=self.mode, order=order)
 
     def __repr__(self):
         return (f'KPConv(radius: {self.radius:.2f}, extent: {self.KP_extent:.2f}, in_feat: {self.in_channels:d}, '
@@ -184,8 +184,11 @@ class SimpleBlock(nn.Module):
         self.batch_norm = BatchNormBlock(out_dim // 2, self.use_bn, self.bn_momentum)
 
     def forward(self, x, batch):
-        q_pts, s_pts, inds, lengths = _level_io(batch, self.layer_ind, 'strided' in self.block_name)
-        x = self.KPConv(q_pts, s_pts, inds, x)
+        strided = 'strided' in self.block_name
+        q_pts, s_pts, inds, lengths = _level_io(batch, self.layer_ind, strided)
+        orders = getattr(batch, 'order', None)
+        order = orders[self.layer_ind + 1 if strided else self.layer_ind] if orders is not None else None
+        x = self.KPConv(q_pts, s_pts, inds, x, order)
         if self.use_bn and x.shape[1] % 32 == 0:
             o = self.batch_norm.forward_ex(x, lengths, slope=LRELU_SLOPE, want_f32=True, want_image=True)
             batch['_operand_image'] = (o['f32'], o['image'])   # for the next block's unary GEMMs (matched by identity)

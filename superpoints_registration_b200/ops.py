@@ -197,7 +197,8 @@ def default_kpconv_mode(cin: int, cout: int) -> int:
     return 1 if (cin == cout and cin in _TC_CHANNELS) else 0
 
 
-def kpconv_forward(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent: float, mode=None):
+def kpconv_forward(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent: float, mode=None, order=None):
+    """order (optional): i32 permutation of the queries = processing order (same result; the Cin = 1 kernel uses it)."""
     L = _lib.lib()
     q, s, xx = _f32c(q_pts, "q_pts"), _f32c(s_pts, "s_pts"), _f32c(x, "x")
     w, kp = _f32c(weights, "weights"), _f32c(kernel_points, "kernel_points")
@@ -210,11 +211,15 @@ def kpconv_forward(q_pts, s_pts, neighb_inds, x, weights, kernel_points, extent:
         raise RuntimeError("neighb_inds must have one row per query point")
     if mode is None:
         mode = default_kpconv_mode(cin, cout)
+    if order is not None:
+        order = _i32c(order, "order")
+        if order.numel() != nq:
+            raise RuntimeError("kpconv_forward: order must have one entry per query")
     out = torch.empty((nq, cout), dtype=torch.float32, device=q.device)
     ws = _ws(L.spr_kpconv_workspace_bytes(nq, ns, cin, cout, K), q.device)
     rc = L.spr_kpconv_forward(q.data_ptr(), s.data_ptr(), idx.data_ptr(), is64, stride, H, xx.data_ptr(), cin,
                               w.data_ptr(), cout, kp.data_ptr(), K, float(extent), out.data_ptr(), nq, ns, int(mode),
-                              ws.data_ptr(), ws.numel(), _stream())
+                              ws.data_ptr(), ws.numel(), _ptr(order), _stream())
     _lib.check(rc, "spr_kpconv_forward")
     return out
 

@@ -74,7 +74,7 @@ def test_argument_errors_are_reported_without_touching_the_device():
     assert rc == -1 and b"empty input" in L.spr_last_error()
     rc = L.spr_radius_query(None, None, 10, 1, None, 10, 0.1, 500, None, 1, 500, None, None)
     assert rc == -1 and b"limit" in L.spr_last_error()
-    rc = L.spr_kpconv_forward(None, None, None, 1, 4, 4, None, 32, None, 32, None, 15, 0.1, None, 0, 10, 0, None, 0, None)
+    rc = L.spr_kpconv_forward(None, None, None, 1, 4, 4, None, 32, None, 32, None, 15, 0.1, None, 0, 10, 0, None, 0, None, None)
     assert rc == -1
     with pytest.raises(RuntimeError):
         _lib.check(rc, "spr_kpconv_forward")

@@ -320,6 +320,9 @@ def test_kpconv_stem_cin1_against_oracle(cout):
     # not a multiple of four (row stride 70, 17 and 40 columns), and a view that starts off the 16-byte grid
     out32 = ops.kpconv_forward(_t(q), _t(s), _t(idx, torch.int32), _t(x), _t(w), _t(kp), 0.3)
     assert torch.equal(out32, _t(out))
+    # a processing order (the encoder passes the pyramid's cell order) permutes which thread serves which query only
+    perm = torch.randperm(nq, device=DEV).to(torch.int32)
+    assert torch.equal(ops.kpconv_forward(_t(q), _t(s), _t(idx, torch.int32), _t(x), _t(w), _t(kp), 0.3, order=perm), out32)
     idx72 = np.concatenate([idx, np.full((nq, 2), ns, dtype=idx.dtype)], axis=1)   # row stride 72: 16-byte rows
     i32 = _t(idx72, torch.int32)
     for lo, hi in ((0, 72), (0, 17), (0, 40), (4, 36), (1, 34)):

@@ -208,14 +208,10 @@ SPR_API int spr_kpconv_forward_gather(const float* d_q, const void* d_idx, int i
 SPR_API int spr_kpconv_staged_supported(int c, int H);
 SPR_API size_t spr_kpconv_staged_weight_image_bytes(int c);
 SPR_API int spr_kpconv_staged_prepare_weights(const float* d_w, int c, void* d_img, void* d_amax_w, void* stream);
-/* d_scratch (optional, spr_kpconv_staged_scratch_bytes() bytes, no initialisation needed): lets every producer warp park
- * one finished query while the tensor cores still read the previous channel pass (C >= 128: -10 .. -20 %). */
-SPR_API size_t spr_kpconv_staged_scratch_bytes(void);
 SPR_API int spr_kpconv_forward_staged(const float* d_q, const void* d_idx, int idx_is_64, int row_stride, int H,
                                       const void* d_pts4, const void* d_x16, const void* d_amax_x, int c,
                                       const void* d_wimg, const void* d_amax_w, const float* d_kp, float extent,
-                                      float* d_out, int nq, int ns, const int32_t* d_order, void* d_scratch,
-                                      void* stream);
+                                      float* d_out, int nq, int ns, const int32_t* d_order, void* stream);
 
 /* max_pool(x, inds)  kpconv_blocks.py:127-143: out[n,c] = max_h xpad[idx[n,h],c] where xpad has a zero
  * row appended for the shadow index.  d_order (optional, [nq] i32): a permutation of the pooled points giving the

@@ -55,9 +55,8 @@ _SIGNATURES = {
     "spr_kpconv_staged_supported": (c_int, [c_int, c_int]),
     "spr_kpconv_staged_weight_image_bytes": (c_size_t, [c_int]),
     "spr_kpconv_staged_prepare_weights": (c_int, [c_fp, c_int, c_fp, c_fp, c_void_p]),
-    "spr_kpconv_staged_scratch_bytes": (c_size_t, []),
     "spr_kpconv_forward_staged": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp,
-                                          c_float, c_fp, c_int, c_int, c_fp, c_fp, c_void_p]),
+                                          c_float, c_fp, c_int, c_int, c_fp, c_void_p]),
     "spr_max_pool": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp, c_fp, c_void_p]),
     "spr_match_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "spr_dual_softmax_match": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(SCfg<C>::THREADS, 1)
                const unsigned char* __restrict__ x16p, const unsigned char* __restrict__ wimg,
                const float* __restrict__ kp, const float4* __restrict__ pts4, const unsigned int* __restrict__ amax_x_bits,
                const unsigned int* __restrict__ amax_w_bits, float extent, float* __restrict__ out, int nq, int ns, int tq,
-               int n_tiles, const int* __restrict__ order, uint4* __restrict__ stash) {
+               int n_tiles, const int* __restrict__ order) {
   using K = SCfg<C>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem =
@@ -226,9 +226,6 @@ __global__ void __launch_bounds__(SCfg<C>::THREADS, 1)
     const uint32_t hi_off = pinned(lrow * 128 + ((lm ^ lrow) << 4));  // lo parts: chunk 4 + lm, i.e. bit 6 flipped
     const uint32_t pa_off = pinned(K::SLOT_X + 32 * t);
     constexpr uint32_t hdr_off = K::SLOT_X + K::SLOT_P;
-    // One finished query per warp can be parked in global memory (64 bytes per lane, this lane's own words: no ordering
-    // issue) while the MMAs of the previous pass still read the A tile -- see the query-complete section below.
-    uint4* my_stash = stash ? stash + ((size_t)(blockIdx.x * K::WORKERS + warp) * 32 + lane) * 4 : nullptr;
 
     uint32_t seq = 0;
     int titer = 0;
@@ -274,8 +271,7 @@ __global__ void __launch_bounds__(SCfg<C>::THREADS, 1)
 #pragma unroll 1
       for (int pass = 0; pass < K::PASSES; ++pass, ++seq) {
         const unsigned char* xpass = x16p + pass * 128 + cch * 16;
-        bool first = true, stashed = false;
-        int stash_ql = 0;
+        bool first = true;
         // queries are dealt to the warps dynamically (neighbourhood sizes vary); the dispenser of pass seq+2 is
         // reset by whoever draws query 0 of pass seq (no warp can still be in pass seq-2, see bar_done)
         int* ctr = s_ctr + (seq & 3);
@@ -447,33 +443,16 @@ __global__ void __launch_bounds__(SCfg<C>::THREADS, 1)
           }
           if (!(meta & (1 << 16))) continue;
           // ---- the query is complete: split to fp16 pairs and store its two A rows ----
-          // The A tile still feeds the MMAs of the previous pass until bar_done completes.  The FIRST query a warp
-          // finishes in a pass is therefore parked in the warp's global stash when those MMAs are still running (the
-          // warp goes on with its next query: two queries of look-ahead instead of one -- at C = 256 the producers
-          // spent 23 % of their time in this wait), and written to the tile together with the second one.
+          // the A tile still feeds the MMAs of the previous pass until bar_done completes
+          if (first) {
+            if (seq > 0) mbar_wait_park(bar_done, (seq - 1) & 1);
+            if (pass == 0 && titer > 0) epilogue(prev_q0, prev_cnt, sInv + ((titer - 1) & 1) * K::TQ);
+            first = false;
+          }
           // this lane holds, for kernel points k = g (d[i][0], d[i][1]) and k = g + 8 (d[i][2], d[i][3]), channels
           // 8 i + 2 t, 8 i + 2 t + 1 = K positions 8 t + 2 i, 8 t + 2 i + 1: one 16-byte chunk of fp16 each,
           // K element = k * 32 + position  ->  atom k / 2, chunk (k % 2) * 4 + t
           const int ql = meta & 0xff;
-          const bool park = first && !stashed && my_stash != nullptr && seq > 0 && !mbar_try_wait(bar_done, (seq - 1) & 1);
-          if (first && !park) {
-            if (seq > 0) mbar_wait_park(bar_done, (seq - 1) & 1);
-            if (pass == 0 && titer > 0) epilogue(prev_q0, prev_cnt, sInv + ((titer - 1) & 1) * K::TQ);
-            first = false;
-            if (stashed) {  // the parked query first
-              const uint32_t p0 = 2 * stash_ql, p1 = 2 * stash_ql + 1;
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                const uint4 hv = my_stash[2 * half], lv = my_stash[2 * half + 1];
-                const int k = g + 8 * half;
-                const uint32_t atom = sA32 + (k >> 1) * K::A_ATOM_BYTES;
-                const uint32_t j = (k & 1) * 4 + t;
-                sts128u(atom + sw128_offset(p0, j), hv.x, hv.y, hv.z, hv.w);
-                sts128u(atom + sw128_offset(p1, j), lv.x, lv.y, lv.z, lv.w);
-              }
-              stashed = false;
-            }
-          }
           const uint32_t r0 = 2 * ql, r1 = 2 * ql + 1;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -486,20 +465,11 @@ __global__ void __launch_bounds__(SCfg<C>::THREADS, 1)
               hi[i] = h2_bits(hh);
               lo[i] = h2_bits(__floats2half2_rn(v0 - hf.x, v1 - hf.y));
             }
-            if (park) {
-              my_stash[2 * half] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              my_stash[2 * half + 1] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            } else {
-              const int k = g + 8 * half;
-              const uint32_t atom = sA32 + (k >> 1) * K::A_ATOM_BYTES;
-              const uint32_t j = (k & 1) * 4 + t;
-              sts128u(atom + sw128_offset(r0, j), hi[0], hi[1], hi[2], hi[3]);
-              sts128u(atom + sw128_offset(r1, j), lo[0], lo[1], lo[2], lo[3]);
-            }
-          }
-          if (park) {
-            stashed = true;
-            stash_ql = ql;
+            const int k = g + 8 * half;
+            const uint32_t atom = sA32 + (k >> 1) * K::A_ATOM_BYTES;
+            const uint32_t j = (k & 1) * 4 + t;
+            sts128u(atom + sw128_offset(r0, j), hi[0], hi[1], hi[2], hi[3]);
+            sts128u(atom + sw128_offset(r1, j), lo[0], lo[1], lo[2], lo[3]);
           }
           if (pass == 0) {
             // a neighbour is replicated over g: count the g == 0 copies (lanes 0..3)
@@ -510,22 +480,9 @@ __global__ void __launch_bounds__(SCfg<C>::THREADS, 1)
           }
         }
         cp_async_wait<0>();  // (only empty groups are left)
-        if (first) {         // warp without a query in this pass, or with its only one still parked
+        if (first) {         // warp without a query in this pass
           if (seq > 0) mbar_wait_park(bar_done, (seq - 1) & 1);
           if (pass == 0 && titer > 0) epilogue(prev_q0, prev_cnt, sInv + ((titer - 1) & 1) * K::TQ);
-          if (stashed) {
-            const uint32_t p0 = 2 * stash_ql, p1 = 2 * stash_ql + 1;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const uint4 hv = my_stash[2 * half], lv = my_stash[2 * half + 1];
-              const int k = g + 8 * half;
-              const uint32_t atom = sA32 + (k >> 1) * K::A_ATOM_BYTES;
-              const uint32_t j = (k & 1) * 4 + t;
-              sts128u(atom + sw128_offset(p0, j), hv.x, hv.y, hv.z, hv.w);
-              sts128u(atom + sw128_offset(p1, j), lv.x, lv.y, lv.z, lv.w);
-            }
-            stashed = false;
-          }
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -602,7 +559,7 @@ __global__ void __launch_bounds__(SCfg<C>::THREADS, 1)
 template <int C, typename IdxT>
 int launch_s(const float* q, const void* idx, int row_stride, int H, const unsigned char* x16p, const unsigned char* img,
              const float* kp, const float4* pts4, const unsigned int* amax_x_bits, const unsigned int* amax_w_bits,
-             float extent, float* out, int nq, int ns, const int* order, uint4* stash, cudaStream_t stream) {
+             float extent, float* out, int nq, int ns, const int* order, cudaStream_t stream) {
   using K = SCfg<C>;
   SPR_CHECK_ARG(H <= 96, "kpconv_forward_staged: at most 96 neighbour columns are supported (got %d)", H);
   // Tile size: the largest tq <= 64 that deals every SM the same number of tiles (as kpconv_tc.cu)
@@ -620,7 +577,7 @@ int launch_s(const float* q, const void* idx, int row_stride, int H, const unsig
     SPR_CUDA(ensure_max_dynamic_smem(reinterpret_cast<const void*>(k_kpconv_s<C, IdxT, HR_>), K::SMEM));                 \
     k_kpconv_s<C, IdxT, HR_><<<grid, K::THREADS, K::SMEM, stream>>>(q, idx_t, row_stride, H, x16p, img, kp, pts4,        \
                                                                     amax_x_bits, amax_w_bits, extent, out, nq, ns, tq,   \
-                                                                    n_tiles, order, stash);                              \
+                                                                    n_tiles, order);                                     \
   } while (0)
   if (H <= 32)
     SPR_S(1);
@@ -654,9 +611,6 @@ extern "C" int spr_kpconv_staged_supported(int c, int H) {
   return (c == 32 || c == 64 || c == 128 || c == 256) && H > 0 && H <= 96;
 }
 
-// 64 bytes per producer lane: one parked query per warp (see the query-complete section of k_kpconv_s)
-extern "C" size_t spr_kpconv_staged_scratch_bytes(void) { return (size_t)kNumSMs * SCfg<32>::WORKERS * 32 * 64; }
-
 extern "C" size_t spr_kpconv_staged_weight_image_bytes(int c) {
   switch (c) {
     case 32: return SCfg<32>::IMG_BYTES;
@@ -685,8 +639,7 @@ extern "C" int spr_kpconv_staged_prepare_weights(const float* d_w, int c, void* 
 extern "C" int spr_kpconv_forward_staged(const float* d_q, const void* d_idx, int idx_is_64, int row_stride, int H,
                                          const void* d_pts4, const void* d_x16, const void* d_amax_x, int c,
                                          const void* d_wimg, const void* d_amax_w, const float* d_kp, float extent,
-                                         float* d_out, int nq, int ns, const int32_t* d_order, void* d_scratch,
-                                         void* stream_) {
+                                         float* d_out, int nq, int ns, const int32_t* d_order, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SPR_CHECK_ARG(nq > 0 && ns > 0 && H > 0 && row_stride >= H, "kpconv_forward_staged: bad shape");
   SPR_CHECK_ARG(extent > 0.f, "kpconv_forward_staged: extent must be > 0");
@@ -697,13 +650,12 @@ extern "C" int spr_kpconv_forward_staged(const float* d_q, const void* d_idx, in
   const unsigned char* img = static_cast<const unsigned char*>(d_wimg);
   const unsigned int* ax = static_cast<const unsigned int*>(d_amax_x);
   const unsigned int* aw = static_cast<const unsigned int*>(d_amax_w);
-  uint4* stash = static_cast<uint4*>(d_scratch);  // (optional) spr_kpconv_staged_scratch_bytes()
 #define SPR_SP(CC)                                                                                                         \
   case CC:                                                                                                                 \
     return idx_is_64 ? launch_s<CC, long long>(d_q, d_idx, row_stride, H, x16p, img, d_kp, pts4, ax, aw, extent, d_out, nq, \
-                                               ns, d_order, stash, stream)                                                 \
+                                               ns, d_order, stream)                                                        \
                      : launch_s<CC, int>(d_q, d_idx, row_stride, H, x16p, img, d_kp, pts4, ax, aw, extent, d_out, nq, ns,  \
-                                         d_order, stash, stream);
+                                         d_order, stream);
   switch (c) {
     SPR_SP(32)
     SPR_SP(64)

@@ -430,10 +430,6 @@ def kpconv_forward_prepared(q_pts, neighb_inds, feats: PreparedFeatures, weights
     return out
 
 
-# SPR_KPCONV_STASH=0: no parking scratch for the generation-3 kernel (A/B runs)
-_STAGED_STASH = os.environ.get("SPR_KPCONV_STASH", "1") != "0"
-
-
 def _kpconv_forward_staged(q_pts, neighb_inds, feats: PreparedFeatures, weights, kernel_points, extent, order):
     L = _lib.lib()
     q = _f32c(q_pts, "q_pts")
@@ -446,11 +442,10 @@ def _kpconv_forward_staged(q_pts, neighb_inds, feats: PreparedFeatures, weights,
     if wi.c != feats.c:
         raise RuntimeError("kpconv_forward_prepared: channel mismatch between features and weights")
     out = torch.empty((nq, feats.c), dtype=torch.float32, device=q.device)
-    scratch = _ws(L.spr_kpconv_staged_scratch_bytes(), q.device) if _STAGED_STASH else None
     rc = L.spr_kpconv_forward_staged(q.data_ptr(), idx.data_ptr(), is64, stride, H, feats.pts4.data_ptr(),
                                      feats.x16.data_ptr(), feats.amax.data_ptr(), feats.c, wi.img.data_ptr(),
                                      wi.amax.data_ptr(), kp.data_ptr(), float(extent), out.data_ptr(), nq, ns,
-                                     _ptr(order), _ptr(scratch), _stream())
+                                     _ptr(order), _stream())
     _lib.check(rc, "spr_kpconv_forward_staged")
     return out
 
